@@ -1,0 +1,112 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference modules (authoring container only).
+
+    python -m oracle.make_golden
+
+The reference ships no golden vectors, known-answer tests or fixtures for this path (SURVEY.md 4,
+8c), so the fixtures are outputs of the reference itself: its own `T3.inference`,
+`CausalMaskedDiffWithXvec.inference`, `UpsampleConformerEncoder`, `HiFTGenerator.inference` are
+imported from /root/reference/src (oracle/ref_harness.py), loaded (strict) with the seeded synthetic
+checkpoints of oracle/weights.py, and run on CPU fp32.  The files hold inputs + reference outputs only
+(weights are regenerated from the seed).  tests/test_oracle_pinned.py then checks the CPU restatement
+in oracle/ against these files on any machine; the GPU parity tests compare the CUDA path to the
+restatement and to these same files.
+"""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_harness as R, weights as W  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def text_pair(seed, n, vocab_hi=255):
+    g = torch.Generator().manual_seed(seed)
+    text = torch.randint(1, vocab_hi, (1, n), generator=g)
+    text = torch.cat([text, text], 0)                      # CFG pair (tts.py:237-238)
+    text = F.pad(text, (1, 0), value=255)                  # SOT (tts.py:242)
+    return F.pad(text, (0, 1), value=0)                    # EOT (tts.py:243)
+
+
+def golden_t3():
+    R.install()
+    from chatterbox.models.t3.modules.cond_enc import T3Cond
+    sd = W.make_t3_weights(0)
+    t3 = R.build_t3()
+    t3.load_state_dict(sd, strict=True)
+    c3, _ = W.make_conds()
+    mk = lambda: T3Cond(speaker_emb=c3["speaker_emb"], cond_prompt_speech_tokens=c3["cond_prompt_speech_tokens"],
+                        emotion_adv=c3["emotion_adv"])
+    out = dict(weights_seed=0, conds_seed=1234)
+    cases = []
+    for (tseed, ntext, steps, rng_seed, min_p) in [(7, 24, 24, 11, 0.05), (7, 24, 24, 3, 1.0), (8, 61, 12, 5, 1.0)]:
+        text = text_pair(tseed, ntext)
+        torch.manual_seed(rng_seed)
+        toks = t3.inference(t3_cond=mk(), text_tokens=text, max_new_tokens=steps, temperature=0.8, top_p=1.0,
+                            min_p=min_p, repetition_penalty=1.2, cfg_weight=0.5)
+        # prefill logits of the reference backbone for the same inputs (teacher-forcing anchor)
+        embeds, _ = t3.prepare_input_embeds(t3_cond=mk(), text_tokens=text,
+                                            speech_tokens=6561 * torch.ones_like(text[:, :1]), cfg_weight=0.5)
+        bos = t3.speech_emb(torch.tensor([[6561]])) + t3.speech_pos_emb.get_fixed_embedding(0)
+        x = torch.cat([embeds, torch.cat([bos, bos])], dim=1)
+        with torch.inference_mode():
+            o = t3.patched_model(inputs_embeds=x, past_key_values=None, use_cache=True, output_hidden_states=True,
+                                 return_dict=True)
+        cases.append(dict(text_seed=tseed, n_text=ntext, steps=steps, rng_seed=rng_seed, min_p=min_p,
+                          text_tokens=text, tokens=toks.clone(), prefill_logits=o.logits[:, -1, :].clone(),
+                          cond_emb=t3.prepare_conditioning(mk()).clone()))
+        print("t3 case", tseed, ntext, steps, min_p, toks[0, :8].tolist())
+    out["cases"] = cases
+    torch.save(out, os.path.join(OUT, "t3_golden.pt"))
+
+
+def golden_flow_hift():
+    R.install()
+    fsd = W.make_flow_weights(0)
+    flow = R.build_flow()
+    flow.load_state_dict(fsd, strict=True)
+    hsd = W.make_hift_weights(0)
+    hift = R.build_hift()
+    hift.load_state_dict(hsd, strict=True)
+    out = dict(weights_seed=0)
+    cases = []
+    for (np_, n, tok_seed, rng_seed) in [(40, 30, 5, 21), (17, 9, 6, 22)]:
+        _, cg = W.make_conds(seed=1234, n_gen_prompt=np_)
+        tok = torch.randint(0, 6561, (1, n), generator=torch.Generator().manual_seed(tok_seed))
+        x = fsd["input_embedding.weight"][torch.cat([cg["prompt_token"], tok], 1)]
+        with torch.inference_mode():
+            h, _ = flow.encoder(x, torch.tensor([x.shape[1]]))
+            mu = flow.encoder_proj(h)
+        torch.manual_seed(rng_seed)
+        z = torch.randn(1, 80, 2 * (np_ + n))             # what flow_matching.py:216 will draw
+        torch.manual_seed(rng_seed)
+        mel, _ = flow.inference(token=tok, token_len=torch.tensor([n]), prompt_token=cg["prompt_token"],
+                                prompt_token_len=cg["prompt_token_len"], prompt_feat=cg["prompt_feat"],
+                                prompt_feat_len=None, embedding=cg["embedding"], finalize=True, n_timesteps=10)
+        # one NFE of the estimator on the CFG pair at t=t_span[1] (unit anchor)
+        est = flow.decoder.estimator
+        T = mu.shape[1]
+        with torch.inference_mode():
+            spk = flow.spk_embed_affine_layer(F.normalize(cg["embedding"], dim=1))
+            cond = torch.zeros(1, 80, T)
+            cond[:, :, :2 * np_] = cg["prompt_feat"].transpose(1, 2)
+            t = torch.tensor([0.3])
+            v = est(z, torch.ones(1, 1, T), mu.transpose(1, 2).contiguous(), t, spk, cond)
+        # HiFT on the reference mel
+        torch.manual_seed(rng_seed + 100)
+        wav, s = hift.inference(speech_feat=mel)
+        cases.append(dict(n_prompt=np_, n=n, tok_seed=tok_seed, rng_seed=rng_seed, tokens=tok, mu=mu.clone(),
+                          z=z, mel=mel.clone(), nfe_t=0.3, nfe_v=v.clone(), wav=wav.clone(), source=s.clone()))
+        print("flow case", np_, n, mel.shape, float(mel.std()), wav.shape, float(wav.std()))
+    out["cases"] = cases
+    torch.save(out, os.path.join(OUT, "s3gen_golden.pt"))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    golden_t3()
+    golden_flow_hift()
