@@ -1,0 +1,297 @@
+// C ABI of libcbx (include/cbx.h): handle lifetime, weight staging, exception -> status-code fence.
+#include "engine.h"
+#include <cstdlib>
+
+using namespace cbx;
+
+namespace cbx {
+const HostTensor& host_tensor(cbx_handle* h, const std::string& name) {
+  auto it = h->host.find(name);
+  if (it == h->host.end()) throw std::runtime_error("cbx: missing tensor '" + name + "'");
+  return it->second;
+}
+bool has_tensor(cbx_handle* h, const std::string& name) { return h->host.count(name) != 0; }
+DevVec upload_vec(cbx_handle* h, const float* p, size_t n) {
+  DevVec v; v.n = n;
+  CBX_CHECK(cudaMalloc(&v.p, n * sizeof(float)));
+  CBX_CHECK(cudaMemcpy(v.p, p, n * sizeof(float), cudaMemcpyHostToDevice));
+  h->owned.push_back(v.p);
+  return v;
+}
+DevVec upload_tensor(cbx_handle* h, const std::string& name) {
+  const HostTensor& t = host_tensor(h, name);
+  return upload_vec(h, t.data.data(), t.data.size());
+}
+}  // namespace cbx
+
+static Ctx make_ctx(cbx_handle* h, void* ws, size_t ws_bytes, cbx_stream stream, bool dry = false) {
+  Ctx c;
+  c.stream = reinterpret_cast<cudaStream_t>(stream);
+  c.ws.base = static_cast<char*>(ws); c.ws.cap = ws_bytes; c.ws.dry = dry; c.dry = dry;
+  c.gemm_impl = h->gemm_impl; c.attn_impl = h->attn_impl;
+  return c;
+}
+
+#define CBX_GUARD_BEGIN try {
+#define CBX_GUARD_END(h)                                                                   \
+  } catch (const std::exception& e) {                                                      \
+    if (h) (h)->err = e.what();                                                            \
+    const std::string _m = e.what();                                                       \
+    if (_m.find("workspace") != std::string::npos) return CBX_ERR_WORKSPACE;               \
+    if (_m.find("CUDA error") != std::string::npos) return CBX_ERR_CUDA;                   \
+    return CBX_ERR_INVALID;                                                                \
+  }                                                                                        \
+  return CBX_OK;
+
+extern "C" {
+
+int cbx_version(void) { return 1; }
+
+int cbx_create(int device, cbx_handle** out) {
+  if (!out) return CBX_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device >= n) return CBX_ERR_CUDA;   // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return CBX_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CBX_ERR_CUDA;
+  cbx_handle* h = new cbx_handle();
+  h->device = device;
+  if (prop.major != 10) { h->err = "libcbx is built for sm_100a only"; }
+  const char* e = getenv("CBX_GEMM");
+  if (e && std::string(e) == "simt") h->gemm_impl = 1;
+  e = getenv("CBX_ATTN");
+  if (e && std::string(e) == "simt") h->attn_impl = 1;
+  *out = h;
+  return prop.major == 10 ? CBX_OK : CBX_ERR_CUDA;
+}
+
+void cbx_destroy(cbx_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->owned) cudaFree(p);
+  auto fw = [](Weight& w) { free_weight(w); };
+  for (auto& l : h->t3.layers) { fw(l.qkv); fw(l.o); fw(l.gu); fw(l.down); }
+  fw(h->t3.head); fw(h->t3.spkr); fw(h->t3.pq); fw(h->t3.pk); fw(h->t3.pv); fw(h->t3.pproj);
+  delete h;   // remaining packed weights are released with the context (process lifetime objects)
+}
+
+const char* cbx_last_error(cbx_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int cbx_set_option(cbx_handle* h, const char* key, const char* value) {
+  if (!h || !key || !value) return CBX_ERR_INVALID;
+  const std::string k = key, v = value;
+  if (k == "gemm") h->gemm_impl = (v == "simt") ? 1 : 0;
+  else if (k == "attn") h->attn_impl = (v == "simt") ? 1 : 0;
+  else { h->err = "unknown option " + k; return CBX_ERR_INVALID; }
+  return CBX_OK;
+}
+
+long long cbx_launch_count(cbx_handle* h) { return h ? h->launches : 0; }
+
+int cbx_load_tensor(cbx_handle* h, const char* name, const float* host_data, int ndim, const int64_t* shape) {
+  if (!h) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  CBX_REQUIRE(name && host_data && ndim >= 0 && ndim <= 4, "bad tensor");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(host_data, host_data + n);
+  h->host[name] = std::move(t);
+  CBX_GUARD_END(h)
+}
+
+int cbx_finalize_weights(cbx_handle* h, const char* model) {
+  if (!h || !model) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  CBX_CHECK(cudaSetDevice(h->device));
+  const std::string m = model;
+  if (m == "t3") t3_finalize(h);
+  else if (m == "flow") flow_finalize(h);
+  else if (m == "hift") hift_finalize(h);
+  else throw std::runtime_error("unknown model " + m);
+  // staged host copies of this model are no longer needed
+  for (auto it = h->host.begin(); it != h->host.end();) {
+    if (it->first.compare(0, m.size() + 1, m + ".") == 0) it = h->host.erase(it); else ++it;
+  }
+  CBX_CHECK(cudaDeviceSynchronize());
+  CBX_GUARD_END(h)
+}
+
+// ---- T3 -------------------------------------------------------------------------------------------
+int cbx_t3_cond_encode(cbx_handle* h, const float* speaker_emb, const int* prompt_tokens, int n_prompt,
+                       const float* emotion_adv, int n_voices, float* cond_out, void* ws, size_t ws_bytes,
+                       cbx_stream stream) {
+  if (!h) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  t3_cond_encode(h, c, speaker_emb, prompt_tokens, n_prompt, emotion_adv, n_voices, cond_out);
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+int cbx_t3_prefill(cbx_handle* h, const cbx_t3_state* st, int n_tok, const int* tok_row, const int* tok_pos,
+                   const int* row_start, const int* row_len, int max_row_len, const float* cond, const int* row_voice,
+                   int len_cond, const int* text_flat, const int* text_start, const int* n_text, const int* row_uncond,
+                   void* ws, size_t ws_bytes, cbx_stream stream) {
+  if (!h || !st) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  t3_prefill(h, c, *st, n_tok, tok_row, tok_pos, row_start, row_len, max_row_len, cond, row_voice, len_cond, text_flat,
+             text_start, n_text, row_uncond);
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+int cbx_t3_decode(cbx_handle* h, const cbx_t3_state* st, const int* act_utt, const int* slot_row, int n_act, int n_steps,
+                  void* ws, size_t ws_bytes, cbx_stream stream) {
+  if (!h || !st) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  t3_decode(h, c, *st, act_utt, slot_row, n_act, n_steps);
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+__global__ void gather_rows_generic_kernel(const float* src, float* dst, const int* idx, int ld) {
+  const int r = blockIdx.x;
+  const float* s = src + (long)idx[r] * ld;
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) dst[(long)r * ld + i] = s[i];
+}
+int cbx_t3_compact(cbx_handle* h, const cbx_t3_state* st, const int* keep_slot, int n_keep, void* ws, size_t ws_bytes,
+                   cbx_stream stream) {
+  if (!h || !st) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  if (n_keep > 0) {
+    float* tx = c.ws.get<float>((size_t)n_keep * 1024);
+    float* tl = c.ws.get<float>((size_t)n_keep * st->ldl);
+    gather_rows_generic_kernel<<<n_keep, 256, 0, c.stream>>>(st->x, tx, keep_slot, 1024);
+    gather_rows_generic_kernel<<<n_keep, 256, 0, c.stream>>>(st->logits, tl, keep_slot, st->ldl);
+    CBX_CHECK(cudaMemcpyAsync(st->x, tx, (size_t)n_keep * 1024 * 4, cudaMemcpyDeviceToDevice, c.stream));
+    CBX_CHECK(cudaMemcpyAsync(st->logits, tl, (size_t)n_keep * st->ldl * 4, cudaMemcpyDeviceToDevice, c.stream));
+    h->launches += 2;
+  }
+  CBX_GUARD_END(h)
+}
+size_t cbx_t3_workspace_bytes(cbx_handle* h, int n_tok_prefill, int n_rows) {
+  if (!h) return 0;
+  try {
+    cbx_t3_state st; memset(&st, 0, sizeof(st));
+    st.n_rows = n_rows; st.cfg = 1; st.n_utts = (n_rows + 1) / 2; st.ldl = 8256;
+    Ctx c = make_ctx(h, nullptr, 0, nullptr, true);
+    t3_prefill(h, c, st, n_tok_prefill, nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr, 34, nullptr, nullptr,
+               nullptr, nullptr);
+    size_t a = c.ws.peak;
+    Ctx d = make_ctx(h, nullptr, 0, nullptr, true);
+    t3_decode(h, d, st, nullptr, nullptr, st.n_utts, 1);
+    size_t b = d.ws.peak + (size_t)n_rows * (1024 + 8256) * 4 + 4096;   // + compaction staging
+    Ctx e = make_ctx(h, nullptr, 0, nullptr, true);
+    t3_cond_encode(h, e, nullptr, nullptr, 512, nullptr, 1, nullptr);
+    size_t m = a > b ? a : b;
+    if (e.ws.peak > m) m = e.ws.peak;
+    return m + (1 << 20);
+  } catch (const std::exception& e) { h->err = e.what(); return 0; }
+}
+
+// ---- flow -----------------------------------------------------------------------------------------
+int cbx_flow_encode(cbx_handle* h, const int* tokens, const cbx_layout* L1, const cbx_layout* L2, const float* xvec,
+                    float* mu, float* spk, void* ws, size_t ws_bytes, cbx_stream stream) {
+  if (!h || !L1 || !L2) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  flow_encode(h, c, tokens, *L1, *L2, xvec, mu, spk);
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+int cbx_cfm_solve(cbx_handle* h, const float* mu, const float* spk, const float* cond, float* x, const cbx_layout* L2,
+                  const cbx_layout* L3, int n_steps, float cfg_rate, int meanflow, void* ws, size_t ws_bytes,
+                  cbx_stream stream) {
+  if (!h || !L2 || !L3) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  cfm_solve(h, c, mu, spk, cond, x, *L2, *L3, n_steps, cfg_rate, meanflow);
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+size_t cbx_flow_workspace_bytes(cbx_handle* h, const cbx_layout* L1, const cbx_layout* L2, const cbx_layout* L3) {
+  if (!h || !L1 || !L2 || !L3) return 0;
+  try {
+    Ctx c = make_ctx(h, nullptr, 0, nullptr, true);
+    flow_encode(h, c, nullptr, *L1, *L2, nullptr, nullptr, nullptr);
+    Ctx d = make_ctx(h, nullptr, 0, nullptr, true);
+    cfm_solve(h, d, nullptr, nullptr, nullptr, nullptr, *L2, *L3, h->flow.meanflow ? 2 : 10, 0.7f, h->flow.meanflow ? 1 : 0);
+    return (c.ws.peak > d.ws.peak ? c.ws.peak : d.ws.peak) + (1 << 20);
+  } catch (const std::exception& e) { h->err = e.what(); return 0; }
+}
+
+// ---- hift -----------------------------------------------------------------------------------------
+int cbx_hift_source(cbx_handle* h, const float* mel, const cbx_hift_geom* g, const float* phase_vec, const float* noise,
+                    unsigned long long seed, float* s_out, float* f0_out, void* ws, size_t ws_bytes, cbx_stream stream) {
+  if (!h || !g) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  hift_source_run(h, c, mel, *g, phase_vec, noise, seed, s_out, f0_out);
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+int cbx_hift_decode(cbx_handle* h, const float* mel, const float* s, const cbx_hift_geom* g, float* wav, int trim_fade,
+                    void* ws, size_t ws_bytes, cbx_stream stream) {
+  if (!h || !g) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  hift_decode_run(h, c, mel, s, *g, wav, trim_fade);
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+size_t cbx_hift_workspace_bytes(cbx_handle* h, const cbx_hift_geom* g) {
+  if (!h || !g) return 0;
+  try {
+    Ctx c = make_ctx(h, nullptr, 0, nullptr, true);
+    hift_source_run(h, c, nullptr, *g, nullptr, nullptr, 0, nullptr, nullptr);
+    Ctx d = make_ctx(h, nullptr, 0, nullptr, true);
+    hift_decode_run(h, d, nullptr, nullptr, *g, nullptr, 1);
+    return (c.ws.peak > d.ws.peak ? c.ws.peak : d.ws.peak) + (1 << 20);
+  } catch (const std::exception& e) { h->err = e.what(); return 0; }
+}
+
+// ---- diagnostics ------------------------------------------------------------------------------------
+int cbx_test_gemm(cbx_handle* h, const float* A, int lda, int M_in, int M, const float* w_host, const float* bias_host,
+                  int N, int cin, int taps, int mode, int dil, int pad, int stride, const cbx_layout* out_layout,
+                  const cbx_layout* in_layout, int act, float act_p, const float* res, int ldr, int swiglu, float* C,
+                  int ldc, cbx_stream stream) {
+  if (!h) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Weight W;
+  if (mode == 1) pack_conv_window(W, w_host, bias_host, N, cin, taps);
+  else pack_conv_taps(W, w_host, bias_host, N, cin, taps);
+  Ctx c = make_ctx(h, nullptr, 0, stream);
+  GemmDev g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.lda = lda; g.M = M; g.M_in = M_in;
+  g.a_mode = mode; g.ntaps = taps; g.ctap = (cin + 63) / 64 * 64; g.c_in = cin; g.dil = dil; g.pad = pad; g.stride = stride;
+  g.k_total = mode == 1 ? taps * cin : taps * g.ctap;
+  if (out_layout && in_layout) { g.has_seq = 1; g.seq = seqmap(*out_layout, *in_layout); }
+  g.Wp = W.w; g.Kpad = W.Kpad; g.Npad = W.Npad;
+  g.C = C; g.ldc = ldc; g.n_out = N; g.bias = W.bias; g.alpha = 1.f; g.act = act; g.act_p = act_p; g.out_scale = 1.f;
+  g.res = res; g.ldr = ldr; g.swiglu = swiglu;
+  gemm(c, g, W);
+  CBX_CHECK(cudaStreamSynchronize(c.stream));
+  free_weight(W);
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+int cbx_test_attention(cbx_handle* h, const float* Q, const float* K, const float* V, int ld, float* O, int ldo,
+                       int n_heads, const cbx_layout* L, float scale, int causal, const float* bias,
+                       long long bias_head_stride, int bias_ld, int bias_rel, int bias_center, cbx_stream stream) {
+  if (!h || !L) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, nullptr, 0, stream);
+  AttnArgs a;
+  a.Q = Q; a.K = K; a.V = V; a.ldq = a.ldk = a.ldv = ld; a.O = O; a.ldo = ldo; a.n_seq = L->n_seq; a.n_heads = n_heads;
+  a.q_start = L->start; a.q_len = L->len; a.kv_start = L->start; a.kv_len = L->len; a.max_q_len = L->max_len;
+  a.scale = scale; a.causal = causal; a.bias = bias; a.bias_head_stride = bias_head_stride; a.bias_ld = bias_ld;
+  a.bias_row0 = 0; a.bias_rel = bias_rel; a.bias_center = bias_center;
+  attention(c, a);
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+
+}  // extern "C"

@@ -1,0 +1,492 @@
+// Attention kernels of libcbx.
+//
+//  * flash_attn_kernel      head_dim 64, fp32 in/out, online softmax in fp32; Q.K^T and P.V on the legacy
+//                           tensor path (mma.sync m16n8k16 bf16) with every operand split into bf16 hi+lo
+//                           (3 MMAs per product: hi.hi + hi.lo + lo.hi) so results track the fp32 reference.
+//                           Options: causal, per-sequence kv length, additive bias incl. espnet rel-pos shift.
+//                           Used by: T3 prefill, conformer encoder, CFM estimator blocks.
+//  * attn_simt_kernel       same contract on CUDA cores (debug reference, CBX_ATTN=simt).
+//  * attn_generic_kernel    tiny generic-head-dim attention (perceiver resampler, 4 heads x 256).
+//  * paged_decode_kernel    one query token per row against the paged KV cache (HBM-bound: every K/V byte is
+//                           read exactly once, 16-byte coalesced loads, flash-decoding split over CTAs).
+//  * rope_store_kernel      llama3 RoPE on q,k (in place) + append k,v to the paged cache.
+#include "ops.h"
+
+namespace cbx {
+
+// ================================================================================================
+// flash attention (mma.sync bf16, 3-term split)
+// ================================================================================================
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat16 h0, l0, h1, l1;
+  split_bf16(x, h0, l0);
+  split_bf16(y, h1, l1);
+  hi = pack_bf16(h0, h1);
+  lo = pack_bf16(l0, l1);
+}
+
+constexpr int FA_BM = 64, FA_BN = 64, FA_LD = 72;   // smem row stride (bf16) - conflict-free fragment loads
+
+struct FlashDev {
+  const float* Q; const float* K; const float* V; float* O;
+  int ldq, ldk, ldv, ldo;
+  const int* q_start; const int* q_len; const int* kv_start; const int* kv_len;
+  float scale; int causal;
+  const float* bias; long bias_head_stride; int bias_ld; long bias_row0; int bias_center; int bias_rel;
+};
+
+__global__ void __launch_bounds__(128) flash_attn_kernel(const FlashDev p) {
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
+  const int q0 = blockIdx.x * FA_BM;
+  if (q0 >= qlen) return;
+  const long qrow0 = p.q_start[seq], krow0 = p.kv_start[seq];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  __shared__ __align__(16) __nv_bfloat16 Kh[FA_BN * FA_LD], Kl[FA_BN * FA_LD];   // [key][d]
+  __shared__ __align__(16) __nv_bfloat16 Vh[64 * FA_LD], Vl[64 * FA_LD];         // [d][key] (transposed)
+
+  // ---- Q fragments (A operand, 16 rows x 64 d per warp), hi and lo planes
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;     // local query indices of this thread's two rows
+  uint32_t qh[4][4], ql[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int d0 = ks * 16 + 2 * t;
+    float2 a = make_float2(0.f, 0.f), b = a, c = a, d = a;
+    if (r0 < qlen) {
+      const float* q = p.Q + (qrow0 + r0) * p.ldq + head * 64;
+      a = *reinterpret_cast<const float2*>(q + d0);
+      c = *reinterpret_cast<const float2*>(q + d0 + 8);
+    }
+    if (r1 < qlen) {
+      const float* q = p.Q + (qrow0 + r1) * p.ldq + head * 64;
+      b = *reinterpret_cast<const float2*>(q + d0);
+      d = *reinterpret_cast<const float2*>(q + d0 + 8);
+    }
+    split2(a.x, a.y, qh[ks][0], ql[ks][0]);
+    split2(b.x, b.y, qh[ks][1], ql[ks][1]);
+    split2(c.x, c.y, qh[ks][2], ql[ks][2]);
+    split2(d.x, d.y, qh[ks][3], ql[ks][3]);
+  }
+
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  const int coff = kvlen - qlen;   // causal offset
+  int kv_end = kvlen;
+  if (p.causal) { int last = q0 + FA_BM - 1 + coff; if (last + 1 < kv_end) kv_end = last + 1; }
+
+  for (int kb = 0; kb < kv_end; kb += FA_BN) {
+    __syncthreads();   // previous tile fully consumed
+    // ---- stage K tile [64 keys][64 d] and V tile transposed [64 d][64 keys], split to hi/lo
+    for (int i = threadIdx.x; i < 64 * 16; i += 128) {          // K: key = i/16, d4 = i%16
+      const int key = i >> 4, d4 = (i & 15) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kb + key < kvlen) x = *reinterpret_cast<const float4*>(p.K + (krow0 + kb + key) * p.ldk + head * 64 + d4);
+      uint32_t h0, l0_, h1, l1_;
+      split2(x.x, x.y, h0, l0_); split2(x.z, x.w, h1, l1_);
+      *reinterpret_cast<uint2*>(&Kh[key * FA_LD + d4]) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(&Kl[key * FA_LD + d4]) = make_uint2(l0_, l1_);
+    }
+    for (int i = threadIdx.x; i < 32 * 16; i += 128) {          // V: key pair = i/16, d4 = i%16
+      const int kp = (i >> 4) * 2, d4 = (i & 15) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+      if (kb + kp < kvlen) x = *reinterpret_cast<const float4*>(p.V + (krow0 + kb + kp) * p.ldv + head * 64 + d4);
+      if (kb + kp + 1 < kvlen) y = *reinterpret_cast<const float4*>(p.V + (krow0 + kb + kp + 1) * p.ldv + head * 64 + d4);
+      const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        uint32_t h, l;
+        split2(xs[e], ys[e], h, l);
+        *reinterpret_cast<uint32_t*>(&Vh[(d4 + e) * FA_LD + kp]) = h;
+        *reinterpret_cast<uint32_t*>(&Vl[(d4 + e) * FA_LD + kp]) = l;
+      }
+    }
+    __syncthreads();
+
+    // ---- S = Q K^T (16 x 64 per warp)
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int off = (j * 8 + g) * FA_LD + ks * 16 + 2 * t;
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&Kh[off]);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&Kh[off + 8]);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&Kl[off]);
+        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&Kl[off + 8]);
+        mma_bf16_16816(s[j], ql[ks], bh0, bh1);
+        mma_bf16_16816(s[j], qh[ks], bl0, bl1);
+        mma_bf16_16816(s[j], qh[ks], bh0, bh1);
+      }
+    }
+    // ---- bias, scale, mask, online softmax
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qi = (e < 2) ? r0 : r1;
+        const int kj = kb + j * 8 + 2 * t + (e & 1);
+        float v = s[j][e];
+        bool ok = (kj < kvlen) && (qi < qlen) && (!p.causal || kj <= qi + coff);
+        if (ok && p.bias) {
+          const long brow = (qrow0 + qi) - p.bias_row0;
+          const long bcol = p.bias_rel ? (long)(p.bias_center - qi + kj) : (long)kj;
+          v += p.bias[(long)head * p.bias_head_stride + brow * p.bias_ld + bcol];
+        }
+        v = ok ? v * p.scale : -INFINITY;
+        s[j][e] = v;
+        if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = (mn0 == -INFINITY) ? 1.f : expf(m0 - mn0);
+    const float c1 = (mn1 == -INFINITY) ? 1.f : expf(m1 - mn1);
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = (s[j][0] == -INFINITY) ? 0.f : expf(s[j][0] - mn0);
+      s[j][1] = (s[j][1] == -INFINITY) ? 0.f : expf(s[j][1] - mn0);
+      s[j][2] = (s[j][2] == -INFINITY) ? 0.f : expf(s[j][2] - mn1);
+      s[j][3] = (s[j][3] == -INFINITY) ? 0.f : expf(s[j][3] - mn1);
+      rs0 += s[j][0] + s[j][1];
+      rs1 += s[j][2] + s[j][3];
+      o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
+    }
+    l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+    m0 = mn0; m1 = mn1;
+
+    // ---- O += P V   (P from the S accumulators, V^T tile as the col-major B operand)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {         // 16 keys per step
+      uint32_t ph[4], pl[4];
+      split2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+      split2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+      split2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+      split2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd) {
+        const int off = (jd * 8 + g) * FA_LD + kk * 16 + 2 * t;
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&Vh[off]);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&Vh[off + 8]);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&Vl[off]);
+        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&Vl[off + 8]);
+        mma_bf16_16816(o[jd], pl, bh0, bh1);
+        mma_bf16_16816(o[jd], ph, bl0, bl1);
+        mma_bf16_16816(o[jd], ph, bh0, bh1);
+      }
+    }
+  }
+  // ---- finalize
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+  for (int jd = 0; jd < 8; ++jd) {
+    const int d = jd * 8 + 2 * t;
+    if (r0 < qlen)
+      *reinterpret_cast<float2*>(p.O + (qrow0 + r0) * p.ldo + head * 64 + d) = make_float2(o[jd][0] * i0, o[jd][1] * i0);
+    if (r1 < qlen)
+      *reinterpret_cast<float2*>(p.O + (qrow0 + r1) * p.ldo + head * 64 + d) = make_float2(o[jd][2] * i1, o[jd][3] * i1);
+  }
+}
+
+// SIMT reference: one warp per (seq, head, query); lanes own 2 of the 64 dims.
+__global__ void __launch_bounds__(128) attn_simt_kernel(const FlashDev p) {
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
+  const int qi = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (qi >= qlen) return;
+  const int lane = threadIdx.x & 31;
+  const long qrow0 = p.q_start[seq], krow0 = p.kv_start[seq];
+  const float2 q = *reinterpret_cast<const float2*>(p.Q + (qrow0 + qi) * p.ldq + head * 64 + 2 * lane);
+  const int coff = kvlen - qlen;
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int kj = 0; kj < kvlen; ++kj) {
+    if (p.causal && kj > qi + coff) break;
+    const float2 k = *reinterpret_cast<const float2*>(p.K + (krow0 + kj) * p.ldk + head * 64 + 2 * lane);
+    float sc = warp_sum(q.x * k.x + q.y * k.y);
+    if (p.bias) {
+      const long brow = (qrow0 + qi) - p.bias_row0;
+      const long bcol = p.bias_rel ? (long)(p.bias_center - qi + kj) : (long)kj;
+      sc += p.bias[(long)head * p.bias_head_stride + brow * p.bias_ld + bcol];
+    }
+    sc *= p.scale;
+    const float mn = fmaxf(m, sc);
+    const float c = (m == -INFINITY) ? 0.f : expf(m - mn);
+    const float e = expf(sc - mn);
+    const float2 v = *reinterpret_cast<const float2*>(p.V + (krow0 + kj) * p.ldv + head * 64 + 2 * lane);
+    o0 = o0 * c + e * v.x; o1 = o1 * c + e * v.y;
+    l = l * c + e; m = mn;
+  }
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  *reinterpret_cast<float2*>(p.O + (qrow0 + qi) * p.ldo + head * 64 + 2 * lane) = make_float2(o0 * inv, o1 * inv);
+}
+
+void attention(Ctx& ctx, const AttnArgs& a) {
+  if (ctx.dry) return;
+  FlashDev p;
+  p.Q = a.Q; p.K = a.K; p.V = a.V; p.O = a.O; p.ldq = a.ldq; p.ldk = a.ldk; p.ldv = a.ldv; p.ldo = a.ldo;
+  p.q_start = a.q_start; p.q_len = a.q_len; p.kv_start = a.kv_start; p.kv_len = a.kv_len;
+  p.scale = a.scale; p.causal = a.causal;
+  p.bias = a.bias; p.bias_head_stride = a.bias_head_stride; p.bias_ld = a.bias_ld; p.bias_row0 = a.bias_row0;
+  p.bias_center = a.bias_center; p.bias_rel = a.bias_rel;
+  ctx.launches++;
+  if (ctx.attn_impl == 1) {
+    dim3 grid((a.max_q_len + 3) / 4, a.n_heads, a.n_seq);
+    attn_simt_kernel<<<grid, 128, 0, ctx.stream>>>(p);
+  } else {
+    dim3 grid((a.max_q_len + FA_BM - 1) / FA_BM, a.n_heads, a.n_seq);
+    flash_attn_kernel<<<grid, 128, 0, ctx.stream>>>(p);
+  }
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ================================================================================================
+// tiny generic attention (any head_dim <= 256): one CTA per (query, head)
+// ================================================================================================
+__global__ void attn_generic_kernel(const float* Q, const float* K, const float* V, float* O, int n_q, int n_kv,
+                                    int head_dim, int ldq, int ldk, int ldv, int ldo, float scale) {
+  extern __shared__ float sm[];         // scores [n_kv]
+  const int qi = blockIdx.x, head = blockIdx.y;
+  const float* q = Q + (long)qi * ldq + head * head_dim;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < n_kv; j += nw) {
+    const float* k = K + (long)j * ldk + head * head_dim;
+    float acc = 0.f;
+    for (int d = lane; d < head_dim; d += 32) acc += q[d] * k[d];
+    acc = warp_sum(acc);
+    if (lane == 0) sm[j] = acc * scale;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = 0; j < n_kv; ++j) mx = fmaxf(mx, sm[j]);
+  float sum = 0.f;
+  for (int j = 0; j < n_kv; ++j) sum += expf(sm[j] - mx);
+  for (int d = threadIdx.x; d < head_dim; d += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < n_kv; ++j) acc += expf(sm[j] - mx) * V[(long)j * ldv + head * head_dim + d];
+    O[(long)qi * ldo + head * head_dim + d] = acc / sum;
+  }
+}
+void attention_generic(Ctx& ctx, const float* Q, const float* K, const float* V, float* O, int n_q, int n_kv,
+                       int n_heads, int head_dim, int ldq, int ldk, int ldv, int ldo, float scale) {
+  if (ctx.dry) return;
+  ctx.launches++;
+  attn_generic_kernel<<<dim3(n_q, n_heads), 256, n_kv * sizeof(float), ctx.stream>>>(Q, K, V, O, n_q, n_kv, head_dim,
+                                                                                    ldq, ldk, ldv, ldo, scale);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ================================================================================================
+// paged KV cache: layout [page][layer][k|v][head][token][64]
+// ================================================================================================
+template <typename T> struct KvTraits;
+template <> struct KvTraits<__nv_bfloat16> { static constexpr int LPT = 8, DPL = 8; };   // lanes per token, dims per lane
+template <> struct KvTraits<float> { static constexpr int LPT = 16, DPL = 4; };
+
+template <typename T> __device__ __forceinline__ void load_chunk(const T* p, float (&x)[KvTraits<T>::DPL]);
+template <> __device__ __forceinline__ void load_chunk<__nv_bfloat16>(const __nv_bfloat16* p, float (&x)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { x[2 * i] = __uint_as_float(w[i] << 16); x[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+}
+template <> __device__ __forceinline__ void load_chunk<float>(const float* p, float (&x)[4]) {
+  const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+  x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w;
+}
+
+struct PagedDev {
+  const float* qkv; int ldqkv;        // [slots][3*H*64] (q rotated in place by rope_store)
+  const void* pages; int n_layers, n_heads, page_tokens, layer;
+  const int* page_table; int max_pages;
+  const int* slot_row;                // compact slot -> physical row
+  const int* positions;               // [rows] index of the current token (attend to 0..pos)
+  float* out; int ldo;                // [slots][H*64]
+  float* scratch;                     // [slots][H][nsplit][66] partial (m, l, o[64])
+  int nsplit; float scale;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) paged_decode_kernel(const PagedDev p) {
+  constexpr int LPT = KvTraits<T>::LPT, DPL = KvTraits<T>::DPL, TPI = 32 / LPT;   // tokens per warp-iteration
+  const int slot = blockIdx.x, head = blockIdx.y, split = blockIdx.z;
+  const int row = p.slot_row[slot];
+  const int S = p.positions[row] + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane % LPT, grp = lane / LPT;
+  const int H = p.n_heads;
+  float q[DPL];
+  {
+    const float* qp = p.qkv + (long)slot * p.ldqkv + head * 64 + sub * DPL;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) q[i] = qp[i] * p.scale;
+  }
+  float m = -INFINITY, l = 0.f, o[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) o[i] = 0.f;
+  const long slab = (long)p.page_tokens * 64;                         // elements per (page,layer,kv,head)
+  const long page_stride = (long)p.n_layers * 2 * H * slab;
+  const T* base = reinterpret_cast<const T*>(p.pages) + ((long)p.layer * 2 * H + head) * slab;
+  const int* pt = p.page_table + (long)row * p.max_pages;
+  const int n_iter = (S + TPI - 1) / TPI;
+  const int stride = 4 * p.nsplit;
+  for (int it = split * 4 + warp; it < n_iter; it += stride) {
+    const int tok = it * TPI + grp;
+    const bool ok = tok < S;
+    float kx[DPL], vx[DPL];
+    if (ok) {
+      const int page = pt[tok / p.page_tokens];
+      const T* kp = base + (long)page * page_stride + (long)(tok % p.page_tokens) * 64 + sub * DPL;
+      load_chunk<T>(kp, kx);
+      load_chunk<T>(kp + (long)H * slab, vx);
+    } else {
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) { kx[i] = 0.f; vx[i] = 0.f; }
+    }
+    float sc = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) sc = fmaf(q[i], kx[i], sc);
+#pragma unroll
+    for (int ofs = 1; ofs < LPT; ofs <<= 1) sc += __shfl_xor_sync(0xffffffffu, sc, ofs);
+    if (ok) {
+      const float mn = fmaxf(m, sc);
+      const float c = (m == -INFINITY) ? 0.f : expf(m - mn);
+      const float e = expf(sc - mn);
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) o[i] = o[i] * c + e * vx[i];
+      l = l * c + e; m = mn;
+    }
+  }
+  // ---- merge the 4*TPI independent streams of this CTA
+  __shared__ float sm_m[4 * 32], sm_l[4 * 32], sm_o[4 * 32 * 8];
+  sm_m[threadIdx.x] = m; sm_l[threadIdx.x] = l;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) sm_o[threadIdx.x * 8 + i] = o[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int d = threadIdx.x;
+    const int osub = d / DPL, oi = d % DPL;
+    float mt = -INFINITY;
+    for (int w = 0; w < 4; ++w)
+      for (int gq = 0; gq < TPI; ++gq) mt = fmaxf(mt, sm_m[w * 32 + gq * LPT + osub]);
+    float lt = 0.f, ot = 0.f;
+    for (int w = 0; w < 4; ++w)
+      for (int gq = 0; gq < TPI; ++gq) {
+        const int th = w * 32 + gq * LPT + osub;
+        const float ms = sm_m[th];
+        if (ms == -INFINITY) continue;
+        const float c = expf(ms - mt);
+        lt += sm_l[th] * c;
+        ot += sm_o[th * 8 + oi] * c;
+      }
+    if (p.nsplit == 1) {
+      p.out[(long)slot * p.ldo + head * 64 + d] = lt > 0.f ? ot / lt : 0.f;
+    } else {
+      float* sp = p.scratch + (((long)slot * H + head) * p.nsplit + split) * 66;
+      sp[2 + d] = ot;
+      if (d == 0) { sp[0] = mt; sp[1] = lt; }
+    }
+  }
+}
+
+__global__ void paged_combine_kernel(const float* scratch, float* out, int ldo, int H, int nsplit) {
+  const int slot = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
+  const float* sp = scratch + ((long)slot * H + head) * nsplit * 66;
+  float mt = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) mt = fmaxf(mt, sp[s * 66]);
+  float lt = 0.f, ot = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float ms = sp[s * 66];
+    if (ms == -INFINITY) continue;
+    const float c = expf(ms - mt);
+    lt += sp[s * 66 + 1] * c;
+    ot += sp[s * 66 + 2 + d] * c;
+  }
+  out[(long)slot * ldo + head * 64 + d] = lt > 0.f ? ot / lt : 0.f;
+}
+
+void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* slot_row,
+                            int n_slots, const int* positions, float* out, int ldo, float* scratch, int nsplit) {
+  if (ctx.dry) return;
+  PagedDev p;
+  p.qkv = qkv; p.ldqkv = ldqkv; p.pages = kv.pages; p.n_layers = kv.n_layers; p.n_heads = kv.n_heads;
+  p.page_tokens = kv.page_tokens; p.layer = layer; p.page_table = kv.page_table; p.max_pages = kv.max_pages_per_row;
+  p.slot_row = slot_row; p.positions = positions; p.out = out; p.ldo = ldo; p.scratch = scratch; p.nsplit = nsplit;
+  p.scale = 0.125f;
+  dim3 grid(n_slots, kv.n_heads, nsplit);
+  ctx.launches++;
+  if (kv.kv_fp32) paged_decode_kernel<float><<<grid, 128, 0, ctx.stream>>>(p);
+  else paged_decode_kernel<__nv_bfloat16><<<grid, 128, 0, ctx.stream>>>(p);
+  if (nsplit > 1) {
+    ctx.launches++;
+    paged_combine_kernel<<<dim3(n_slots, kv.n_heads), 64, 0, ctx.stream>>>(scratch, out, ldo, kv.n_heads, nsplit);
+  }
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ---- RoPE (rotate_half convention) on q,k in place + append k,v to the paged cache -------------------
+// token i of the launch: qkv row i, physical cache row tok_row[i], position tok_pos[i]
+template <typename T>
+__global__ void __launch_bounds__(256) rope_store_kernel(float* qkv, int ldqkv, void* pages, int n_layers, int H,
+                                                         int page_tokens, int layer, const int* page_table,
+                                                         int max_pages, const int* tok_row, const int* tok_pos,
+                                                         int pos_is_per_row, const float* cos_t, const float* sin_t) {
+  const int i = blockIdx.x;
+  const int row = tok_row[i];
+  const int pos = pos_is_per_row ? tok_pos[row] : tok_pos[i];
+  float* base = qkv + (long)i * ldqkv;
+  const long slab = (long)page_tokens * 64;
+  const long page_stride = (long)n_layers * 2 * H * slab;
+  const int page = page_table[(long)row * max_pages + pos / page_tokens];
+  T* kbase = reinterpret_cast<T*>(pages) + (long)page * page_stride + ((long)layer * 2 * H) * slab +
+             (long)(pos % page_tokens) * 64;
+  for (int idx = threadIdx.x; idx < H * 32; idx += blockDim.x) {
+    const int head = idx >> 5, j = idx & 31;
+    const float c = cos_t[(long)pos * 32 + j], s = sin_t[(long)pos * 32 + j];
+    float* q = base + head * 64;
+    float* k = base + H * 64 + head * 64;
+    const float* v = base + 2 * H * 64 + head * 64;
+    const float q1 = q[j], q2 = q[j + 32];
+    q[j] = q1 * c - q2 * s; q[j + 32] = q2 * c + q1 * s;
+    const float k1 = k[j], k2 = k[j + 32];
+    const float kr1 = k1 * c - k2 * s, kr2 = k2 * c + k1 * s;
+    k[j] = kr1; k[j + 32] = kr2;
+    T* kd = kbase + (long)head * slab;
+    T* vd = kd + (long)H * slab;
+    kd[j] = (T)kr1; kd[j + 32] = (T)kr2;
+    vd[j] = (T)v[j]; vd[j + 32] = (T)v[j + 32];
+  }
+}
+
+void rope_and_store_kv(Ctx& ctx, float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* tok_row,
+                       const int* tok_pos, int pos_is_per_row, int n_tok, const float* cos_t, const float* sin_t) {
+  if (ctx.dry || n_tok == 0) return;
+  ctx.launches++;
+  if (kv.kv_fp32)
+    rope_store_kernel<float><<<n_tok, 256, 0, ctx.stream>>>(qkv, ldqkv, kv.pages, kv.n_layers, kv.n_heads, kv.page_tokens,
+                                                           layer, kv.page_table, kv.max_pages_per_row, tok_row, tok_pos,
+                                                           pos_is_per_row, cos_t, sin_t);
+  else
+    rope_store_kernel<__nv_bfloat16><<<n_tok, 256, 0, ctx.stream>>>(qkv, ldqkv, kv.pages, kv.n_layers, kv.n_heads,
+                                                                   kv.page_tokens, layer, kv.page_table,
+                                                                   kv.max_pages_per_row, tok_row, tok_pos,
+                                                                   pos_is_per_row, cos_t, sin_t);
+  CBX_CHECK(cudaGetLastError());
+}
+
+}  // namespace cbx

@@ -1,0 +1,668 @@
+// Row-wise norms, elementwise kernels, gathers and the T3 sampler of libcbx (all fp32, HBM-bound).
+#include "ops.h"
+#include "kernels.h"
+
+namespace cbx {
+
+// ------------------------------------------------------------------------------------------------
+// block reduce helpers (blockDim.x <= 1024)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (warp == 0) { r = warp_sum(r); if (lane == 0) sh[0] = r; }
+  __syncthreads();
+  r = sh[0];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : -INFINITY;
+  if (warp == 0) { r = warp_max(r); if (lane == 0) sh[0] = r; }
+  __syncthreads();
+  r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm (modeling_llama.py LlamaRMSNorm: x * rsqrt(mean(x^2)+eps) * w), one CTA per row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* x, int ldx, const float* w, float* y, int ldy, int dim,
+                                                      float eps, const int* row_idx) {
+  __shared__ float sh[32];
+  const int r = blockIdx.x;
+  const float* xr = x + (long)(row_idx ? row_idx[r] : r) * ldx;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) { float v = xr[i]; ss += v * v; }
+  ss = block_sum(ss, sh);
+  const float inv = rsqrtf(ss / dim + eps);
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) y[(long)r * ldy + i] = w[i] * (xr[i] * inv);
+}
+void rmsnorm(Ctx& ctx, const float* x, int ldx, const float* w, float* y, int ldy, int rows, int dim, float eps,
+             const int* row_idx) {
+  if (ctx.dry || rows == 0) return;
+  ctx.launches++;
+  rmsnorm_kernel<<<rows, 256, 0, ctx.stream>>>(x, ldx, w, y, ldy, dim, eps, row_idx);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over channels (+ activation, + per-sequence vector add, + scale), one warp per row.
+// y = (act(LN(x)) * valid + seq_add[seq]) * out_scale ; padding rows of the packed layout are zeroed.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx, const float* w, const float* b, float* y,
+                                                        int ldy, int rows, int dim, float eps, int act, float out_scale,
+                                                        const float* seq_add, int seq_add_ld, int has_seq, SeqMap seq) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  int s = 0; bool valid = true;
+  if (has_seq) {
+    s = seq.tile_seq[r / kTileM];
+    valid = (s >= 0) && (r - seq.out_start[s] < seq.out_len[s]);
+  }
+  float* yr = y + (long)r * ldy;
+  if (!valid) { for (int i = lane; i < dim; i += 32) yr[i] = 0.f; return; }
+  const float* xr = x + (long)r * ldx;
+  float sum = 0.f;
+  for (int i = lane; i < dim; i += 32) sum += xr[i];
+  const float mean = warp_sum(sum) / dim;
+  float var = 0.f;
+  for (int i = lane; i < dim; i += 32) { float d = xr[i] - mean; var += d * d; }
+  const float inv = rsqrtf(warp_sum(var) / dim + eps);
+  for (int i = lane; i < dim; i += 32) {
+    float v = (xr[i] - mean) * inv * w[i] + b[i];
+    v = act_apply(act, v, 0.f);
+    if (seq_add) v += seq_add[(long)s * seq_add_ld + i];
+    yr[i] = v * out_scale;
+  }
+}
+void layernorm(Ctx& ctx, const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int dim,
+               float eps, int act, float out_scale, const float* seq_add, int seq_add_ld, const SeqMap* seq) {
+  if (ctx.dry || rows == 0) return;
+  ctx.launches++;
+  SeqMap sm; if (seq) sm = *seq;
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, ctx.stream>>>(x, ldx, w, b, y, ldy, rows, dim, eps, act, out_scale, seq_add,
+                                                          seq_add_ld, seq ? 1 : 0, sm);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise
+// ------------------------------------------------------------------------------------------------
+__global__ void ew_act_kernel(const float* x, int ldx, float* y, int ldy, long rows, int cols, int act, float p,
+                              const float* vec) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long r = i / cols; const int c = (int)(i - r * cols);
+  y[r * ldy + c] = act_apply(act, x[r * ldx + c], vec ? vec[c] : p);
+}
+void ew_act(Ctx& ctx, const float* x, int ldx, float* y, int ldy, long rows, int cols, int act, float p, const float* vec) {
+  if (ctx.dry || rows == 0) return;
+  ctx.launches++;
+  ew_act_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, ctx.stream>>>(x, ldx, y, ldy, rows, cols, act, p, vec);
+  CBX_CHECK(cudaGetLastError());
+}
+__global__ void copy2d_kernel(const float* src, int lds, float* dst, int ldd, long rows, int cols) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long r = i / cols; const int c = (int)(i - r * cols);
+  dst[r * ldd + c] = src[r * lds + c];
+}
+void copy2d(Ctx& ctx, const float* src, int lds, float* dst, int ldd, long rows, int cols) {
+  if (ctx.dry || rows == 0) return;
+  ctx.launches++;
+  copy2d_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, ctx.stream>>>(src, lds, dst, ldd, rows, cols);
+  CBX_CHECK(cudaGetLastError());
+}
+__global__ void fill_kernel(float* p, long n, float v) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+void fill(Ctx& ctx, float* p, long n, float v) {
+  if (ctx.dry || n == 0) return;
+  ctx.launches++;
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx.stream>>>(p, n, v);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// out[r] = table[ids[r]] (+ add_table[add_ids ? add_ids[r] : r]) ; one CTA per row
+__global__ void gather_rows_kernel(const float* table, int ld, const int* ids, float* out, int ldo, int dim,
+                                   const float* add_table, int add_ld, const int* add_ids, int id_limit) {
+  const int r = blockIdx.x;
+  int id = ids[r];
+  if (id < 0 || id >= id_limit) id = 0;
+  const float* t = table + (long)id * ld;
+  const float* a = add_table ? add_table + (long)(add_ids ? add_ids[r] : r) * add_ld : nullptr;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) out[(long)r * ldo + i] = t[i] + (a ? a[i] : 0.f);
+}
+void gather_rows(Ctx& ctx, const float* table, int ld, const int* ids, float* out, int ldo, int rows, int dim,
+                 const float* add_table, int add_ld, const int* add_ids, int id_limit) {
+  if (ctx.dry || rows == 0) return;
+  ctx.launches++;
+  gather_rows_kernel<<<rows, 128, 0, ctx.stream>>>(table, ld, ids, out, ldo, dim, add_table, add_ld, add_ids, id_limit);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// fp32 [N][K] (ld) -> padded bf16 hi / lo planes [Npad][Kpad] (activation-derived "weights", e.g. rel-pos P)
+__global__ void pack_hilo_kernel(const float* src, int ld, int N, int K, __nv_bfloat16* hi, __nv_bfloat16* lo, int Npad,
+                                 int Kpad) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)Npad * Kpad) return;
+  const int n = (int)(i / Kpad), k = (int)(i - (long)n * Kpad);
+  float v = (n < N && k < K) ? src[(long)n * ld + k] : 0.f;
+  __nv_bfloat16 h, l;
+  split_bf16(v, h, l);
+  hi[i] = h; lo[i] = l;
+}
+void pack_hilo(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat16* hi, __nv_bfloat16* lo, int Npad, int Kpad) {
+  if (ctx.dry) return;
+  ctx.launches++;
+  pack_hilo_kernel<<<(unsigned)(((long)Npad * Kpad + 255) / 256), 256, 0, ctx.stream>>>(src, ld, N, K, hi, lo, Npad, Kpad);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ================================================================================================
+// T3: embedding assembly for the prefill
+// token i: row = tok_row[i], pos = tok_pos[i];  [cond(34) | text(n_text) | BOS | BOS]
+// ================================================================================================
+__global__ void t3_embed_kernel(float* out, int n_tok, const int* tok_row, const int* tok_pos, const float* cond,
+                                const int* row_voice, int len_cond, const int* text_flat, const int* text_start,
+                                const int* n_text, const int* row_uncond, const float* text_emb, int text_vocab,
+                                const float* text_pos, const float* speech_emb, const float* speech_pos, int bos_id) {
+  const int i = blockIdx.x;
+  const int row = tok_row[i], pos = tok_pos[i];
+  float* o = out + (long)i * 1024;
+  const int nt = n_text[row];
+  if (pos < len_cond) {
+    const float* c = cond + ((long)row_voice[row] * len_cond + pos) * 1024;
+    for (int d = threadIdx.x; d < 1024; d += blockDim.x) o[d] = c[d];
+  } else if (pos < len_cond + nt) {
+    const int j = pos - len_cond;
+    int id = text_flat[text_start[row] + j];
+    if (id < 0 || id >= text_vocab) id = 0;
+    const float* e = text_emb + (long)id * 1024;
+    const float* pe = text_pos + (long)j * 1024;
+    const bool unc = row_uncond[row] != 0;
+    for (int d = threadIdx.x; d < 1024; d += blockDim.x) o[d] = (unc ? 0.f : e[d]) + pe[d];
+  } else {
+    const float* e = speech_emb + (long)bos_id * 1024;
+    for (int d = threadIdx.x; d < 1024; d += blockDim.x) o[d] = e[d] + speech_pos[d];
+  }
+}
+void t3_embed(Ctx& ctx, float* out, int n_tok, const int* tok_row, const int* tok_pos, const float* cond,
+              const int* row_voice, int len_cond, const int* text_flat, const int* text_start, const int* n_text,
+              const int* row_uncond, const float* text_emb, int text_vocab, const float* text_pos,
+              const float* speech_emb, const float* speech_pos, int bos_id) {
+  if (ctx.dry || n_tok == 0) return;
+  ctx.launches++;
+  t3_embed_kernel<<<n_tok, 256, 0, ctx.stream>>>(out, n_tok, tok_row, tok_pos, cond, row_voice, len_cond, text_flat,
+                                                text_start, n_text, row_uncond, text_emb, text_vocab, text_pos,
+                                                speech_emb, speech_pos, bos_id);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ================================================================================================
+// T3 sampler: CFG combine -> repetition penalty -> temperature -> min-p -> top-p -> softmax ->
+// multinomial(1) == argmax(p / q), q ~ Exp(1)   (reference t3.py:339-368; transformers logits processors)
+// one CTA (1024 threads) per active utterance; also emits the next input embedding for its slots.
+// ================================================================================================
+__device__ __forceinline__ uint32_t philox_mix(uint64_t seed, uint32_t a, uint32_t b, uint32_t c) {
+  // counter-based hash (splitmix-style); statistical quality is ample for Exp(1) sampling noise
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * ((uint64_t)a + 1) + 0xBF58476D1CE4E5B9ull * ((uint64_t)b + 1) +
+               0x94D049BB133111EBull * ((uint64_t)c + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+
+constexpr int SV = 8194;        // speech vocab
+constexpr int SV_PAD = 16384;   // bitonic sort size
+
+__global__ void __launch_bounds__(1024) t3_sample_kernel(T3SampleDev p) {
+  extern __shared__ float smf[];
+  float* lg = smf;                              // [SV] logits -> probabilities
+  float* sh = smf + SV;                         // [64] reduction scratch
+  float* skey = sh + 64;                        // [SV_PAD] sort keys (top-p only)
+  int* sidx = reinterpret_cast<int*>(skey + SV_PAD);   // [SV_PAD]
+  const int j = blockIdx.x;
+  const int utt = p.act_utt[j];
+  if (p.done[utt]) return;
+  const int rows_per = p.cfg ? 2 : 1;
+  const float* lc = p.logits + (long)(j * rows_per) * p.ldl;
+  const float* lu = p.cfg ? lc + p.ldl : nullptr;
+  const int step = p.n_gen[utt];
+  unsigned char* seen = p.seen + (long)utt * SV;
+  const float w = p.cfg_weight, rp = p.rep_penalty, invT = 1.0f / p.temperature;
+  // 1-3: CFG combine, repetition penalty (history incl. BOS), temperature
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < SV; v += blockDim.x) {
+    float l = lc[v];
+    if (lu) l = l + w * (l - lu[v]);
+    if (seen[v]) l = (l < 0.f) ? l * rp : l / rp;
+    if (p.temperature != 1.0f) l = l / p.temperature;
+    lg[v] = l;
+    mx = fmaxf(mx, l);
+  }
+  (void)invT;
+  mx = block_max(mx, sh);
+  // 4: min-p: drop softmax(l) < min_p * max prob (max prob = 1/Z); keep >= 1 token (the max itself)
+  float z = 0.f;
+  for (int v = threadIdx.x; v < SV; v += blockDim.x) z += expf(lg[v] - mx);
+  z = block_sum(z, sh);
+  const float pmax = 1.0f / z;
+  for (int v = threadIdx.x; v < SV; v += blockDim.x) {
+    const float pr = expf(lg[v] - mx) / z;
+    if (pr < p.min_p * pmax && lg[v] < mx) lg[v] = -INFINITY;
+  }
+  __syncthreads();
+  // 5: top-p (ascending sort; remove while cumulative prob <= 1 - top_p; keep the last one)
+  if (p.top_p < 1.0f) {
+    float z2 = 0.f;
+    for (int v = threadIdx.x; v < SV; v += blockDim.x) z2 += (lg[v] == -INFINITY) ? 0.f : expf(lg[v] - mx);
+    z2 = block_sum(z2, sh);
+    for (int v = threadIdx.x; v < SV_PAD; v += blockDim.x) { skey[v] = (v < SV) ? lg[v] : INFINITY; sidx[v] = v; }
+    __syncthreads();
+    for (int k = 2; k <= SV_PAD; k <<= 1)
+      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (int i = threadIdx.x; i < SV_PAD; i += blockDim.x) {
+          const int ixj = i ^ jj;
+          if (ixj > i) {
+            const bool up = ((i & k) == 0);
+            const float a = skey[i], b = skey[ixj];
+            const bool sw = up ? (a > b || (a == b && sidx[i] > sidx[ixj])) : (a < b || (a == b && sidx[i] < sidx[ixj]));
+            if (sw) { skey[i] = b; skey[ixj] = a; const int t = sidx[i]; sidx[i] = sidx[ixj]; sidx[ixj] = t; }
+          }
+        }
+        __syncthreads();
+      }
+    // sequential fp64 cumulative sum over the ascending order (torch CPU cumsum accumulates float in fp64)
+    if (threadIdx.x == 0) {
+      double cum = 0.0;
+      const float thr = 1.0f - p.top_p;
+      for (int i = 0; i < SV - 1; ++i) {          // never remove the last (largest) one
+        const float pr = (skey[i] == -INFINITY) ? 0.f : expf(skey[i] - mx) / z2;
+        cum += (double)pr;
+        if ((float)cum <= thr) lg[sidx[i]] = -INFINITY; else break;
+      }
+    }
+    __syncthreads();
+  }
+  // 6: softmax + sample
+  float z3 = 0.f;
+  for (int v = threadIdx.x; v < SV; v += blockDim.x) z3 += (lg[v] == -INFINITY) ? 0.f : expf(lg[v] - mx);
+  z3 = block_sum(z3, sh);
+  float best = -1.f; int besti = SV;
+  for (int v = threadIdx.x; v < SV; v += blockDim.x) {
+    const float pr = (lg[v] == -INFINITY) ? 0.f : expf(lg[v] - mx) / z3;
+    float q;
+    if (p.q_noise) q = p.q_noise[((long)step * p.n_utts + utt) * SV + v];
+    else {
+      const uint32_t u = philox_mix(p.seed, (uint32_t)utt, (uint32_t)step, (uint32_t)v);
+      q = -logf(((float)(u >> 8) + 0.5f) * (1.0f / 16777216.0f));
+    }
+    const float sc = pr / q;
+    if (sc > best || (sc == best && v < besti)) { best = sc; besti = v; }
+  }
+  // block argmax (first index wins ties, like torch.argmax)
+  __shared__ float bv[32]; __shared__ int bi[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = besti; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = bv[threadIdx.x]; besti = bi[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    if (threadIdx.x == 0) bi[0] = besti;
+  }
+  __syncthreads();
+  const int tok = bi[0];
+  // 7: bookkeeping + next embedding (speech_emb[tok] + speech_pos[step+1], both CFG rows)
+  const bool finished = (tok == p.eos_id) || (step + 1 >= p.max_new[utt]);
+  if (threadIdx.x == 0) {
+    p.tokens[(long)utt * p.max_tokens + step] = tok;
+    p.n_gen[utt] = step + 1;
+    seen[tok] = 1;
+    if (finished) p.done[utt] = 1;
+    for (int r = 0; r < rows_per; ++r) {
+      const int row = utt * rows_per + r;
+      p.positions[row] = p.base_pos[row] + step;
+    }
+  }
+  const float* e = p.speech_emb + (long)tok * 1024;
+  const float* pe = p.speech_pos + (long)(step + 1) * 1024;
+  for (int d = threadIdx.x; d < 1024; d += blockDim.x) {
+    const float v = e[d] + pe[d];
+    for (int r = 0; r < rows_per; ++r) p.x[((long)(j * rows_per + r)) * 1024 + d] = v;
+  }
+}
+void t3_sample(Ctx& ctx, const T3SampleDev& p, int n_act) {
+  if (ctx.dry || n_act == 0) return;
+  static bool attr = false;
+  const int smem = (SV + 64 + SV_PAD) * 4 + SV_PAD * 4;
+  if (!attr) { CBX_CHECK(cudaFuncSetAttribute(t3_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+  ctx.launches++;
+  t3_sample_kernel<<<n_act, 1024, smem, ctx.stream>>>(p);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ================================================================================================
+// conformer encoder helpers
+// ================================================================================================
+// q_u = q + pos_bias_u, q_v = q + pos_bias_v  (transformer/attention.py:303-306); q lives in qkv[:, 0:512]
+__global__ void add_pos_bias_kernel(const float* qkv, int ld, const float* u, const float* v, float* qu, float* qv,
+                                    long rows) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 512) return;
+  const long r = i >> 9; const int c = (int)(i & 511);
+  const float q = qkv[r * ld + c];
+  qu[r * 512 + c] = q + u[c];
+  qv[r * 512 + c] = q + v[c];
+}
+void add_pos_bias(Ctx& ctx, const float* qkv, int ld, const float* u, const float* v, float* qu, float* qv, long rows) {
+  if (ctx.dry || rows == 0) return;
+  ctx.launches++;
+  add_pos_bias_kernel<<<(unsigned)((rows * 512 + 255) / 256), 256, 0, ctx.stream>>>(qkv, ld, u, v, qu, qv, rows);
+  CBX_CHECK(cudaGetLastError());
+}
+// espnet relative positional table for length T: row p (0..2T-2) <-> relative position (T-1-p)
+// (transformer/embedding.py:229-258): even cols sin(pos*div), odd cols cos(pos*div)
+__global__ void relpos_table_kernel(float* pe, int T, int d_model) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)(2 * T - 1) * d_model) return;
+  const int prow = (int)(i / d_model), c = (int)(i - (long)prow * d_model);
+  const float rel = (float)(T - 1 - prow);
+  const float div = expf((float)(c & ~1) * -(logf(10000.0f) / (float)d_model));
+  const float a = rel * div;
+  pe[i] = (c & 1) ? cosf(a) : sinf(a);
+}
+void relpos_table(Ctx& ctx, float* pe, int T, int d_model) {
+  if (ctx.dry) return;
+  ctx.launches++;
+  relpos_table_kernel<<<(unsigned)(((long)(2 * T - 1) * d_model + 255) / 256), 256, 0, ctx.stream>>>(pe, T, d_model);
+  CBX_CHECK(cudaGetLastError());
+}
+// nearest x2 upsample between two packed layouts: out row (start2[s] + t) = in row (start1[s] + t/2)
+__global__ void upsample2_kernel(const float* x, float* y, int C, const int* tile_seq2, const int* start2,
+                                 const int* len2, const int* start1, long rows2) {
+  const long r = blockIdx.x;
+  const int s = tile_seq2[r / kTileM];
+  float* yr = y + r * C;
+  bool valid = s >= 0;
+  int t = 0;
+  if (valid) { t = (int)(r - start2[s]); valid = t < len2[s]; }
+  if (!valid) { for (int c = threadIdx.x; c < C; c += blockDim.x) yr[c] = 0.f; return; }
+  const float* xr = x + ((long)start1[s] + (t >> 1)) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) yr[c] = xr[c];
+}
+void upsample2(Ctx& ctx, const float* x, float* y, int C, const int* tile_seq2, const int* start2, const int* len2,
+               const int* start1, long rows2) {
+  if (ctx.dry || rows2 == 0) return;
+  ctx.launches++;
+  upsample2_kernel<<<(unsigned)rows2, 128, 0, ctx.stream>>>(x, y, C, tile_seq2, start2, len2, start1, rows2);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ================================================================================================
+// CFM solver helpers
+// ================================================================================================
+// sinusoidal embedding (matcha/decoder.py:20-29): emb[k] = scale*t*exp(-k*ln(1e4)/(half-1)); out=[sin | cos]
+__global__ void time_sinusoid_kernel(const float* t, float* out, int n, int dim, float scale) {
+  const int i = blockIdx.x, half = dim / 2;
+  for (int k = threadIdx.x; k < half; k += blockDim.x) {
+    const float f = expf((float)k * -(logf(10000.0f) / (float)(half - 1)));
+    const float a = scale * t[i] * f;
+    out[(long)i * dim + k] = sinf(a);
+    out[(long)i * dim + half + k] = cosf(a);
+  }
+}
+void time_sinusoid(Ctx& ctx, const float* t, float* out, int n, int dim, float scale) {
+  if (ctx.dry || n == 0) return;
+  ctx.launches++;
+  time_sinusoid_kernel<<<n, 160, 0, ctx.stream>>>(t, out, n, dim, scale);
+  CBX_CHECK(cudaGetLastError());
+}
+// xin[row] = [x(80) | mu(80) | spk(80) | cond(80)] for the conditional half, [x | 0 | 0 | 0] for the uncond half.
+// layout3 has 2B sequences: s < B conditional, s >= B unconditional copy of sequence s-B (layout2 rows).
+__global__ void cfm_assemble_kernel(float* xin, const float* x, const float* mu, const float* spk, const float* cond,
+                                    const int* tile_seq3, const int* start3, const int* len3, const int* start2, int B,
+                                    int write_static) {
+  const long r = blockIdx.x;
+  const int s = tile_seq3[r / kTileM];
+  float* o = xin + r * 320;
+  bool valid = s >= 0; int t = 0;
+  if (valid) { t = (int)(r - start3[s]); valid = t < len3[s]; }
+  if (!valid) { for (int c = threadIdx.x; c < 320; c += blockDim.x) o[c] = 0.f; return; }
+  const int sb = s < B ? s : s - B;
+  const long r2 = (long)start2[sb] + t;
+  for (int c = threadIdx.x; c < 80; c += blockDim.x) o[c] = x[r2 * 80 + c];
+  if (write_static) {
+    for (int c = threadIdx.x; c < 80; c += blockDim.x) {
+      o[80 + c] = s < B ? mu[r2 * 80 + c] : 0.f;
+      o[160 + c] = s < B ? spk[(long)sb * 80 + c] : 0.f;
+      o[240 + c] = s < B ? cond[r2 * 80 + c] : 0.f;
+    }
+  }
+}
+void cfm_assemble(Ctx& ctx, float* xin, const float* x, const float* mu, const float* spk, const float* cond,
+                  const int* tile_seq3, const int* start3, const int* len3, const int* start2, int B, long rows3,
+                  int write_static) {
+  if (ctx.dry || rows3 == 0) return;
+  ctx.launches++;
+  cfm_assemble_kernel<<<(unsigned)rows3, 96, 0, ctx.stream>>>(xin, x, mu, spk, cond, tile_seq3, start3, len3, start2, B,
+                                                            write_static);
+  CBX_CHECK(cudaGetLastError());
+}
+// x += dt * ((1+w) v_c - w v_u)   (flow_matching.py:138-141);  meanflow/no-CFG: x += dt * v_c
+__global__ void cfm_euler_kernel(float* x, const float* v, const int* tile_seq2, const int* start2, const int* len2,
+                                 const int* start3, int B, float dt, float w, int cfg, long rows2) {
+  const long r = blockIdx.x;
+  const int s = tile_seq2[r / kTileM];
+  if (s < 0) return;
+  const int t = (int)(r - start2[s]);
+  if (t >= len2[s]) return;
+  const long rc = (long)start3[s] + t, ru = cfg ? (long)start3[s + B] + t : 0;
+  for (int c = threadIdx.x; c < 80; c += blockDim.x) {
+    const float vc = v[rc * 80 + c];
+    float d = vc;
+    if (cfg) d = (1.0f + w) * vc - w * v[ru * 80 + c];
+    x[r * 80 + c] = x[r * 80 + c] + dt * d;
+  }
+}
+void cfm_euler(Ctx& ctx, float* x, const float* v, const int* tile_seq2, const int* start2, const int* len2,
+               const int* start3, int B, float dt, float w, int cfg, long rows2) {
+  if (ctx.dry || rows2 == 0) return;
+  ctx.launches++;
+  cfm_euler_kernel<<<(unsigned)rows2, 96, 0, ctx.stream>>>(x, v, tile_seq2, start2, len2, start3, B, dt, w, cfg, rows2);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ================================================================================================
+// HiFT helpers
+// ================================================================================================
+// harmonic-plus-noise source (hifigan.py SineGen.forward :200-231 + SourceModuleHnNSF :267-283)
+// Phase: torch.cumsum on CPU accumulates float32 sequentially in fp64 and rounds every output to fp32
+// (ATen cpu_cum_base_kernel, acc_type<float> = double); the '% 1' comes after.  hift_phase_scan_kernel replays that
+// scan exactly: one thread per (sequence, harmonic) walks all 480*T samples.
+__global__ void hift_phase_scan_kernel(const float* f0, float* cumf, const int* startT, const int* lenT,
+                                       const long* startS, int n_seq) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_seq * 9) return;
+  const int s = id / 9, h = id % 9;
+  const long L = (long)lenT[s] * 480;
+  float* out = cumf + startS[s] * 9 + (long)h * L;
+  double c = 0.0;
+  for (int tau = 0; tau < lenT[s]; ++tau) {
+    const float inc = f0[(long)startT[s] + tau] * (float)(h + 1) / 24000.0f;   // F_mat value (fp32)
+    const double d = (double)inc;
+    float* o = out + (long)tau * 480;
+    for (int k = 0; k < 480; ++k) { c += d; o[k] = (float)c; }
+  }
+}
+__global__ void __launch_bounds__(480) hift_source_kernel(const float* f0, const float* cumf, const float* phase_vec,
+                                                          const float* noise, const float* lin_w, float lin_b,
+                                                          float* s_out, const int* startT, const int* lenT,
+                                                          const long* startS, int n_seq, unsigned long long seed) {
+  const int s = blockIdx.y, tau = blockIdx.x;
+  if (tau >= lenT[s]) return;
+  const int o = threadIdx.x;
+  const float f = f0[(long)startT[s] + tau];
+  const long L = (long)lenT[s] * 480;
+  const long n = (long)tau * 480 + o;
+  const float uv = f > 10.0f ? 1.0f : 0.0f;
+  const float namp = uv * 0.003f + (1.0f - uv) * 0.1f / 3.0f;
+  float acc = lin_b;
+#pragma unroll
+  for (int h = 0; h < 9; ++h) {
+    const float cf = cumf[startS[s] * 9 + (long)h * L + n];
+    const float frac = cf - floorf(cf);                                     // torch '% 1' on non-negative values
+    const float theta = 6.283185307179586f * frac;
+    const float ph = phase_vec ? phase_vec[s * 9 + h] : 0.f;
+    float sw = 0.1f * sinf(theta + ph);
+    float nz;
+    if (noise) nz = noise[startS[s] * 9 + (long)h * L + n];
+    else {
+      const uint32_t u1 = philox_mix(seed, (uint32_t)s, (uint32_t)h, (uint32_t)(2 * n));
+      const uint32_t u2 = philox_mix(seed, (uint32_t)s, (uint32_t)h, (uint32_t)(2 * n + 1));
+      const float a = ((float)(u1 >> 8) + 0.5f) * (1.0f / 16777216.0f), b = ((float)(u2 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      nz = sqrtf(-2.0f * logf(a)) * cosf(6.283185307179586f * b);
+    }
+    sw = sw * uv + namp * nz;
+    acc += sw * lin_w[h];
+  }
+  s_out[startS[s] + n] = tanhf(acc);
+}
+void hift_source(Ctx& ctx, const float* f0, float* cumf, const float* phase_vec, const float* noise, const float* lin_w,
+                 float lin_b, float* s_out, const int* startT, const int* lenT, const long* startS, int n_seq, int maxT,
+                 unsigned long long seed) {
+  if (ctx.dry || n_seq == 0) return;
+  ctx.launches += 2;
+  hift_phase_scan_kernel<<<(n_seq * 9 + 31) / 32, 32, 0, ctx.stream>>>(f0, cumf, startT, lenT, startS, n_seq);
+  hift_source_kernel<<<dim3(maxT, n_seq), 480, 0, ctx.stream>>>(f0, cumf, phase_vec, noise, lin_w, lin_b, s_out, startT,
+                                                               lenT, startS, n_seq, seed);
+  CBX_CHECK(cudaGetLastError());
+}
+// |Linear(512->1)| per frame (f0_predictor.py:52-55): one warp per row
+__global__ void f0_head_kernel(const float* x, int ld, const float* w, float b, float* f0, long rows) {
+  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int i = lane; i < 512; i += 32) acc += x[r * ld + i] * w[i];
+  acc = warp_sum(acc);
+  if (lane == 0) f0[r] = fabsf(acc + b);
+}
+void f0_head(Ctx& ctx, const float* x, int ld, const float* w, float b, float* f0, long rows) {
+  if (ctx.dry || rows == 0) return;
+  ctx.launches++;
+  f0_head_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ctx.stream>>>(x, ld, w, b, f0, rows);
+  CBX_CHECK(cudaGetLastError());
+}
+// STFT(n_fft 16, hop 4, hann, center/reflect) of the source: out[frame][0..8]=Re, [9..17]=Im (hifigan.py:396-402)
+__global__ void hift_stft_kernel(const float* s, float* out, const int* startF, const int* lenT, const long* startS,
+                                 int n_seq) {
+  const int sq = blockIdx.y;
+  const long F = (long)lenT[sq] * 120 + 1, L = (long)lenT[sq] * 480;
+  const long f = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (f >= F) return;
+  const int k = threadIdx.x & 31;
+  if (k >= 9) return;
+  const float* sp = s + startS[sq];
+  float re = 0.f, im = 0.f;
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    long idx = f * 4 + n - 8;
+    if (idx < 0) idx = -idx;                      // reflect
+    if (idx >= L) idx = 2 * (L - 1) - idx;
+    const float w = 0.5f - 0.5f * cospif((float)n / 8.0f);   // periodic hann(16)
+    const float v = w * sp[idx];
+    float sn, cs;
+    sincospif((float)((k * n) & 15) / 8.0f, &sn, &cs);
+    re += v * cs; im -= v * sn;
+  }
+  float* o = out + ((long)startF[sq] + f) * 18;
+  o[k] = re; o[9 + k] = im;
+}
+void hift_stft(Ctx& ctx, const float* s, float* out, const int* startF, const int* lenT, const long* startS, int n_seq,
+               int maxT) {
+  if (ctx.dry || n_seq == 0) return;
+  ctx.launches++;
+  const long maxF = (long)maxT * 120 + 1;
+  hift_stft_kernel<<<dim3((unsigned)((maxF + 7) / 8), n_seq), 256, 0, ctx.stream>>>(s, out, startF, lenT, startS, n_seq);
+  CBX_CHECK(cudaGetLastError());
+}
+// reflection pad (1,0) of the last upsampling stage (hifigan.py:421-422): rows were written at +1; row0 = row2
+__global__ void reflect_row0_kernel(float* x, int C, const int* start, int n_seq) {
+  const int s = blockIdx.x;
+  float* base = x + (long)start[s] * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) base[c] = base[2 * C + c];
+}
+void reflect_row0(Ctx& ctx, float* x, int C, const int* start, int n_seq) {
+  if (ctx.dry || n_seq == 0) return;
+  ctx.launches++;
+  reflect_row0_kernel<<<n_seq, 64, 0, ctx.stream>>>(x, C, start, n_seq);
+  CBX_CHECK(cudaGetLastError());
+}
+// conv_post output [F][18] -> magnitude/phase -> iSTFT(16,4,hann) -> clamp +-0.99 -> trim-fade (s3gen.py:254-258)
+__global__ void hift_istft_kernel(const float* y, float* wav, const int* startF, const int* lenT, const long* startS,
+                                  int trim_fade) {
+  const int sq = blockIdx.y;
+  const long L = (long)lenT[sq] * 480, F = (long)lenT[sq] * 120 + 1;
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;     // output sample
+  if (n >= L) return;
+  const long np = n + 8;                                          // position in the padded signal
+  float num = 0.f, den = 0.f;
+  for (long f = np / 4; f >= 0 && f * 4 + 15 >= np; --f) {
+    if (f >= F) continue;
+    const int m = (int)(np - f * 4);
+    const float* yf = y + ((long)startF[sq] + f) * 18;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float mag = expf(yf[k]);
+      mag = fminf(mag, 100.0f);
+      const float ph = sinf(yf[9 + k]);
+      float sp, cp; sincosf(ph, &sp, &cp);
+      const float re = mag * cp, im = mag * sp;
+      float sn, cs; sincospif((float)((k * m) & 15) / 8.0f, &sn, &cs);
+      const float ck = (k == 0 || k == 8) ? 1.0f : 2.0f;
+      acc += ck * (re * cs - ((k == 0 || k == 8) ? 0.f : im * sn));
+    }
+    const float w = 0.5f - 0.5f * cospif((float)m / 8.0f);
+    num += w * (acc / 16.0f);
+    den += w * w;
+  }
+  float v = den > 1e-11f ? num / den : num;
+  v = fminf(fmaxf(v, -0.99f), 0.99f);
+  if (trim_fade && n < 960) {
+    float fd = 0.f;
+    if (n >= 480) fd = (cosf(3.14159265358979323846f * (1.0f - (float)(n - 480) / 479.0f)) + 1.0f) * 0.5f;
+    v *= fd;
+  }
+  wav[startS[sq] + n] = v;
+}
+void hift_istft(Ctx& ctx, const float* y, float* wav, const int* startF, const int* lenT, const long* startS, int n_seq,
+                int maxT, int trim_fade) {
+  if (ctx.dry || n_seq == 0) return;
+  ctx.launches++;
+  const long maxL = (long)maxT * 480;
+  hift_istft_kernel<<<dim3((unsigned)((maxL + 255) / 256), n_seq), 256, 0, ctx.stream>>>(y, wav, startF, lenT, startS,
+                                                                                      trim_fade);
+  CBX_CHECK(cudaGetLastError());
+}
+
+}  // namespace cbx

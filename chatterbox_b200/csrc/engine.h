@@ -1,0 +1,106 @@
+// Internal engine state behind the C ABI (include/cbx.h).
+#pragma once
+#include "ops.h"
+#include "kernels.h"
+#include "../../include/cbx.h"
+#include <memory>
+
+namespace cbx {
+
+struct HostTensor { std::vector<float> data; std::vector<int64_t> shape; };
+
+struct DevVec {   // small fp32 parameter vector on the device
+  float* p = nullptr; size_t n = 0;
+};
+
+// ---- T3 ------------------------------------------------------------------------------------------
+struct T3Layer { Weight qkv, o, gu, down; DevVec ln1, ln2; };
+struct T3Model {
+  bool ready = false;
+  int n_layers = 0, text_vocab = 0, max_pos = 0;
+  std::vector<T3Layer> layers;
+  DevVec final_norm, text_emb, speech_emb, text_pos, speech_pos, rope_cos, rope_sin;
+  Weight head;
+  // conditioning encoder
+  Weight spkr, pq, pk, pv, pproj;
+  DevVec emotion_w, perc_query, perc_ln_w, perc_ln_b;
+};
+
+// ---- flow ----------------------------------------------------------------------------------------
+struct EncLayer { Weight qkv, out, pos, w1, w2; DevVec ln_mha_w, ln_mha_b, ln_ff_w, ln_ff_b, bias_u, bias_v; };
+struct EncEmbed { Weight lin; DevVec ln_w, ln_b; };
+struct CfmResnet { Weight conv1, conv2, res, mlp; DevVec ln1_w, ln1_b, ln2_w, ln2_b; };
+struct CfmTfmr { Weight qkv, out, ff1, ff2; DevVec ln1_w, ln1_b, ln3_w, ln3_b; };
+struct CfmStage { CfmResnet res; CfmTfmr t[4]; };
+struct FlowModel {
+  bool ready = false, meanflow = false;
+  DevVec input_embedding;
+  Weight spk_affine, enc_proj;
+  EncEmbed embed, up_embed;
+  Weight pre_conv1, pre_conv2, up_conv;
+  EncLayer enc[6], up_enc[4];
+  DevVec after_w, after_b, pe_table; int pe_center = 0;
+  Weight time1, time2, time_mixer;
+  CfmStage down, mid[12], up;
+  Weight down_conv, up_conv2, final_conv, final_proj;
+  DevVec final_ln_w, final_ln_b;
+};
+
+// ---- HiFT ----------------------------------------------------------------------------------------
+struct HiftResBlock { Weight c1[3], c2[3]; DevVec a1[3], a2[3]; int k = 0; };
+struct HiftModel {
+  bool ready = false;
+  Weight f0conv[5]; DevVec f0_w; float f0_b = 0.f;
+  DevVec src_w; float src_b = 0.f;
+  Weight conv_pre, ups[3], src_down[3], conv_post;
+  HiftResBlock src_rb[3], rb[9];
+};
+
+}  // namespace cbx
+
+struct cbx_handle {
+  int device = 0;
+  std::string err;
+  std::map<std::string, cbx::HostTensor> host;   // staged tensors until finalize
+  cbx::T3Model t3;
+  cbx::FlowModel flow;
+  cbx::HiftModel hift;
+  int gemm_impl = 0, attn_impl = 0;
+  long long launches = 0;
+  std::vector<void*> owned;                      // device allocations to free
+};
+
+namespace cbx {
+// model builders / runners (t3.cu, flow.cu, hift.cu)
+void t3_finalize(cbx_handle* h);
+void t3_cond_encode(cbx_handle* h, Ctx& ctx, const float* spk, const int* prompt, int n_prompt, const float* emo,
+                    int n_voices, float* cond_out);
+void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, const int* tok_row, const int* tok_pos,
+                const int* row_start, const int* row_len, int max_row_len, const float* cond, const int* row_voice,
+                int len_cond, const int* text_flat, const int* text_start, const int* n_text, const int* row_uncond);
+void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, const int* act_utt, const int* slot_row, int n_act,
+               int n_steps);
+void flow_finalize(cbx_handle* h);
+void flow_encode(cbx_handle* h, Ctx& ctx, const int* tokens, const cbx_layout& L1, const cbx_layout& L2,
+                 const float* xvec, float* mu, float* spk);
+void cfm_solve(cbx_handle* h, Ctx& ctx, const float* mu, const float* spk, const float* cond, float* x,
+               const cbx_layout& L2, const cbx_layout& L3, int n_steps, float cfg_rate, int meanflow);
+void hift_finalize(cbx_handle* h);
+void hift_source_run(cbx_handle* h, Ctx& ctx, const float* mel, const cbx_hift_geom& g, const float* phase_vec,
+                     const float* noise, unsigned long long seed, float* s_out, float* f0_out);
+void hift_decode_run(cbx_handle* h, Ctx& ctx, const float* mel, const float* s, const cbx_hift_geom& g, float* wav,
+                     int trim_fade);
+
+// helpers shared by the model files
+const HostTensor& host_tensor(cbx_handle* h, const std::string& name);
+bool has_tensor(cbx_handle* h, const std::string& name);
+DevVec upload_vec(cbx_handle* h, const float* p, size_t n);
+DevVec upload_tensor(cbx_handle* h, const std::string& name);
+inline SeqMap seqmap(const cbx_layout& out, const cbx_layout& in) {
+  SeqMap m; m.tile_seq = out.tile_seq; m.out_start = out.start; m.out_len = out.len; m.in_start = in.start; m.in_len = in.len;
+  return m;
+}
+// conv as implicit GEMM on packed layouts
+GemmDev conv_args(const float* A, int lda, const Weight& W, int c_in, int ntaps, int dil, int pad, int stride,
+                  const cbx_layout& out, const cbx_layout& in, float* C, int ldc);
+}  // namespace cbx

@@ -1,0 +1,514 @@
+// GEMM family of libcbx:  C[M,N] = epilogue( A_gathered[M,K] (fp32) x W[N,K]^T (bf16) )
+//
+//  * gemm_tc_kernel<BN>   tcgen05 tensor-core tiles (M=128 x N=BN x K=64 per stage), accumulator in TMEM,
+//                         W tiles by TMA (SWIZZLE_128B), A tiles gathered from fp32 activations by 8 producer
+//                         warps (implicit im2col), split on the fly into bf16 hi+lo so that the product keeps
+//                         ~16 significand bits of the activations (2 MMAs per K step share one W tile).
+//  * gemv_kernel<R,NB>    weight-streaming GEMV for the AR decode step with few rows (HBM-bound).
+//  * gemm_simt_kernel     plain fp32 tiles -- debug reference for the two kernels above (CBX_GEMM=simt).
+//
+// Algorithmic HBM bytes per launch (roofline): N*K*2 (weights) + M*K_in*4 (activations) + M*N*4 (output).
+#include "ops.h"
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace cbx {
+
+// ================================================================================================
+// shared device helpers: row geometry + epilogue
+// ================================================================================================
+struct RowGeom {
+  long in_row0;  // input row feeding tap 0 (may be outside [lo,hi))
+  int lo, hi;    // valid input rows
+  int valid;     // output row is a real row (not layout padding / beyond M)
+};
+
+__device__ __forceinline__ RowGeom row_geom(const GemmDev& g, int row) {
+  RowGeom r;
+  if (row >= g.M) { r.in_row0 = 0; r.lo = 0; r.hi = 0; r.valid = 0; return r; }
+  if (g.has_seq) {
+    int tile = row / kTileM;
+    int s = g.seq.tile_seq[tile];
+    if (s < 0) { r.in_row0 = 0; r.lo = 0; r.hi = 0; r.valid = 0; return r; }
+    int t = row - g.seq.out_start[s];
+    int ist = g.seq.in_start[s];
+    r.in_row0 = (long)ist + (long)t * g.stride - g.pad;
+    r.lo = ist;
+    r.hi = ist + g.seq.in_len[s];
+    r.valid = (t < g.seq.out_len[s]);
+    if (!r.valid) { r.lo = 0; r.hi = 0; }
+  } else {
+    r.in_row0 = (long)row * g.stride - g.pad;
+    r.lo = 0; r.hi = g.M_in; r.valid = 1;
+  }
+  return r;
+}
+
+// one A element (used by the SIMT reference and by the scalar tails of the producers)
+__device__ __forceinline__ float load_a_elem(const GemmDev& g, const RowGeom& rg, int k) {
+  if (!rg.valid) return 0.0f;
+  if (g.a_mode == A_TAPS) {
+    int tap = k / g.ctap, c = k - tap * g.ctap;
+    long ir = rg.in_row0 + (long)tap * g.dil;
+    if (tap >= g.ntaps || c >= g.c_in || ir < rg.lo || ir >= rg.hi) return 0.0f;
+    return g.A[ir * g.lda + c];
+  } else {
+    if (k >= g.k_total) return 0.0f;
+    long flat = rg.in_row0 * g.c_in + k;
+    if (flat < (long)rg.lo * g.c_in || flat >= (long)rg.hi * g.c_in) return 0.0f;
+    return g.A[flat];
+  }
+}
+
+// epilogue for one output element (non-swiglu)
+__device__ __forceinline__ void epilogue_store(const GemmDev& g, int row, int n, float acc, bool row_valid) {
+  if (n >= g.n_out) return;
+  float v = acc * g.alpha + (g.bias ? g.bias[n] : 0.0f);
+  v = act_apply(g.act, v, g.act_vec ? g.act_vec[n] : g.act_p);
+  if (g.res) v += g.res[(long)row * g.ldr + n];
+  v *= g.out_scale;
+  float* cp = g.C + (long)row * g.ldc + n;
+  if (g.accumulate) v += *cp;
+  if (!row_valid) v = 0.0f;
+  *cp = v;
+  if (g.C2) g.C2[(long)row * g.ldc2 + n] = row_valid ? act_apply(g.act2, v, g.act2_vec ? g.act2_vec[n] : g.act2_p) : 0.0f;
+}
+__device__ __forceinline__ void epilogue_store_swiglu(const GemmDev& g, int row, int n_even, float a0, float a1,
+                                                      bool row_valid) {
+  if (n_even >= g.n_out) return;
+  float v0 = a0 * g.alpha + (g.bias ? g.bias[n_even] : 0.0f);
+  float v1 = a1 * g.alpha + (g.bias ? g.bias[n_even + 1] : 0.0f);
+  float v = (v0 / (1.0f + expf(-v0))) * v1;
+  if (!row_valid) v = 0.0f;
+  g.C[(long)row * g.ldc + (n_even >> 1)] = v;
+}
+
+// ================================================================================================
+// tcgen05 kernel
+// ================================================================================================
+constexpr int TC_BM = 128, TC_BK = 64;
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;   // + TMA warp + MMA warp
+
+template <int BN> struct TcCfg {
+  static constexpr int STAGES = (BN == 256) ? 3 : 4;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;        // 16 KB per hi / lo plane
+  static constexpr int W_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + W_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]  8 producer-warp arrivals + 1 TMA arrive(expect_tx)
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]  1 arrival (tcgen05.commit)
+  uint64_t* accum_bar = bars + 2 * STAGES;   // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * BN;
+  const int KB = g.Kpad / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCER_WARPS + 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == TC_PRODUCER_WARPS + 1) tmem_alloc<BN>(tmem_slot);   // MMA warp owns TMEM
+  if (warp == TC_PRODUCER_WARPS && lane == 0) tma_prefetch_desc(&tmapW);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TC_PRODUCER_WARPS) {
+    // ===================== A producers: gather fp32 -> bf16 hi/lo -> swizzled smem ====================
+    const int t = threadIdx.x;            // 0..255
+    const int c4 = t & 15;                // float4 chunk inside the 64-wide K block
+    const int rsub = t >> 4;              // 0..15
+    RowGeom rg[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) rg[p] = row_geom(g, m0 + p * 16 + rsub);
+    const bool vec_ok = (g.a_mode == A_TAPS) && ((g.lda & 3) == 0) && ((g.c_in & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* a_hi = smem + s * Cfg::STAGE_BYTES;
+      uint8_t* a_lo = a_hi + Cfg::A_BYTES;
+      const int k0 = kb * TC_BK + c4 * 4;
+      int tap = 0, c = k0;
+      if (g.a_mode == A_TAPS) { tap = k0 / g.ctap; c = k0 - tap * g.ctap; }
+      float4 v[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const RowGeom& r = rg[p];
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r.valid) {
+          if (vec_ok) {
+            long ir = r.in_row0 + (long)tap * g.dil;
+            if (tap < g.ntaps && c < g.c_in && ir >= r.lo && ir < r.hi)
+              x = __ldg(reinterpret_cast<const float4*>(g.A + ir * g.lda + c));
+          } else {
+            x.x = load_a_elem(g, r, k0 + 0); x.y = load_a_elem(g, r, k0 + 1);
+            x.z = load_a_elem(g, r, k0 + 2); x.w = load_a_elem(g, r, k0 + 3);
+          }
+        }
+        v[p] = x;
+      }
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int row = p * 16 + rsub;
+        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(v[p].x, h0, l0); split_bf16(v[p].y, h1, l1);
+        split_bf16(v[p].z, h2, l2); split_bf16(v[p].w, h3, l3);
+        // SWIZZLE_128B: 16-byte chunk index XOR (row % 8); rows are 128 B apart
+        const uint32_t off = row * 128 + ((((uint32_t)c4 >> 1) ^ ((uint32_t)row & 7)) << 4) + (c4 & 1) * 8;
+        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+        *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+      }
+      fence_proxy_async_smem();   // make generic-proxy stores visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    // ===================== epilogue: TMEM -> registers -> global =====================================
+    mbar_wait(accum_bar, 0);
+    tcgen05_fence_after();
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = warp >> 2;             // column half
+    const int row = m0 + q * 32 + lane;
+    const RowGeom er = row_geom(g, row);
+    const bool in_range = row < g.M;
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 2; cc += 32) {
+      const int col = half * (BN / 2) + cc;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+      tmem_ld_wait();
+      if (in_range) {
+        if (g.swiglu) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2)
+            if (n0 + col + j < g.n_out)
+              epilogue_store_swiglu(g, row, n0 + col + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), er.valid);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) epilogue_store(g, row, n0 + col + j, __uint_as_float(r[j]), er.valid);
+        }
+      }
+    }
+  } else if (warp == TC_PRODUCER_WARPS) {
+    // ===================== TMA producer for W tiles ===================================================
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* wdst = smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::W_BYTES);
+        tma_load_2d(wdst, &tmapW, &full_bar[s], kb * TC_BK, n0);
+      }
+    }
+  } else {
+    // ===================== MMA issuer (one elected thread) ============================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t a_lo = a_hi + Cfg::A_BYTES;
+        const uint32_t wb = a_hi + 2 * Cfg::A_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < TC_BK / 16; ++k4) {   // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
+          const uint64_t db = umma_desc_sw128(wb + k4 * 32);
+          umma_bf16(tmem_base, umma_desc_sw128(a_hi + k4 * 32), db, idesc, (kb | k4) != 0 ? 1u : 0u);
+          umma_bf16(tmem_base, umma_desc_sw128(a_lo + k4 * 32), db, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);     // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(accum_bar);           // accumulator complete
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == TC_PRODUCER_WARPS + 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// ================================================================================================
+// SIMT reference tiles (debug only)
+// ================================================================================================
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDev g) {
+  __shared__ float As[16][64 + 1];
+  __shared__ float Ws[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < g.Kpad; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int r = i >> 4, k = i & 15;
+      RowGeom rg = row_geom(g, m0 + r);
+      As[k][r] = load_a_elem(g, rg, k0 + k);
+      int n = n0 + r;
+      Ws[k][r] = (n < g.Npad) ? __bfloat162float(g.Wp[(long)n * g.Kpad + k0 + k]) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i) {
+    int row = m0 + ty * 4 + i;
+    if (row >= g.M) continue;
+    RowGeom rg = row_geom(g, row);
+    if (g.swiglu) {
+      for (int j = 0; j < 4; j += 2) {
+        int n = n0 + tx * 4 + j;
+        if (n < g.n_out) epilogue_store_swiglu(g, row, n, acc[i][j], acc[i][j + 1], rg.valid);
+      }
+    } else {
+      for (int j = 0; j < 4; ++j) epilogue_store(g, row, n0 + tx * 4 + j, acc[i][j], rg.valid);
+    }
+  }
+}
+
+// ================================================================================================
+// GEMV (few rows, Linear only): CTA = 4 warps; each CTA owns NB output columns; warp w streams the K
+// slices [w*256 + i*1024, +256) with one 16-byte (8 x bf16) load per lane per column.
+// ================================================================================================
+template <int R, int NB>
+__global__ void __launch_bounds__(128) gemv_kernel(const GemmDev g) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb0 = blockIdx.x * NB;
+  float acc[R][NB];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[r][j] = 0.0f;
+  const int K = g.Kpad;
+  for (int k = warp * 256 + lane * 8; k < K; k += 1024) {
+    uint4 w[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      int n = nb0 + j;
+      w[j] = (n < g.Npad) ? __ldg(reinterpret_cast<const uint4*>(g.Wp + (long)n * K + k)) : make_uint4(0, 0, 0, 0);
+    }
+    float x[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r < g.M && k < g.k_total) {   // k_total == logical K (multiple of 8 for every Linear on this path)
+        const float4 a = __ldg(reinterpret_cast<const float4*>(g.A + (long)r * g.lda + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(g.A + (long)r * g.lda + k + 4));
+        x[r][0] = a.x; x[r][1] = a.y; x[r][2] = a.z; x[r][3] = a.w;
+        x[r][4] = b.x; x[r][5] = b.y; x[r][6] = b.z; x[r][7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[r][i] = 0.0f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const uint32_t ww[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float w0 = __uint_as_float(ww[i] << 16);            // bf16 -> fp32 is a 16-bit shift
+        const float w1 = __uint_as_float(ww[i] & 0xFFFF0000u);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r][j] = fmaf(x[r][2 * i], w0, acc[r][j]);
+          acc[r][j] = fmaf(x[r][2 * i + 1], w1, acc[r][j]);
+        }
+      }
+    }
+  }
+  __shared__ float red[4][R][NB];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      float v = warp_sum(acc[r][j]);
+      if (lane == 0) red[warp][r][j] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < R * NB) {
+    const int r = threadIdx.x / NB, j = threadIdx.x % NB;
+    if (r < g.M) {
+      if (g.swiglu) {
+        if ((j & 1) == 0) {
+          float a0 = red[0][r][j] + red[1][r][j] + red[2][r][j] + red[3][r][j];
+          float a1 = red[0][r][j + 1] + red[1][r][j + 1] + red[2][r][j + 1] + red[3][r][j + 1];
+          if (nb0 + j < g.n_out) epilogue_store_swiglu(g, r, nb0 + j, a0, a1, true);
+        }
+      } else {
+        float a = red[0][r][j] + red[1][r][j] + red[2][r][j] + red[3][r][j];
+        epilogue_store(g, r, nb0 + j, a, true);
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p)
+      throw std::runtime_error("cbx: cuTensorMapEncodeTiled not available from the driver");
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+void make_tmaps_for(Weight& W) {
+  PFN_encodeTiled enc = get_encode_fn();
+  const int boxes[3] = {64, 128, 256};
+  for (int i = 0; i < 3; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)W.Kpad, (cuuint64_t)W.Npad};
+    cuuint64_t strides[1] = {(cuuint64_t)W.Kpad * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)boxes[i]};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&W.tmap[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W.w, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cbx: cuTensorMapEncodeTiled failed");
+  }
+}
+
+static inline uint16_t f2bf16_host(float f) {   // round-to-nearest-even
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+  uint32_t lsb = (u >> 16) & 1;
+  u += 0x7FFFu + lsb;
+  return (uint16_t)(u >> 16);
+}
+
+static void upload_packed(Weight& W, const std::vector<uint16_t>& host, const float* host_bias) {
+  CBX_CHECK(cudaMalloc(&W.w, host.size() * 2));
+  CBX_CHECK(cudaMemcpy(W.w, host.data(), host.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> b(W.Npad, 0.0f);
+  if (host_bias) for (int i = 0; i < W.N; ++i) b[i] = host_bias[i];
+  CBX_CHECK(cudaMalloc(&W.bias, W.Npad * 4));
+  CBX_CHECK(cudaMemcpy(W.bias, b.data(), W.Npad * 4, cudaMemcpyHostToDevice));
+  make_tmaps_for(W);
+}
+
+void pack_linear(Weight& W, const float* w, const float* bias, int N, int K) {
+  W.N = N; W.K = K; W.Npad = (N + 63) / 64 * 64; W.Kpad = (K + 63) / 64 * 64;
+  std::vector<uint16_t> h((size_t)W.Npad * W.Kpad, 0);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) h[(size_t)n * W.Kpad + k] = f2bf16_host(w[(size_t)n * K + k]);
+  upload_packed(W, h, bias);
+}
+// torch Conv1d weight [N][cin][taps] -> [N][tap][ctap], ctap = cin rounded up to 64
+void pack_conv_taps(Weight& W, const float* w, const float* bias, int N, int cin, int taps) {
+  const int ctap = (cin + 63) / 64 * 64;
+  W.N = N; W.K = taps * ctap; W.Npad = (N + 63) / 64 * 64; W.Kpad = W.K;
+  std::vector<uint16_t> h((size_t)W.Npad * W.Kpad, 0);
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < taps; ++t)
+        h[(size_t)n * W.Kpad + (size_t)t * ctap + c] = f2bf16_host(w[((size_t)n * cin + c) * taps + t]);
+  upload_packed(W, h, bias);
+}
+// torch Conv1d weight [N][cin][taps] -> [N][tap*cin + c]  (contiguous window of a channel-last input)
+void pack_conv_window(Weight& W, const float* w, const float* bias, int N, int cin, int taps) {
+  W.N = N; W.K = taps * cin; W.Npad = (N + 63) / 64 * 64; W.Kpad = (W.K + 63) / 64 * 64;
+  std::vector<uint16_t> h((size_t)W.Npad * W.Kpad, 0);
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < taps; ++t)
+        h[(size_t)n * W.Kpad + (size_t)t * cin + c] = f2bf16_host(w[((size_t)n * cin + c) * taps + t]);
+  upload_packed(W, h, bias);
+}
+void free_weight(Weight& W) {
+  if (W.w) cudaFree(W.w);
+  if (W.bias) cudaFree(W.bias);
+  W.w = nullptr; W.bias = nullptr;
+}
+
+GemmDev gemm_args_linear(const float* A, int lda, int M, const Weight& W, float* C, int ldc) {
+  GemmDev g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.lda = lda; g.M = M; g.M_in = M;
+  g.a_mode = A_TAPS; g.ntaps = 1; g.ctap = W.Kpad; g.c_in = W.K; g.dil = 0; g.pad = 0; g.stride = 1;
+  g.k_total = W.K;
+  g.has_seq = 0;
+  g.Wp = W.w; g.Kpad = W.Kpad; g.Npad = W.Npad;
+  g.C = C; g.ldc = ldc; g.n_out = W.N; g.bias = W.bias; g.alpha = 1.0f;
+  g.act = ACT_NONE; g.out_scale = 1.0f;
+  return g;
+}
+
+template <int BN> static void launch_tc(Ctx& ctx, const GemmDev& g, const Weight& W, int tmap_idx) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    attr_set = true;
+  }
+  dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.Npad + BN - 1) / BN);
+  gemm_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], g);
+}
+
+template <int R> static void launch_gemv(Ctx& ctx, const GemmDev& g) {
+  if (g.Npad <= 2048) {
+    gemv_kernel<R, 2><<<(g.Npad + 1) / 2, 128, 0, ctx.stream>>>(g);
+  } else {
+    gemv_kernel<R, 4><<<(g.Npad + 3) / 4, 128, 0, ctx.stream>>>(g);
+  }
+}
+
+void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
+  CBX_REQUIRE(g.Kpad % 64 == 0 && g.Npad % 64 == 0, "padded weight dims");
+  if (g.a_mode == A_TAPS) CBX_REQUIRE(g.ctap % 64 == 0, "TAPS mode needs 64-channel chunks");
+  if (ctx.dry) return;
+  ctx.launches++;
+  if (ctx.gemm_impl == 1) {
+    dim3 grid((g.M + 63) / 64, (g.Npad + 63) / 64);
+    gemm_simt_kernel<<<grid, 256, 0, ctx.stream>>>(g);
+  } else {
+    const bool plain = !g.has_seq && g.a_mode == A_TAPS && g.ntaps == 1 && g.stride == 1 && g.pad == 0 &&
+                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 &&
+                       ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+    if (plain && g.M <= 8) {
+      if (g.M <= 2) launch_gemv<2>(ctx, g);
+      else if (g.M <= 4) launch_gemv<4>(ctx, g);
+      else launch_gemv<8>(ctx, g);
+    } else {
+      const int mt = (g.M + TC_BM - 1) / TC_BM;
+      // widest N tile that still gives every SM a tile (L2->SM traffic per flop falls with BN)
+      if (g.Npad % 256 == 0 && (long)mt * (g.Npad / 256) >= 120) launch_tc<256>(ctx, g, W, 2);
+      else if (g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 100) launch_tc<128>(ctx, g, W, 1);
+      else launch_tc<64>(ctx, g, W, 0);
+    }
+  }
+  CBX_CHECK(cudaGetLastError());
+}
+
+}  // namespace cbx

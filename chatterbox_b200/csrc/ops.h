@@ -1,0 +1,140 @@
+// Host-side op layer of libcbx: packed weights, workspace arena, kernel launch wrappers.
+#pragma once
+#include "common.cuh"
+#include <map>
+#include <vector>
+#include <string>
+
+namespace cbx {
+
+// ----------------------------------------------------------------------------------------------
+// Packed weight: W[Npad][Kpad] bf16, K-major (exactly torch's Linear [out, in] / conv [out, tap*Cin_pad]).
+// ----------------------------------------------------------------------------------------------
+struct Weight {
+  __nv_bfloat16* w = nullptr;
+  float* bias = nullptr;     // [Npad] fp32 (zeros when the layer has none)
+  int N = 0, K = 0;          // logical sizes
+  int Npad = 0, Kpad = 0;    // N padded to 64, K padded to 64
+  CUtensorMap tmap[3];       // TMA maps with box {64 (K), 64|128|256 (N)}, SWIZZLE_128B
+};
+
+// Geometry of a packed variable-length batch.  Every sequence starts at a multiple of kTileM rows, so
+// one 128-row tile never straddles two sequences.  All arrays live on the device.
+struct SeqMap {
+  const int* tile_seq = nullptr;   // [n_tiles] sequence id of each output tile
+  const int* out_start = nullptr;  // [n_seq] first output row of the sequence
+  const int* out_len = nullptr;    // [n_seq] valid output rows
+  const int* in_start = nullptr;   // [n_seq] first input row (input buffer may use another layout)
+  const int* in_len = nullptr;     // [n_seq] valid input rows
+};
+
+enum AMode : int { A_TAPS = 0, A_WINDOW = 1 };
+
+// Device-visible argument block of every GEMM flavour (tcgen05 tiles, SIMT tiles, GEMV).
+struct GemmDev {
+  // ---- A operand: fp32 activations gathered as an implicit im2col -----------------------------
+  const float* A;
+  int lda;        // floats per input row
+  int M;          // output rows (grid covers ceil(M/128) tiles)
+  int M_in;       // input rows (flat case bound)
+  int a_mode;     // A_TAPS: k = tap*ctap + c, input row = in_row0 + tap*dil, needs ctap % 64 == 0
+                  // A_WINDOW: element k of output row = flat input element in_row0*c_in + k (lda == c_in)
+  int ntaps, ctap, c_in, dil, pad, stride;
+  int k_total;    // logical K (ntaps*c_in for WINDOW, ntaps*ctap for TAPS)
+  int has_seq;
+  SeqMap seq;
+  // ---- B operand -------------------------------------------------------------------------------
+  const __nv_bfloat16* Wp;  // [Npad][Kpad]
+  int Kpad, Npad;
+  // ---- epilogue --------------------------------------------------------------------------------
+  float* C; int ldc;
+  int n_out;                // valid output columns
+  const float* bias;        // [Npad] or null
+  float alpha;              // v = acc*alpha + bias
+  int act; float act_p; const float* act_vec;   // activation (+ per-channel parameter, e.g. snake alpha)
+  const float* res; int ldr;                    // v += res[r][n]
+  int accumulate;                               // v += C[r][n] (old value)
+  float out_scale;                              // v *= out_scale (after act/res)
+  int swiglu;                                   // columns (2j,2j+1) -> out[j] = silu(v0)*v1
+  float* C2; int ldc2; int act2; float act2_p; const float* act2_vec;  // optional 2nd output act2(v)
+};
+
+struct Arena {  // bump allocator over caller-owned workspace; dry=true only counts
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    if (off > peak) peak = off;
+    if (dry) return reinterpret_cast<void*>(size_t(0x1000) + a);  // fake non-null pointer, never dereferenced
+    if (off > cap) throw std::runtime_error("cbx: workspace too small");
+    return base + a;
+  }
+  template <typename T> T* get(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
+  size_t mark() const { return off; }
+  void reset(size_t m) { off = m; }
+};
+
+struct Ctx {
+  cudaStream_t stream = nullptr;
+  Arena ws;
+  bool dry = false;       // size-only pass: no launches
+  int gemm_impl = 0;      // 0 = tcgen05 (default), 1 = SIMT reference tiles (debug, env CBX_GEMM=simt)
+  int attn_impl = 0;      // 0 = tensor-core flash (default), 1 = SIMT reference (debug, env CBX_ATTN=simt)
+  long launches = 0;      // kernels launched through this context
+};
+
+// ---- weights ------------------------------------------------------------------------------------
+// host fp32 [N][K] (row-major) -> device packed bf16 + TMA maps.  taps/cin describe conv weights given
+// as [N][cin][taps] (torch Conv1d layout); they are re-ordered to [N][tap][cin_pad].
+void pack_linear(Weight& W, const float* host_w, const float* host_bias, int N, int K);
+void pack_conv_taps(Weight& W, const float* host_w, const float* host_bias, int N, int cin, int taps);    // k = tap*ctap + c
+void pack_conv_window(Weight& W, const float* host_w, const float* host_bias, int N, int cin, int taps);  // k = tap*cin + c
+void free_weight(Weight& W);
+void make_tmaps_for(Weight& W);   // (re)build the TMA maps of a weight whose .w/.Npad/.Kpad are set
+
+// ---- GEMM ---------------------------------------------------------------------------------------
+GemmDev gemm_args_linear(const float* A, int lda, int M, const Weight& W, float* C, int ldc);
+void gemm(Ctx& ctx, GemmDev g, const Weight& W);
+
+// ---- attention ------------------------------------------------------------------------------------
+struct AttnArgs {
+  const float* Q; const float* K; const float* V;  // row-major [rows][ld*], head h at column h*64
+  int ldq, ldk, ldv;
+  float* O; int ldo;
+  int n_seq, n_heads;
+  const int* q_start; const int* q_len;     // per sequence (device)
+  const int* kv_start; const int* kv_len;
+  int max_q_len;                            // host-side bound for the grid
+  float scale;                              // S = (Q K^T + bias) * scale
+  int causal;                               // query i attends keys j <= i + (kv_len - q_len)
+  const float* bias = nullptr;              // optional additive bias, indexed by packed q row
+  long bias_head_stride = 0; int bias_ld = 0; long bias_row0 = 0;
+  int bias_rel = 0; int bias_center = 0;    // bias_rel: column = bias_center - i + j (espnet rel_shift)
+};
+void attention(Ctx& ctx, const AttnArgs& a);
+void attention_generic(Ctx& ctx, const float* Q, const float* K, const float* V, float* O, int n_q, int n_kv,
+                       int n_heads, int head_dim, int ldq, int ldk, int ldv, int ldo, float scale);
+
+// ---- T3 paged KV cache ------------------------------------------------------------------------------
+struct PagedKV {
+  void* pages;            // [n_pages][n_layers][2][n_heads][page_tokens][64] of kv dtype
+  int kv_fp32;            // 0 = bf16, 1 = fp32
+  int n_layers, n_heads, page_tokens;
+  const int* page_table;  // [rows][max_pages_per_row]
+  int max_pages_per_row;
+};
+void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* slot_row,
+                            int n_slots, const int* positions, float* out, int ldo, float* scratch, int nsplit);
+void rope_and_store_kv(Ctx& ctx, float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* tok_row,
+                       const int* tok_pos, int pos_is_per_row, int n_tok, const float* cos_t, const float* sin_t);
+
+// ---- norms / fill -------------------------------------------------------------------------------------
+void rmsnorm(Ctx& ctx, const float* x, int ldx, const float* w, float* y, int ldy, int rows, int dim, float eps,
+             const int* row_idx);
+void layernorm(Ctx& ctx, const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int dim,
+               float eps, int act, float out_scale, const float* seq_add, int seq_add_ld, const SeqMap* seq);
+void fill(Ctx& ctx, float* p, long n, float v);
+
+}  // namespace cbx

@@ -1,0 +1,222 @@
+// T3: Llama-style 0.5B speech-token LM (reference src/chatterbox/models/t3/t3.py, transformers LlamaModel).
+//   prefill  : packed tokens -> 30 x [RMSNorm, QKV GEMM, RoPE + KV append, causal flash attention, O GEMM(+res),
+//              RMSNorm, gate/up GEMM with fused SiLU*mul, down GEMM(+res)] -> final norm -> speech head
+//   decode   : per step  sampler kernel -> same layer stack with paged decode attention (one token per row)
+#include "engine.h"
+
+namespace cbx {
+
+static std::vector<float> concat_rows(const std::vector<const HostTensor*>& ts) {
+  std::vector<float> out;
+  for (auto* t : ts) out.insert(out.end(), t->data.begin(), t->data.end());
+  return out;
+}
+
+void t3_finalize(cbx_handle* h) {
+  T3Model& m = h->t3;
+  int L = 0;
+  while (has_tensor(h, "t3.tfmr.layers." + std::to_string(L) + ".self_attn.q_proj.weight")) ++L;
+  CBX_REQUIRE(L > 0, "no T3 layers loaded");
+  m.n_layers = L;
+  m.layers.resize(L);
+  for (int i = 0; i < L; ++i) {
+    const std::string p = "t3.tfmr.layers." + std::to_string(i) + ".";
+    T3Layer& ly = m.layers[i];
+    auto qkv = concat_rows({&host_tensor(h, p + "self_attn.q_proj.weight"), &host_tensor(h, p + "self_attn.k_proj.weight"),
+                            &host_tensor(h, p + "self_attn.v_proj.weight")});
+    pack_linear(ly.qkv, qkv.data(), nullptr, 3072, 1024);
+    pack_linear(ly.o, host_tensor(h, p + "self_attn.o_proj.weight").data.data(), nullptr, 1024, 1024);
+    const auto& g = host_tensor(h, p + "mlp.gate_proj.weight").data;
+    const auto& u = host_tensor(h, p + "mlp.up_proj.weight").data;
+    std::vector<float> gu((size_t)8192 * 1024);
+    for (int j = 0; j < 4096; ++j) {       // interleave so that the GEMM epilogue sees (gate_j, up_j) side by side
+      memcpy(&gu[(size_t)(2 * j) * 1024], &g[(size_t)j * 1024], 4096);
+      memcpy(&gu[(size_t)(2 * j + 1) * 1024], &u[(size_t)j * 1024], 4096);
+    }
+    pack_linear(ly.gu, gu.data(), nullptr, 8192, 1024);
+    pack_linear(ly.down, host_tensor(h, p + "mlp.down_proj.weight").data.data(), nullptr, 1024, 4096);
+    ly.ln1 = upload_tensor(h, p + "input_layernorm.weight");
+    ly.ln2 = upload_tensor(h, p + "post_attention_layernorm.weight");
+  }
+  m.final_norm = upload_tensor(h, "t3.tfmr.norm.weight");
+  m.text_emb = upload_tensor(h, "t3.text_emb.weight");
+  m.text_vocab = (int)host_tensor(h, "t3.text_emb.weight").shape[0];
+  m.speech_emb = upload_tensor(h, "t3.speech_emb.weight");
+  m.text_pos = upload_tensor(h, "t3.text_pos_emb.emb.weight");
+  m.speech_pos = upload_tensor(h, "t3.speech_pos_emb.emb.weight");
+  m.rope_cos = upload_tensor(h, "t3.rope_cos");
+  m.rope_sin = upload_tensor(h, "t3.rope_sin");
+  m.max_pos = (int)host_tensor(h, "t3.rope_cos").shape[0];
+  pack_linear(m.head, host_tensor(h, "t3.speech_head.weight").data.data(), nullptr, 8194, 1024);
+  // conditioning encoder
+  pack_linear(m.spkr, host_tensor(h, "t3.cond_enc.spkr_enc.weight").data.data(),
+              host_tensor(h, "t3.cond_enc.spkr_enc.bias").data.data(), 1024, 256);
+  const std::string pa = "t3.cond_enc.perceiver.attn.";
+  pack_linear(m.pq, host_tensor(h, pa + "to_q.weight").data.data(), host_tensor(h, pa + "to_q.bias").data.data(), 1024, 1024);
+  pack_linear(m.pk, host_tensor(h, pa + "to_k.weight").data.data(), host_tensor(h, pa + "to_k.bias").data.data(), 1024, 1024);
+  pack_linear(m.pv, host_tensor(h, pa + "to_v.weight").data.data(), host_tensor(h, pa + "to_v.bias").data.data(), 1024, 1024);
+  pack_linear(m.pproj, host_tensor(h, pa + "proj_out.weight").data.data(), host_tensor(h, pa + "proj_out.bias").data.data(), 1024, 1024);
+  m.emotion_w = upload_tensor(h, "t3.cond_enc.emotion_adv_fc.weight");
+  m.perc_query = upload_tensor(h, "t3.cond_enc.perceiver.pre_attention_query");
+  m.perc_ln_w = upload_tensor(h, pa + "norm.weight");
+  m.perc_ln_b = upload_tensor(h, pa + "norm.bias");
+  m.ready = true;
+}
+
+// ---- small kernels -------------------------------------------------------------------------------
+__global__ void scale_vec_kernel(const float* w, const float* scalar, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = w[i] * scalar[0];
+}
+__global__ void iota_kernel(int* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+__global__ void last_index_kernel(const int* row_start, const int* row_len, int* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = row_start[i] + row_len[i] - 1;
+}
+
+// AttentionBlock2 of the perceiver (modules/perceiver.py:156-170): x1 [n1,1024] attends x2 [n2,1024]
+static void perceiver_block(cbx_handle* h, Ctx& ctx, const float* x1, int n1, const float* x2, int n2, float* out) {
+  T3Model& m = h->t3;
+  const size_t mark = ctx.ws.mark();
+  float* x1n = ctx.ws.get<float>((size_t)n1 * 1024);
+  float* x2n = ctx.ws.get<float>((size_t)n2 * 1024);
+  float* q = ctx.ws.get<float>((size_t)n1 * 1024);
+  float* k = ctx.ws.get<float>((size_t)n2 * 1024);
+  float* v = ctx.ws.get<float>((size_t)n2 * 1024);
+  float* a = ctx.ws.get<float>((size_t)n1 * 1024);
+  layernorm(ctx, x1, 1024, m.perc_ln_w.p, m.perc_ln_b.p, x1n, 1024, n1, 1024, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
+  layernorm(ctx, x2, 1024, m.perc_ln_w.p, m.perc_ln_b.p, x2n, 1024, n2, 1024, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
+  gemm(ctx, gemm_args_linear(x1n, 1024, n1, m.pq, q, 1024), m.pq);
+  gemm(ctx, gemm_args_linear(x2n, 1024, n2, m.pk, k, 1024), m.pk);
+  gemm(ctx, gemm_args_linear(x2n, 1024, n2, m.pv, v, 1024), m.pv);
+  attention_generic(ctx, q, k, v, a, n1, n2, 4, 256, 1024, 1024, 1024, 1024, 1.0f / 16.0f);
+  GemmDev g = gemm_args_linear(a, 1024, n1, m.pproj, out, 1024);
+  g.res = x1; g.ldr = 1024;
+  gemm(ctx, g, m.pproj);
+  ctx.ws.reset(mark);
+}
+
+void t3_cond_encode(cbx_handle* h, Ctx& ctx, const float* spk, const int* prompt, int n_prompt, const float* emo,
+                    int n_voices, float* cond_out) {
+  T3Model& m = h->t3;
+  CBX_REQUIRE(m.ready, "t3 weights not finalized");
+  const int len_cond = 34;
+  float* emb = ctx.ws.get<float>((size_t)n_prompt * 1024);
+  float* pre = ctx.ws.get<float>((size_t)32 * 1024);
+  for (int v = 0; v < n_voices; ++v) {
+    float* out = cond_out + (size_t)v * len_cond * 1024;
+    // speech_emb(prompt) + speech_pos_emb(0..n-1)   (t3.py:97-99)
+    gather_rows(ctx, m.speech_emb.p, 1024, prompt + (size_t)v * n_prompt, emb, 1024, n_prompt, 1024, m.speech_pos.p, 1024,
+                nullptr, 8194);
+    gemm(ctx, gemm_args_linear(spk + (size_t)v * 256, 256, 1, m.spkr, out, 1024), m.spkr);         // cond_enc.py:70
+    perceiver_block(h, ctx, m.perc_query.p, 32, emb, n_prompt, pre);                                  // perceiver.py:209
+    perceiver_block(h, ctx, pre, 32, pre, 32, out + 1024);                                            // perceiver.py:211
+    if (!ctx.dry) {
+      ctx.launches++;
+      scale_vec_kernel<<<4, 256, 0, ctx.stream>>>(m.emotion_w.p, emo + v, out + (size_t)33 * 1024, 1024);  // cond_enc.py:88
+    }
+  }
+}
+
+static PagedKV paged_of(const cbx_t3_state& st, int n_layers) {
+  PagedKV kv;
+  kv.pages = st.kv_pages; kv.kv_fp32 = st.kv_dtype; kv.n_layers = n_layers; kv.n_heads = 16;
+  kv.page_tokens = st.page_tokens; kv.page_table = st.page_table; kv.max_pages_per_row = st.max_pages_per_row;
+  return kv;
+}
+
+void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, const int* tok_row, const int* tok_pos,
+                const int* row_start, const int* row_len, int max_row_len, const float* cond, const int* row_voice,
+                int len_cond, const int* text_flat, const int* text_start, const int* n_text, const int* row_uncond) {
+  T3Model& m = h->t3;
+  CBX_REQUIRE(m.ready, "t3 weights not finalized");
+  const int R = st.n_rows;
+  float* x = ctx.ws.get<float>((size_t)n_tok * 1024);
+  float* xn = ctx.ws.get<float>((size_t)n_tok * 1024);
+  float* qkv = ctx.ws.get<float>((size_t)n_tok * 3072);
+  float* att = ctx.ws.get<float>((size_t)n_tok * 1024);
+  float* act = ctx.ws.get<float>((size_t)n_tok * 4096);
+  float* hn = ctx.ws.get<float>((size_t)R * 1024);
+  int* last = ctx.ws.get<int>(R);
+  t3_embed(ctx, x, n_tok, tok_row, tok_pos, cond, row_voice, len_cond, text_flat, text_start, n_text, row_uncond,
+           m.text_emb.p, m.text_vocab, m.text_pos.p, m.speech_emb.p, m.speech_pos.p, 6561);
+  PagedKV kv = paged_of(st, m.n_layers);
+  for (int l = 0; l < m.n_layers; ++l) {
+    T3Layer& ly = m.layers[l];
+    rmsnorm(ctx, x, 1024, ly.ln1.p, xn, 1024, n_tok, 1024, 1e-5f, nullptr);
+    gemm(ctx, gemm_args_linear(xn, 1024, n_tok, ly.qkv, qkv, 3072), ly.qkv);
+    rope_and_store_kv(ctx, qkv, 3072, kv, l, tok_row, tok_pos, 0, n_tok, m.rope_cos.p, m.rope_sin.p);
+    AttnArgs a;
+    a.Q = qkv; a.K = qkv + 1024; a.V = qkv + 2048; a.ldq = a.ldk = a.ldv = 3072; a.O = att; a.ldo = 1024;
+    a.n_seq = R; a.n_heads = 16; a.q_start = row_start; a.q_len = row_len; a.kv_start = row_start; a.kv_len = row_len;
+    a.max_q_len = max_row_len; a.scale = 0.125f; a.causal = 1;
+    attention(ctx, a);
+    GemmDev go = gemm_args_linear(att, 1024, n_tok, ly.o, x, 1024);
+    go.res = x; go.ldr = 1024;
+    gemm(ctx, go, ly.o);
+    rmsnorm(ctx, x, 1024, ly.ln2.p, xn, 1024, n_tok, 1024, 1e-5f, nullptr);
+    GemmDev gg = gemm_args_linear(xn, 1024, n_tok, ly.gu, act, 4096);
+    gg.swiglu = 1;
+    gemm(ctx, gg, ly.gu);
+    GemmDev gd = gemm_args_linear(act, 4096, n_tok, ly.down, x, 1024);
+    gd.res = x; gd.ldr = 1024;
+    gemm(ctx, gd, ly.down);
+  }
+  if (!ctx.dry) {
+    ctx.launches++;
+    last_index_kernel<<<(R + 127) / 128, 128, 0, ctx.stream>>>(row_start, row_len, last, R);
+  }
+  rmsnorm(ctx, x, 1024, m.final_norm.p, hn, 1024, R, 1024, 1e-5f, last);
+  gemm(ctx, gemm_args_linear(hn, 1024, R, m.head, st.logits, st.ldl), m.head);
+}
+
+void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, const int* act_utt, const int* slot_row, int n_act,
+               int n_steps) {
+  T3Model& m = h->t3;
+  CBX_REQUIRE(m.ready, "t3 weights not finalized");
+  const int rows_per = st.cfg ? 2 : 1;
+  const int S = n_act * rows_per;
+  float* xn = ctx.ws.get<float>((size_t)S * 1024);
+  float* qkv = ctx.ws.get<float>((size_t)S * 3072);
+  float* att = ctx.ws.get<float>((size_t)S * 1024);
+  float* act = ctx.ws.get<float>((size_t)S * 4096);
+  int nsplit = 1;
+  if (S * 16 < 592) { nsplit = (592 + S * 16 - 1) / (S * 16); if (nsplit > 16) nsplit = 16; }
+  float* scratch = ctx.ws.get<float>((size_t)S * 16 * nsplit * 66);
+  PagedKV kv = paged_of(st, m.n_layers);
+  T3SampleDev sp;
+  sp.logits = st.logits; sp.ldl = st.ldl; sp.act_utt = act_utt; sp.cfg = st.cfg; sp.n_utts = st.n_utts;
+  sp.cfg_weight = st.cfg_weight; sp.rep_penalty = st.rep_penalty; sp.temperature = st.temperature;
+  sp.min_p = st.min_p; sp.top_p = st.top_p; sp.eos_id = 6562;
+  sp.tokens = st.tokens; sp.max_tokens = st.max_tokens; sp.n_gen = st.n_gen; sp.max_new = st.max_new; sp.done = st.done;
+  sp.seen = st.seen; sp.positions = st.positions; sp.base_pos = st.base_pos; sp.x = st.x;
+  sp.speech_emb = m.speech_emb.p; sp.speech_pos = m.speech_pos.p; sp.q_noise = st.q_noise; sp.seed = st.seed;
+  float* x = st.x;
+  for (int step = 0; step < n_steps; ++step) {
+    t3_sample(ctx, sp, n_act);
+    for (int l = 0; l < m.n_layers; ++l) {
+      T3Layer& ly = m.layers[l];
+      rmsnorm(ctx, x, 1024, ly.ln1.p, xn, 1024, S, 1024, 1e-5f, nullptr);
+      gemm(ctx, gemm_args_linear(xn, 1024, S, ly.qkv, qkv, 3072), ly.qkv);
+      rope_and_store_kv(ctx, qkv, 3072, kv, l, slot_row, st.positions, 1, S, m.rope_cos.p, m.rope_sin.p);
+      paged_decode_attention(ctx, qkv, 3072, kv, l, slot_row, S, st.positions, att, 1024, scratch, nsplit);
+      GemmDev go = gemm_args_linear(att, 1024, S, ly.o, x, 1024);
+      go.res = x; go.ldr = 1024;
+      gemm(ctx, go, ly.o);
+      rmsnorm(ctx, x, 1024, ly.ln2.p, xn, 1024, S, 1024, 1e-5f, nullptr);
+      GemmDev gg = gemm_args_linear(xn, 1024, S, ly.gu, act, 4096);
+      gg.swiglu = 1;
+      gemm(ctx, gg, ly.gu);
+      GemmDev gd = gemm_args_linear(act, 4096, S, ly.down, x, 1024);
+      gd.res = x; gd.ldr = 1024;
+      gemm(ctx, gd, ly.down);
+    }
+    rmsnorm(ctx, x, 1024, m.final_norm.p, xn, 1024, S, 1024, 1e-5f, nullptr);
+    gemm(ctx, gemm_args_linear(xn, 1024, S, m.head, st.logits, st.ldl), m.head);
+  }
+}
+
+}  // namespace cbx

@@ -1,0 +1,153 @@
+/* libcbx -- C ABI of the B200-native Chatterbox inference engine (sm_100a).
+ *
+ * The reference (resemble-ai/chatterbox) has no FFI / plugin interface: its boundary is the Python
+ * module API.  This header is the C-ABI that the thin Python shim in chatterbox_b200/
+ * binds with ctypes; each entry point cites the reference method whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - every function returns an int status (CBX_OK == 0); nothing throws or aborts across the boundary;
+ *    cbx_last_error() returns the message of the last failure on that handle;
+ *  - the caller owns every activation buffer (KV pages, workspace, inputs, outputs) and passes raw device
+ *    pointers + explicit sizes + a cudaStream_t; the library owns only its packed weights;
+ *  - no hidden allocation or host synchronisation on the hot path; calls are ordered by the stream;
+ *  - there is no CPU fallback: without a CUDA device cbx_create() fails.
+ *
+ * Packed variable-length batches ("layout"): sequences are stored back to back in one [rows, C] fp32
+ * channel-last buffer, each sequence starting at a multiple of 128 rows (tile_seq[row/128] names the owner).
+ */
+#ifndef CBX_H_
+#define CBX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBX_OK 0
+#define CBX_ERR_INVALID 1
+#define CBX_ERR_CUDA 2
+#define CBX_ERR_WORKSPACE 3
+
+typedef struct cbx_handle cbx_handle;
+typedef void* cbx_stream; /* cudaStream_t */
+
+typedef struct {
+  int n_seq;           /* sequences */
+  int rows;            /* total rows incl. alignment padding (multiple of 128) */
+  int max_len;         /* longest sequence (host-side bound for grids) */
+  const int* tile_seq; /* device [rows/128] sequence id per tile (-1 = unused) */
+  const int* start;    /* device [n_seq] first row */
+  const int* len;      /* device [n_seq] valid rows */
+  const int* h_start;  /* host copy of start (needed by cbx_flow_encode to chunk the rel-pos bias), may be NULL elsewhere */
+  const int* h_len;    /* host copy of len */
+} cbx_layout;
+
+/* ---- lifetime / weights -------------------------------------------------------------------------
+ * replaces: ChatterboxTTS.from_local() module construction + load_state_dict  (reference tts.py:133-163) */
+int cbx_create(int device, cbx_handle** out);
+void cbx_destroy(cbx_handle* h);
+const char* cbx_last_error(cbx_handle* h);
+int cbx_version(void);
+/* debug switches: key "gemm" = "tc"|"simt", key "attn" = "tc"|"simt" (SIMT = reference kernels for bisecting) */
+int cbx_set_option(cbx_handle* h, const char* key, const char* value);
+/* number of kernels launched through this handle so far (bench.py's gpu_launches) */
+long long cbx_launch_count(cbx_handle* h);
+/* host fp32 tensor with the reference's state-dict name ("t3." / "flow." / "hift." prefix added by the caller) */
+int cbx_load_tensor(cbx_handle* h, const char* name, const float* host_data, int ndim, const int64_t* shape);
+/* pack loaded tensors of one model ("t3" | "flow" | "hift"): bf16 K-major weights + TMA maps, QKV concat,
+ * gate/up interleave, weight-norm folding (reference hifigan.py weight_norm parametrisations) */
+int cbx_finalize_weights(cbx_handle* h, const char* model);
+
+/* ---- T3 (reference src/chatterbox/models/t3/) ----------------------------------------------------- */
+typedef struct {
+  int n_utts, n_rows, cfg;    /* n_rows = n_utts * (cfg ? 2 : 1); rows (2b, 2b+1) = (cond, uncond) */
+  /* paged KV cache: pages[page][layer][k|v][head][token][64] */
+  void* kv_pages; int kv_dtype; /* 0 = bf16, 1 = fp32 */ int page_tokens;
+  const int* page_table; int max_pages_per_row; /* device [n_rows][max_pages_per_row] */
+  int* positions;          /* device [n_rows] rope position of the token being fed */
+  const int* base_pos;     /* device [n_rows] prefill length S0 */
+  int* tokens; int max_tokens; /* device [n_utts][max_tokens] generated ids */
+  int* n_gen;              /* device [n_utts] */
+  const int* max_new;      /* device [n_utts] per-utterance budget (reference max_new_tokens) */
+  int* done;               /* device [n_utts] */
+  unsigned char* seen;     /* device [n_utts][8194] repetition-penalty history, BOS (6561) preset to 1 */
+  float* x;                /* device [n_rows][1024] next input embedding per slot */
+  float* logits; int ldl;  /* device [n_rows][ldl] logits per slot, ldl >= 8194 */
+  float cfg_weight, rep_penalty, temperature, min_p, top_p;
+  const float* q_noise;    /* optional device [steps][n_utts][8194] Exp(1) draws (torch.multinomial parity) */
+  unsigned long long seed; /* counter-RNG seed when q_noise == NULL */
+} cbx_t3_state;
+
+/* replaces T3.prepare_conditioning + T3CondEnc.forward + Perceiver.forward
+ * (t3.py:92-100, modules/cond_enc.py:64-97, modules/perceiver.py:200-212).  cond_out [n_voices][34][1024] */
+int cbx_t3_cond_encode(cbx_handle* h, const float* speaker_emb, const int* prompt_tokens, int n_prompt,
+                       const float* emotion_adv, int n_voices, float* cond_out, void* ws, size_t ws_bytes,
+                       cbx_stream stream);
+/* replaces T3.prepare_input_embeds + the prefill forward of T3.inference (t3.py:102-130, 303-335 ->
+ * transformers LlamaModel.forward) for a packed batch of n_tok tokens; fills the KV pages and st->logits */
+int cbx_t3_prefill(cbx_handle* h, const cbx_t3_state* st, int n_tok, const int* tok_row, const int* tok_pos,
+                   const int* row_start, const int* row_len, int max_row_len, const float* cond,
+                   const int* row_voice, int len_cond, const int* text_flat, const int* text_start,
+                   const int* n_text, const int* row_uncond, void* ws, size_t ws_bytes, cbx_stream stream);
+/* replaces n_steps iterations of the sampling loop of T3.inference (t3.py:338-386): sample (CFG, repetition
+ * penalty, temperature, min-p, top-p, multinomial) then one cached forward, for the n_act active utterances */
+int cbx_t3_decode(cbx_handle* h, const cbx_t3_state* st, const int* act_utt, const int* slot_row, int n_act,
+                  int n_steps, void* ws, size_t ws_bytes, cbx_stream stream);
+/* keep only slots whose utterance is listed in new_act (gathers x / logits rows; keep_slot = old slot index) */
+int cbx_t3_compact(cbx_handle* h, const cbx_t3_state* st, const int* keep_slot, int n_keep_slots, void* ws,
+                   size_t ws_bytes, cbx_stream stream);
+size_t cbx_t3_workspace_bytes(cbx_handle* h, int n_tok_prefill, int n_rows);
+
+/* ---- S3Gen flow: token -> mel (reference src/chatterbox/models/s3gen/) ---------------------------- */
+/* replaces CausalMaskedDiffWithXvec.inference up to the decoder call (flow.py:149-185) incl.
+ * UpsampleConformerEncoder.forward (transformer/upsample_encoder.py:237-304).
+ * tokens: device int32 [L1.rows] (prompt+generated ids per sequence); xvec [n_seq][192];
+ * outputs mu [L2.rows][80], spk [n_seq][80] */
+int cbx_flow_encode(cbx_handle* h, const int* tokens, const cbx_layout* L1, const cbx_layout* L2,
+                    const float* xvec, float* mu, float* spk, void* ws, size_t ws_bytes, cbx_stream stream);
+/* replaces CausalConditionalCFM.forward / solve_euler / basic_euler (flow_matching.py:195-246, 78-145) with
+ * ConditionalDecoder.forward (decoder.py:243-333) as the estimator.  x: in = noise z, out = mel, [L2.rows][80]
+ * channel-last; cond [L2.rows][80] (prompt mel then zeros); L3 = CFG layout with 2*n_seq sequences
+ * (or L2 again when meanflow / no CFG). */
+int cbx_cfm_solve(cbx_handle* h, const float* mu, const float* spk, const float* cond, float* x,
+                  const cbx_layout* L2, const cbx_layout* L3, int n_steps, float cfg_rate, int meanflow,
+                  void* ws, size_t ws_bytes, cbx_stream stream);
+size_t cbx_flow_workspace_bytes(cbx_handle* h, const cbx_layout* L1, const cbx_layout* L2, const cbx_layout* L3);
+
+/* ---- HiFT vocoder: mel -> waveform (reference hifigan.py, f0_predictor.py) ------------------------ */
+typedef struct {
+  cbx_layout LT;          /* mel frames T per sequence */
+  cbx_layout L8, L40;     /* 8T, 40T rows */
+  cbx_layout L120;        /* 120T + 1 rows (also the STFT frame layout) */
+  const long long* sample_start; /* device [n_seq] first sample of each sequence in s / wav (480T samples each) */
+  long long total_samples;
+} cbx_hift_geom;
+/* replaces ConvRNNF0Predictor.forward + f0_upsamp + SourceModuleHnNSF.forward (f0_predictor.py:52-55,
+ * hifigan.py:200-231,267-283, 462-466).  phase_vec [n_seq][9] and noise (per sequence [9][480T] at 9*sample_start)
+ * may be NULL (phase 0 / counter RNG).  s_out [total_samples]; f0_out optional [LT.rows] */
+int cbx_hift_source(cbx_handle* h, const float* mel, const cbx_hift_geom* g, const float* phase_vec,
+                    const float* noise, unsigned long long seed, float* s_out, float* f0_out, void* ws,
+                    size_t ws_bytes, cbx_stream stream);
+/* replaces HiFTGenerator.decode (hifigan.py:412-444) + the trim-fade of S3Token2Wav.inference (s3gen.py:359-360) */
+int cbx_hift_decode(cbx_handle* h, const float* mel, const float* s, const cbx_hift_geom* g, float* wav,
+                    int trim_fade, void* ws, size_t ws_bytes, cbx_stream stream);
+size_t cbx_hift_workspace_bytes(cbx_handle* h, const cbx_hift_geom* g);
+
+/* ---- diagnostic entry points (unit tests of single kernels) --------------------------------------- */
+/* C[M][N] = act(A_gather x W^T + bias) with W given on the host [N][cin][taps] (torch conv layout; taps=1, cin=K
+ * for Linear).  mode 0 = TAPS (k = tap*ceil64(cin)+c), 1 = WINDOW.  A, C device pointers. */
+int cbx_test_gemm(cbx_handle* h, const float* A, int lda, int M_in, int M, const float* w_host, const float* bias_host,
+                  int N, int cin, int taps, int mode, int dil, int pad, int stride, const cbx_layout* out_layout,
+                  const cbx_layout* in_layout, int act, float act_p, const float* res, int ldr, int swiglu,
+                  float* C, int ldc, cbx_stream stream);
+/* O = softmax((Q K^T + bias) * scale) V on packed rows, head_dim 64 */
+int cbx_test_attention(cbx_handle* h, const float* Q, const float* K, const float* V, int ld, float* O, int ldo,
+                       int n_heads, const cbx_layout* L, float scale, int causal, const float* bias, long long bias_head_stride,
+                       int bias_ld, int bias_rel, int bias_center, cbx_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBX_H_ */
