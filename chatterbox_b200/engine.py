@@ -1,0 +1,377 @@
+"""Host side of the B200 engine: owns the cbx handle, packs batches into the layouts libcbx expects,
+and drives the stage-level C-ABI calls.  PyTorch is only the container for device memory / streams.
+
+Batch semantics: the reference is batch-1; a batch here equals running the reference once
+per utterance (per-utterance noise / RNG streams are explicit inputs).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from ._lib import Handle, Layout, T3State, HiftGeom, CbxError
+
+TILE = 128
+SPEECH_VOCAB = 8194
+START_SPEECH, STOP_SPEECH = 6561, 6562
+LEN_COND = 34
+LDL = 8256          # logits row stride (8194 padded to a multiple of 64)
+PAGE_TOKENS = 32
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class PackedLayout:
+    """Sequences back to back, each starting at a multiple of 128 rows (cbx_layout)."""
+
+    def __init__(self, lens, device, alloc=None, starts=None):
+        lens = np.asarray(lens, dtype=np.int32)
+        if starts is None:
+            alloc = lens if alloc is None else np.asarray(alloc, dtype=np.int64)
+            padded = ((np.asarray(alloc, dtype=np.int64) + TILE - 1) // TILE) * TILE
+            padded = np.maximum(padded, TILE)
+            starts = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int32)
+            rows = int(padded.sum())
+        else:
+            starts, rows = starts
+        self.lens, self.starts, self.rows = lens, np.asarray(starts, dtype=np.int32), int(rows)
+        self.n_seq = len(lens)
+        self.max_len = int(lens.max()) if len(lens) else 0
+        tile_seq = np.full(self.rows // TILE, -1, dtype=np.int32)
+        ends = np.concatenate([self.starts[1:], [self.rows]])
+        for s in range(self.n_seq):
+            tile_seq[self.starts[s] // TILE: ends[s] // TILE] = s
+        self.d_tile = torch.from_numpy(tile_seq).to(device)
+        self.d_start = torch.from_numpy(self.starts.copy()).to(device)
+        self.d_len = torch.from_numpy(self.lens.copy()).to(device)
+        self._h_start = np.ascontiguousarray(self.starts)
+        self._h_len = np.ascontiguousarray(self.lens)
+        self.c = Layout(self.n_seq, self.rows, self.max_len, _ptr(self.d_tile), _ptr(self.d_start), _ptr(self.d_len),
+                        C.c_void_p(self._h_start.ctypes.data), C.c_void_p(self._h_len.ctypes.data))
+
+    def scaled(self, factor, lens, device):
+        """Layout whose starts / rows are exact multiples of this one (polyphase up-convs write through it)."""
+        return PackedLayout(lens, device, starts=(self.starts.astype(np.int64) * factor, self.rows * factor))
+
+    def concat_twice(self, device):
+        """CFG layout: the same sequences twice (conditional copies then unconditional copies)."""
+        starts = np.concatenate([self.starts, self.starts + self.rows])
+        return PackedLayout(np.concatenate([self.lens, self.lens]), device, starts=(starts, 2 * self.rows))
+
+
+def espnet_pe_table(max_len=5000, d_model=512):
+    """The reference's relative positional table (transformer/embedding.py:229-258), built with the same torch
+    ops so that the engine reads bit-identical values: row p <-> relative position (max_len-1-p)."""
+    position = torch.arange(0, max_len, dtype=torch.float32).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float32) * -(math.log(10000.0) / d_model))
+    pe_pos = torch.zeros(max_len, d_model)
+    pe_neg = torch.zeros(max_len, d_model)
+    pe_pos[:, 0::2] = torch.sin(position * div_term)
+    pe_pos[:, 1::2] = torch.cos(position * div_term)
+    pe_neg[:, 0::2] = torch.sin(-1 * position * div_term)
+    pe_neg[:, 1::2] = torch.cos(-1 * position * div_term)
+    return torch.cat([torch.flip(pe_pos, [0]), pe_neg[1:]], dim=0).contiguous()
+
+
+def llama3_rope_tables(n_pos, head_dim=64, base=500000.0, factor=8.0, low=1.0, high=4.0, orig=8192):
+    """cos/sin [n_pos, 32] exactly as transformers computes them (modeling_rope_utils._compute_llama3_parameters +
+    LlamaRotaryEmbedding.forward) for the reference's rope_scaling (t3/llama_configs.py:23-30)."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.int64).to(torch.float) / head_dim))
+    low_w, high_w = orig / low, orig / high
+    wavelen = 2 * math.pi / inv_freq
+    inv_l = torch.where(wavelen > low_w, inv_freq / factor, inv_freq)
+    smooth = (orig / wavelen - low) / (high - low)
+    smoothed = (1 - smooth) * inv_l / factor + smooth * inv_l
+    is_med = ~(wavelen < high_w) * ~(wavelen > low_w)
+    inv = torch.where(is_med, smoothed, inv_l)
+    pos = torch.arange(n_pos, dtype=torch.float32)
+    freqs = (inv[None, :, None].float() @ pos[None, None, :].float()).transpose(1, 2)[0]
+    return freqs.cos().contiguous(), freqs.sin().contiguous()
+
+
+class Engine:
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise CbxError("chatterbox_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.h = Handle(device)
+        self._ws = None
+        self.t3_layers = 0
+        self.meanflow = False
+
+    # ------------------------------------------------------------------ weights
+    def _load(self, prefix, sd):
+        for k, v in sd.items():
+            t = v.detach().to(torch.float32).contiguous().cpu()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            self.h.call("cbx_load_tensor", (prefix + k).encode(), C.c_void_p(t.data_ptr()), t.dim(), shape)
+
+    def load_t3(self, sd, max_pos=4608):
+        sd = {k: v for k, v in sd.items() if not k.startswith("text_head") and not k.startswith("tfmr.embed_tokens")}
+        self._load("t3.", sd)
+        cos, sin = llama3_rope_tables(max_pos)
+        self._load("t3.", {"rope_cos": cos, "rope_sin": sin})
+        self.h.call("cbx_finalize_weights", b"t3")
+        self.t3_layers = len({k.split(".")[2] for k in sd if k.startswith("tfmr.layers.")})
+
+    def load_flow(self, sd, max_len=5000):
+        self._load("flow.", sd)
+        self._load("flow.", {"pe_table": espnet_pe_table(max_len)})
+        self.h.call("cbx_finalize_weights", b"flow")
+        self.meanflow = any("time_embed_mixer" in k for k in sd)
+
+    def load_hift(self, sd):
+        self._load("hift.", sd)
+        self.h.call("cbx_finalize_weights", b"hift")
+
+    def workspace(self, nbytes):
+        if nbytes == 0:
+            raise CbxError("workspace query failed: " + self.h.lib.cbx_last_error(self.h.h).decode())
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ T3
+    def t3_cond(self, speaker_emb, prompt_tokens, emotion_adv):
+        """[n_voices,256], [n_voices,n_prompt] int, [n_voices] -> cond [n_voices, 34, 1024]
+        (reference T3.prepare_conditioning, t3.py:92-100)."""
+        dev = self.device
+        spk = speaker_emb.to(dev, torch.float32).reshape(-1, 256).contiguous()
+        nv = spk.shape[0]
+        ptok = prompt_tokens.to(dev, torch.int32).reshape(nv, -1).contiguous()
+        emo = emotion_adv.to(dev, torch.float32).reshape(nv).contiguous()
+        out = torch.empty(nv, LEN_COND, 1024, device=dev, dtype=torch.float32)
+        ws = self.workspace(self.h.lib.cbx_t3_workspace_bytes(self.h.h, 256, 2))
+        self.h.call("cbx_t3_cond_encode", _ptr(spk), _ptr(ptok), ptok.shape[1], _ptr(emo), nv, _ptr(out), _ptr(ws),
+                    ws.numel(), self._stream())
+        return out
+
+    def t3_generate(self, text_tokens, cond, voice_ids=None, max_new_tokens=1000, cfg_weight=0.5, temperature=0.8,
+                    top_p=1.0, min_p=0.05, repetition_penalty=1.2, q_noise=None, seed=0, kv_dtype="bf16",
+                    max_sync_steps=32, return_state=False):
+        """Batched equivalent of T3.inference (t3.py:225-390).
+        text_tokens: list of 1-D int tensors incl. SOT/EOT (one per utterance).  cond: [n_voices,34,1024].
+        max_new_tokens: int or per-utterance list.  Returns a list of 1-D int64 CPU tensors (EOS included if hit)."""
+        dev = self.device
+        B = len(text_tokens)
+        cfg = 1 if cfg_weight > 0.0 else 0
+        rp = 2 if cfg else 1
+        R = B * rp
+        voice_ids = [0] * B if voice_ids is None else list(voice_ids)
+        max_new = [int(max_new_tokens)] * B if np.isscalar(max_new_tokens) else [int(m) for m in max_new_tokens]
+        n_text = np.array([len(t) for t in text_tokens], dtype=np.int32)
+        s0 = LEN_COND + n_text + 2
+        row_len = np.repeat(s0, rp).astype(np.int32)
+        row_start = np.concatenate([[0], np.cumsum(row_len)[:-1]]).astype(np.int32)
+        n_tok = int(row_len.sum())
+        tok_row = np.repeat(np.arange(R, dtype=np.int32), row_len)
+        tok_pos = np.concatenate([np.arange(l, dtype=np.int32) for l in row_len])
+        text_flat = np.concatenate([np.asarray(t, dtype=np.int32).reshape(-1) for t in text_tokens])
+        utt_text_start = np.concatenate([[0], np.cumsum(n_text)[:-1]]).astype(np.int32)
+        row_text_start = np.repeat(utt_text_start, rp)
+        row_ntext = np.repeat(n_text, rp)
+        row_voice = np.repeat(np.asarray(voice_ids, dtype=np.int32), rp)
+        row_uncond = np.tile(np.array([0, 1], dtype=np.int32), B) if cfg else np.zeros(R, dtype=np.int32)
+        # paged KV cache: just enough pages per row for prefill + budget
+        pages_per_row = (np.repeat(s0 + np.asarray(max_new, dtype=np.int32), rp) + PAGE_TOKENS - 1) // PAGE_TOKENS
+        max_pages = int(pages_per_row.max())
+        page_table = np.zeros((R, max_pages), dtype=np.int32)
+        nxt = 0
+        for r in range(R):
+            page_table[r, :pages_per_row[r]] = np.arange(nxt, nxt + pages_per_row[r])
+            nxt += int(pages_per_row[r])
+        n_pages = nxt
+        kvt = torch.float32 if kv_dtype in ("fp32", "f32", torch.float32) else torch.bfloat16
+        L = self.t3_layers
+        kv = torch.empty(n_pages, L, 2, 16, PAGE_TOKENS, 64, dtype=kvt, device=dev)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        d = dict(tok_row=t(tok_row), tok_pos=t(tok_pos), row_start=t(row_start), row_len=t(row_len),
+                 text_flat=t(text_flat), row_text_start=t(row_text_start), row_ntext=t(row_ntext),
+                 row_voice=t(row_voice), row_uncond=t(row_uncond), page_table=t(page_table))
+        max_tokens = int(max(max_new))
+        st_t = dict(
+            positions=torch.zeros(R, dtype=torch.int32, device=dev), base_pos=t(row_len),
+            tokens=torch.zeros(B, max_tokens, dtype=torch.int32, device=dev),
+            n_gen=torch.zeros(B, dtype=torch.int32, device=dev), max_new=t(np.asarray(max_new, dtype=np.int32)),
+            done=torch.zeros(B, dtype=torch.int32, device=dev),
+            seen=torch.zeros(B, SPEECH_VOCAB, dtype=torch.uint8, device=dev),
+            x=torch.zeros(R, 1024, dtype=torch.float32, device=dev),
+            logits=torch.zeros(R, LDL, dtype=torch.float32, device=dev))
+        st_t["seen"][:, START_SPEECH] = 1          # repetition penalty history starts with BOS (t3.py:316,347)
+        qn = q_noise.to(dev, torch.float32).contiguous() if q_noise is not None else None
+        st = T3State(B, R, cfg, _ptr(kv), 1 if kvt == torch.float32 else 0, PAGE_TOKENS, _ptr(d["page_table"]), max_pages,
+                     _ptr(st_t["positions"]), _ptr(st_t["base_pos"]), _ptr(st_t["tokens"]), max_tokens,
+                     _ptr(st_t["n_gen"]), _ptr(st_t["max_new"]), _ptr(st_t["done"]), _ptr(st_t["seen"]),
+                     _ptr(st_t["x"]), _ptr(st_t["logits"]), LDL, float(cfg_weight), float(repetition_penalty),
+                     float(temperature), float(min_p), float(top_p), _ptr(qn), int(seed))
+        ws = self.workspace(self.h.lib.cbx_t3_workspace_bytes(self.h.h, n_tok, R))
+        cond = cond.to(dev, torch.float32).contiguous()
+        self.h.call("cbx_t3_prefill", C.byref(st), n_tok, _ptr(d["tok_row"]), _ptr(d["tok_pos"]), _ptr(d["row_start"]),
+                    _ptr(d["row_len"]), int(row_len.max()), _ptr(cond), _ptr(d["row_voice"]), LEN_COND,
+                    _ptr(d["text_flat"]), _ptr(d["row_text_start"]), _ptr(d["row_ntext"]), _ptr(d["row_uncond"]),
+                    _ptr(ws), ws.numel(), self._stream())
+        if return_state == "prefill":
+            return st_t
+        # decode with host-driven retirement of finished utterances
+        act = np.arange(B, dtype=np.int32)
+        n_gen_h = np.zeros(B, dtype=np.int64)
+        budget = np.asarray(max_new, dtype=np.int64)
+        while len(act):
+            remaining = budget[act] - n_gen_h[act]
+            k = int(max(1, min(max_sync_steps, remaining.min())))
+            d_act = t(act)
+            slot_row = (np.repeat(act * rp, rp) + np.tile(np.arange(rp), len(act))).astype(np.int32)
+            d_slot = t(slot_row)
+            self.h.call("cbx_t3_decode", C.byref(st), _ptr(d_act), _ptr(d_slot), len(act), k, _ptr(ws), ws.numel(),
+                        self._stream())
+            done_h = st_t["done"].cpu().numpy()          # device->host sync every k steps (reference: every step)
+            n_gen_h = st_t["n_gen"].cpu().numpy().astype(np.int64)
+            keep = done_h[act] == 0
+            if keep.all():
+                continue
+            keep_slots = np.repeat(np.nonzero(keep)[0] * rp, rp) + np.tile(np.arange(rp), int(keep.sum()))
+            act = act[keep]
+            if len(act):
+                d_keep = t(keep_slots.astype(np.int32))
+                self.h.call("cbx_t3_compact", C.byref(st), _ptr(d_keep), len(keep_slots), _ptr(ws), ws.numel(), self._stream())
+        toks = st_t["tokens"].cpu()
+        n_gen = st_t["n_gen"].cpu()
+        out = [toks[b, :int(n_gen[b])].to(torch.int64) for b in range(B)]
+        if return_state:
+            return out, st_t
+        return out
+
+    # ------------------------------------------------------------------ flow
+    def flow_mel(self, tokens, ref_dicts, z=None, n_timesteps=None, cfg_rate=0.7, return_mu=False):
+        """Batched equivalent of S3Token2Wav.flow_inference (s3gen.py:301-321 -> flow.py:131-198).
+        tokens: list of 1-D int tensors; ref_dicts: one dict (shared voice) or a list of dicts with
+        prompt_token [1,Np], prompt_feat [1,2Np,80], embedding [1,192].  z: optional list of [80, 2(Np+N)] noise
+        tensors (what flow_matching.py:216 would draw).  Returns a list of mel tensors [80, 2N] on the device."""
+        dev = self.device
+        B = len(tokens)
+        refs = ref_dicts if isinstance(ref_dicts, (list, tuple)) else [ref_dicts] * B
+        n_timesteps = n_timesteps or (2 if self.meanflow else 10)
+        np_len = np.array([int(r["prompt_token"].shape[-1]) for r in refs], dtype=np.int32)
+        n_gen = np.array([int(t.numel()) for t in tokens], dtype=np.int32)
+        n = np_len + n_gen
+        L1 = PackedLayout(n, dev)
+        L2 = PackedLayout(2 * n, dev)
+        L3 = L2 if self.meanflow else L2.concat_twice(dev)
+        tok = torch.zeros(L1.rows, dtype=torch.int32)
+        cond = torch.zeros(L2.rows, 80, dtype=torch.float32)
+        xvec = torch.zeros(B, 192, dtype=torch.float32)
+        for b in range(B):
+            r = refs[b]
+            s = int(L1.starts[b])
+            tok[s:s + np_len[b]] = r["prompt_token"].reshape(-1).to(torch.int32).cpu()
+            tok[s + np_len[b]:s + n[b]] = tokens[b].reshape(-1).to(torch.int32).cpu()
+            pf = r["prompt_feat"].reshape(-1, 80).to(torch.float32).cpu()
+            s2 = int(L2.starts[b])
+            cond[s2:s2 + pf.shape[0]] = pf                     # flow.py:178-180
+            xvec[b] = r["embedding"].reshape(-1).to(torch.float32).cpu()
+        tok, cond, xvec = tok.to(dev), cond.to(dev), xvec.to(dev)
+        mu = torch.zeros(L2.rows, 80, dtype=torch.float32, device=dev)
+        spk = torch.zeros(B, 80, dtype=torch.float32, device=dev)
+        x = torch.zeros(L2.rows, 80, dtype=torch.float32, device=dev)
+        for b in range(B):
+            s2, T = int(L2.starts[b]), int(2 * n[b])
+            if z is not None:
+                x[s2:s2 + T] = z[b].reshape(80, T).t().to(dev, torch.float32)
+            else:
+                x[s2:s2 + T] = torch.randn(80, T, device=dev).t()
+        ws = self.workspace(self.h.lib.cbx_flow_workspace_bytes(self.h.h, C.byref(L1.c), C.byref(L2.c), C.byref(L3.c)))
+        self.h.call("cbx_flow_encode", _ptr(tok), C.byref(L1.c), C.byref(L2.c), _ptr(xvec), _ptr(mu), _ptr(spk),
+                    _ptr(ws), ws.numel(), self._stream())
+        if return_mu:
+            return [mu[int(L2.starts[b]):int(L2.starts[b]) + int(2 * n[b])].clone() for b in range(B)], spk
+        self.h.call("cbx_cfm_solve", _ptr(mu), _ptr(spk), _ptr(cond), _ptr(x), C.byref(L2.c), C.byref(L3.c),
+                    int(n_timesteps), float(cfg_rate), 1 if self.meanflow else 0, _ptr(ws), ws.numel(), self._stream())
+        out = []
+        for b in range(B):
+            s2 = int(L2.starts[b])
+            out.append(x[s2 + 2 * np_len[b]:s2 + 2 * n[b]].t().contiguous())      # drop prompt frames (flow.py:196)
+        return out
+
+    def cfm_nfe(self, mu, spk, cond, x, t_value):
+        """Single estimator evaluation (unit-test hook): Euler step with dt=1 from x=0 is not expressible, so
+        tests use cfm_solve with n_timesteps=1 instead."""
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ HiFT
+    def _hift_geom(self, T):
+        dev = self.device
+        T = np.asarray(T, dtype=np.int32)
+        LT = PackedLayout(T, dev, alloc=T + 1)          # +1: room for the 120T+1-th row of the last stage
+        L8 = LT.scaled(8, 8 * T, dev)
+        L40 = LT.scaled(40, 40 * T, dev)
+        L120 = LT.scaled(120, 120 * T + 1, dev)
+        sstart = torch.from_numpy(LT.starts.astype(np.int64) * 480).to(dev)
+        g = HiftGeom(LT.c, L8.c, L40.c, L120.c, _ptr(sstart), int(LT.rows) * 480)
+        keep = (LT, L8, L40, L120, sstart)
+        return g, keep
+
+    def hift(self, mels, source=None, phase_vec=None, noise=None, seed=0, trim_fade=True):
+        """Batched equivalent of S3Token2Wav.hift_inference + trim-fade (s3gen.py:324-327,359-360).
+        mels: list of [80, T] tensors.  source: optional list of [1, 480T] (reference cache_source hook);
+        phase_vec: optional list of [9]; noise: optional list of [9, 480T] (SineGen draws, hifigan.py:212-226).
+        Returns (list of wav [480T], list of source [480T]) on the device."""
+        dev = self.device
+        B = len(mels)
+        T = np.array([int(m.shape[-1]) for m in mels], dtype=np.int32)
+        g, keep = self._hift_geom(T)
+        LT = keep[0]
+        mel = torch.zeros(LT.rows, 80, dtype=torch.float32, device=dev)
+        for b in range(B):
+            mel[int(LT.starts[b]):int(LT.starts[b]) + int(T[b])] = mels[b].reshape(80, -1).t().to(dev, torch.float32)
+        total = int(LT.rows) * 480
+        s = torch.zeros(total, dtype=torch.float32, device=dev)
+        wav = torch.zeros(total, dtype=torch.float32, device=dev)
+        ws = self.workspace(self.h.lib.cbx_hift_workspace_bytes(self.h.h, C.byref(g)))
+        if source is None:
+            pv = None
+            if phase_vec is not None:
+                pv = torch.stack([p.reshape(9).to(torch.float32) for p in phase_vec]).to(dev).contiguous()
+            nz = None
+            if noise is not None:
+                nz = torch.zeros(total * 9, dtype=torch.float32, device=dev)
+                for b in range(B):
+                    o = int(LT.starts[b]) * 480 * 9
+                    nz[o:o + 9 * 480 * int(T[b])] = noise[b].reshape(-1).to(dev, torch.float32)
+            self.h.call("cbx_hift_source", _ptr(mel), C.byref(g), _ptr(pv), _ptr(nz), int(seed), _ptr(s), C.c_void_p(0),
+                        _ptr(ws), ws.numel(), self._stream())
+        else:
+            for b in range(B):
+                o = int(LT.starts[b]) * 480
+                s[o:o + 480 * int(T[b])] = source[b].reshape(-1).to(dev, torch.float32)
+        self.h.call("cbx_hift_decode", _ptr(mel), _ptr(s), C.byref(g), _ptr(wav), 1 if trim_fade else 0, _ptr(ws),
+                    ws.numel(), self._stream())
+        wavs, srcs = [], []
+        for b in range(B):
+            o = int(LT.starts[b]) * 480
+            wavs.append(wav[o:o + 480 * int(T[b])])
+            srcs.append(s[o:o + 480 * int(T[b])])
+        return wavs, srcs
+
+    def hift_f0(self, mels):
+        """F0 predictor only (unit-test hook; f0_predictor.py:52-55)."""
+        dev = self.device
+        T = np.array([int(m.shape[-1]) for m in mels], dtype=np.int32)
+        g, keep = self._hift_geom(T)
+        LT = keep[0]
+        mel = torch.zeros(LT.rows, 80, dtype=torch.float32, device=dev)
+        for b in range(len(mels)):
+            mel[int(LT.starts[b]):int(LT.starts[b]) + int(T[b])] = mels[b].reshape(80, -1).t().to(dev, torch.float32)
+        s = torch.zeros(int(LT.rows) * 480, dtype=torch.float32, device=dev)
+        f0 = torch.zeros(LT.rows, dtype=torch.float32, device=dev)
+        ws = self.workspace(self.h.lib.cbx_hift_workspace_bytes(self.h.h, C.byref(g)))
+        self.h.call("cbx_hift_source", _ptr(mel), C.byref(g), C.c_void_p(0), C.c_void_p(0), 0, _ptr(s), _ptr(f0), _ptr(ws),
+                    ws.numel(), self._stream())
+        return [f0[int(LT.starts[b]):int(LT.starts[b]) + int(T[b])] for b in range(len(mels))]

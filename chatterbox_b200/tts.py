@@ -1,0 +1,171 @@
+"""Public API boundary (reference src/chatterbox/tts.py:106-272)."""
+import math
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .engine import Engine, SPEECH_VOCAB, STOP_SPEECH
+from .t3 import T3, T3Cond
+from .s3gen import S3Gen, S3GEN_SR, SPEECH_VOCAB_SIZE
+
+SOT, EOT = 255, 0
+
+
+def punc_norm(text: str) -> str:
+    """Restates reference tts.py:22-61 (quick punctuation cleanup of the input text)."""
+    if len(text) == 0:
+        return "You need to add some text for me to talk."
+    if text[0].islower():
+        text = text[0].upper() + text[1:]
+    text = " ".join(text.split())
+    for old, new in [("...", ", "), ("…", ", "), (":", ","), (" - ", ", "), (";", ", "), ("—", "-"), ("–", "-"),
+                     (" ,", ","), ("“", "\""), ("”", "\""), ("‘", "'"), ("’", "'")]:
+        text = text.replace(old, new)
+    text = text.rstrip(" ")
+    if not any(text.endswith(p) for p in {".", "!", "?", "-", ","}):
+        text += "."
+    return text
+
+
+@dataclass
+class Conditionals:
+    """reference tts.py:64-103: t3 = T3Cond, gen = S3Gen ref dict."""
+    t3: T3Cond
+    gen: dict
+
+    def to(self, device):
+        self.t3 = self.t3.to(device=device)
+        for k, v in self.gen.items():
+            if torch.is_tensor(v):
+                self.gen[k] = v.to(device=device)
+        return self
+
+    def save(self, fpath):
+        torch.save(dict(t3=self.t3.__dict__, gen=self.gen), fpath)
+
+    @classmethod
+    def load(cls, fpath, map_location="cpu"):
+        kw = torch.load(fpath, map_location=map_location, weights_only=True)
+        return cls(T3Cond(**kw["t3"]), kw["gen"])
+
+
+def drop_invalid_tokens(x):
+    """reference models/s3tokenizer/__init__.py:16-30 for a 1-D tensor."""
+    x = x.reshape(-1)
+    sos = (x == SPEECH_VOCAB_SIZE).nonzero()
+    s = int(sos[0]) + 1 if len(sos) else 0
+    eos = (x == SPEECH_VOCAB_SIZE + 1).nonzero()
+    e = int(eos[0]) if len(eos) else None
+    return x[s:e]
+
+
+class ChatterboxTTS:
+    """Drop-in for reference ChatterboxTTS (tts.py:106-272); every FLOP of generate() runs in libcbx."""
+
+    def __init__(self, t3: T3, s3gen: S3Gen, tokenizer, device, conds: Conditionals = None):
+        self.sr = S3GEN_SR
+        self.t3, self.s3gen, self.tokenizer, self.device, self.conds = t3, s3gen, tokenizer, device, conds
+        self.engine = t3.engine
+
+    @classmethod
+    def from_state_dicts(cls, t3_sd, flow_sd, hift_sd, conds=None, tokenizer=None, device="cuda"):
+        idx = torch.device(device).index or 0
+        eng = Engine(idx)
+        return cls(T3(eng, t3_sd), S3Gen(eng, flow_sd, hift_sd), tokenizer, device, conds)
+
+    @classmethod
+    def from_local(cls, ckpt_dir, device="cuda"):
+        """reference tts.py:133-163: t3_cfg.safetensors, s3gen.safetensors, tokenizer.json, conds.pt."""
+        from safetensors.torch import load_file
+        ckpt_dir = Path(ckpt_dir)
+        t3_sd = load_file(ckpt_dir / "t3_cfg.safetensors")
+        if "model" in t3_sd:
+            t3_sd = t3_sd["model"][0]
+        s3 = load_file(ckpt_dir / "s3gen.safetensors")
+        flow_sd = {k[len("flow."):]: v for k, v in s3.items() if k.startswith("flow.")}
+        hift_sd = {k[len("mel2wav."):]: v for k, v in s3.items() if k.startswith("mel2wav.")}
+        tok = None
+        if (ckpt_dir / "tokenizer.json").exists():
+            from tokenizers import Tokenizer
+            tok = Tokenizer.from_file(str(ckpt_dir / "tokenizer.json"))
+        conds = Conditionals.load(ckpt_dir / "conds.pt") if (ckpt_dir / "conds.pt").exists() else None
+        return cls.from_state_dicts(t3_sd, flow_sd, hift_sd, conds, tok, device)
+
+    @classmethod
+    def from_pretrained(cls, device="cuda"):
+        """reference tts.py:165-180 (needs the HF hub cache; there is no network in the build sandbox)."""
+        from huggingface_hub import hf_hub_download
+        for f in ["t3_cfg.safetensors", "s3gen.safetensors", "tokenizer.json", "conds.pt"]:
+            local = hf_hub_download(repo_id="ResembleAI/chatterbox", filename=f)
+        return cls.from_local(Path(local).parent, device)
+
+    def prepare_conditionals(self, wav_fpath, exaggeration=0.5):
+        raise NotImplementedError("voice-prompt analysis (reference tts.py:182-206) is outside the B200 hot path; "
+                                  "load a Conditionals object produced by the reference instead")
+
+    def text_to_tokens(self, text):
+        """reference models/tokenizers/tokenizer.py:30-42 (EnTokenizer)."""
+        assert self.tokenizer is not None, "no tokenizer.json loaded; pass token ids to generate_tokens()"
+        ids = self.tokenizer.encode(text.replace(" ", "[SPACE]")).ids
+        return torch.IntTensor(ids).unsqueeze(0)
+
+    @torch.inference_mode()
+    def generate(self, text, repetition_penalty=1.2, min_p=0.05, top_p=1.0, audio_prompt_path=None, exaggeration=0.5,
+                 cfg_weight=0.5, temperature=0.8, max_new_tokens=1000, rng="torch_cpu", kv_dtype="bf16"):
+        """reference tts.py:208-272 (watermarking, tts.py:271, is a CPU post-process outside the hot path)."""
+        assert audio_prompt_path is None, "prepare_conditionals is out of scope; set .conds"
+        text_tokens = self.text_to_tokens(punc_norm(text))
+        return self.generate_tokens(text_tokens, repetition_penalty, min_p, top_p, exaggeration, cfg_weight, temperature,
+                                    max_new_tokens, rng, kv_dtype)
+
+    @torch.inference_mode()
+    def generate_tokens(self, text_tokens, repetition_penalty=1.2, min_p=0.05, top_p=1.0, exaggeration=0.5,
+                        cfg_weight=0.5, temperature=0.8, max_new_tokens=1000, rng="torch_cpu", kv_dtype="bf16",
+                        return_intermediates=False):
+        """generate() from text token ids (1, n) without SOT/EOT.  rng='torch_cpu' draws every random tensor from
+        torch's global CPU generator in the reference's order (multinomial -> randn_like(mu) -> SineGen phases ->
+        SineGen noise), so that the same torch.manual_seed gives the reference's output; rng='device' uses the
+        engine's counter RNG (throughput mode)."""
+        assert self.conds is not None, "Please set .conds (Conditionals)"
+        if float(exaggeration) != float(self.conds.t3.emotion_adv.reshape(-1)[0]):
+            c = self.conds.t3
+            self.conds.t3 = T3Cond(speaker_emb=c.speaker_emb, cond_prompt_speech_tokens=c.cond_prompt_speech_tokens,
+                                   emotion_adv=exaggeration * torch.ones(1, 1, 1))
+        tt = torch.atleast_2d(text_tokens).to(torch.long).cpu()
+        if cfg_weight > 0.0:
+            tt = torch.cat([tt, tt], dim=0)
+        tt = F.pad(F.pad(tt, (1, 0), value=SOT), (0, 1), value=EOT)
+        q = None
+        if rng == "torch_cpu":
+            state = torch.get_rng_state()
+            q = torch.stack([torch.empty(SPEECH_VOCAB).exponential_(1) for _ in range(max_new_tokens)])
+        toks = self.t3.inference(t3_cond=self.conds.t3, text_tokens=tt, max_new_tokens=max_new_tokens,
+                                 temperature=temperature, cfg_weight=cfg_weight, repetition_penalty=repetition_penalty,
+                                 min_p=min_p, top_p=top_p, q_noise=q, kv_dtype=kv_dtype)
+        if rng == "torch_cpu":      # leave the generator where the reference's loop would have left it
+            torch.set_rng_state(state)
+            for _ in range(toks.shape[1]):
+                torch.empty(SPEECH_VOCAB).exponential_(1)
+        st = drop_invalid_tokens(toks[0])
+        st = st[st < SPEECH_VOCAB_SIZE]
+        z = phase = noise = None
+        n_p = int(self.conds.gen["prompt_token"].shape[-1])
+        T = 2 * (n_p + st.numel())
+        if rng == "torch_cpu":
+            z = torch.randn(1, 80, T)[0]                                       # flow_matching.py:216
+        mel = self.s3gen.flow_inference(st, ref_dict=self.conds.gen, z=z)
+        if rng == "torch_cpu":
+            from torch.distributions.uniform import Uniform
+            phase = Uniform(low=-np.pi, high=np.pi).sample(sample_shape=(1, 9, 1))   # hifigan.py:212-214
+            phase[:, 0, :] = 0
+            noise = torch.randn(1, 9, 480 * mel.shape[-1])                      # hifigan.py:226
+            torch.randn(1, 480 * mel.shape[-1], 1)                              # hifigan.py:282 (unused draw)
+            phase, noise = phase.reshape(9), noise[0]
+        wav, src = self.s3gen.hift_inference(mel, None, phase_vec=phase, noise=noise, trim_fade=True)
+        out = wav.detach().cpu()
+        if return_intermediates:
+            return out, dict(tokens=toks, speech_tokens=st, mel=mel, source=src)
+        return out

@@ -1,0 +1,154 @@
+"""GPU unit tests of the libcbx kernels against plain torch fp32 expressions (tolerances written per test)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _eng():
+    from gpu_util import engine
+    return engine()
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("M,K,N", [(1, 1024, 3072), (2, 4096, 1024), (5, 256, 1024), (8, 1024, 8192),
+                                   (37, 1024, 1024), (128, 64, 64), (300, 320, 256), (1000, 1024, 3072),
+                                   (513, 512, 80), (260, 2048, 512)])
+def test_linear_gemm(impl, M, K, N):
+    from gpu_util import run_gemm, bf16r, relerr
+    g = torch.Generator().manual_seed(M * 7 + K + N)
+    A = torch.randn(M, K, generator=g).cuda()
+    w = bf16r(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g) * 0.1
+    C_ = run_gemm(_eng(), A, w[:, :, None].contiguous(), b, impl=impl)
+    ref = A.double() @ w.double().t().cuda() + b.double().cuda()
+    err = relerr(C_, ref)
+    # activations keep 16 significand bits (bf16 hi+lo), weights are exact, fp32 accumulation
+    assert torch.isfinite(C_).all() and err < 2e-5, f"{impl} M{M} K{K} N{N}: rel err {err}"
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("act", ["silu", "gelu", "mish", "elu", "lrelu", "snake"])
+def test_gemm_epilogues(impl, act):
+    from gpu_util import run_gemm, bf16r, relerr
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 200, 256, 128
+    A = torch.randn(M, K, generator=g).cuda()
+    w = bf16r(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g) * 0.1
+    res = torch.randn(M, N, generator=g).cuda()
+    C_ = run_gemm(_eng(), A, w[:, :, None].contiguous(), b, act=act, act_p=0.3, res=res, impl=impl)
+    y = (A.double() @ w.double().t().cuda() + b.double().cuda()).float()
+    f = dict(silu=F.silu, gelu=F.gelu, mish=F.mish, elu=F.elu, lrelu=lambda t: F.leaky_relu(t, 0.3),
+             snake=lambda t: t + (1.0 / (0.3 + 1e-9)) * torch.sin(t * 0.3) ** 2)[act]
+    ref = f(y) + res
+    err = relerr(C_, ref)
+    assert err < 3e-5, f"{impl} {act}: rel err {err}"
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_gemm_swiglu(impl):
+    from gpu_util import run_gemm, bf16r, relerr
+    g = torch.Generator().manual_seed(6)
+    for M in (2, 200):
+        K, H = 1024, 512
+        A = torch.randn(M, K, generator=g).cuda()
+        wg = bf16r(torch.randn(H, K, generator=g) / math.sqrt(K))
+        wu = bf16r(torch.randn(H, K, generator=g) / math.sqrt(K))
+        w = torch.stack([wg, wu], dim=1).reshape(2 * H, K)          # interleaved rows (gate_j, up_j)
+        C_ = run_gemm(_eng(), A, w[:, :, None].contiguous(), None, swiglu=True, impl=impl)
+        ref = F.silu(A.double() @ wg.double().t().cuda()) * (A.double() @ wu.double().t().cuda())
+        err = relerr(C_, ref)
+        assert err < 3e-5, f"{impl} M{M}: rel err {err}"
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("cin,cout,k,dil,pad,causal", [(320, 256, 3, 1, 2, True), (256, 256, 7, 3, 9, False),
+                                                      (64, 64, 11, 5, 25, False), (512, 512, 4, 1, 0, False),
+                                                      (64, 18, 7, 1, 3, False)])
+def test_conv_taps_packed(impl, cin, cout, k, dil, pad, causal):
+    """implicit-GEMM conv on a packed variable-length batch == F.conv1d per sequence (zero padding)."""
+    from gpu_util import run_gemm, bf16r, relerr
+    from chatterbox_b200.engine import PackedLayout
+    g = torch.Generator().manual_seed(cin + k)
+    lens = [70, 128, 301]
+    L = PackedLayout(lens, torch.device("cuda"))
+    x = torch.randn(L.rows, cin, generator=g).cuda()
+    w = bf16r(torch.randn(cout, cin, k, generator=g) / math.sqrt(cin * k))
+    b = torch.randn(cout, generator=g) * 0.1
+    C_ = run_gemm(_eng(), x, w, b, mode=0, dil=dil, pad=pad, stride=1, out_layout=L, in_layout=L, impl=impl)
+    for s, n in enumerate(lens):
+        xs = x[L.starts[s]:L.starts[s] + n].t()[None].double()
+        right = dil * (k - 1) - pad
+        ref = F.conv1d(F.pad(xs, (pad, right)), w.double().cuda(), b.double().cuda(), dilation=dil)[0].t()
+        got = C_[L.starts[s]:L.starts[s] + n]
+        assert relerr(got, ref) < 3e-5, f"{impl} seq{s}: {relerr(got, ref)}"
+        tail = C_[L.starts[s] + n:(L.starts[s + 1] if s + 1 < len(lens) else L.rows)]
+        assert (tail == 0).all(), "layout padding rows must be zeroed"
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("cin,cout,k,stride,pad", [(18, 256, 30, 15, 7), (18, 128, 6, 3, 1), (18, 64, 1, 1, 0),
+                                                   (80, 512, 7, 1, 3), (80, 512, 3, 1, 1)])
+def test_conv_window_strided(impl, cin, cout, k, stride, pad):
+    from gpu_util import run_gemm, bf16r, relerr
+    from chatterbox_b200.engine import PackedLayout
+    g = torch.Generator().manual_seed(cin + k + stride)
+    tin = [15 * 9 + 1, 15 * 20 + 1]
+    tout = [(t + 2 * pad - k) // stride + 1 for t in tin]
+    Lin = PackedLayout(tin, torch.device("cuda"))
+    Lout = PackedLayout(tout, torch.device("cuda"))
+    x = torch.randn(Lin.rows, cin, generator=g).cuda()
+    w = bf16r(torch.randn(cout, cin, k, generator=g) / math.sqrt(cin * k))
+    b = torch.randn(cout, generator=g) * 0.1
+    C_ = run_gemm(_eng(), x, w, b, mode=1, dil=0, pad=pad, stride=stride, out_layout=Lout, in_layout=Lin, impl=impl)
+    for s in range(2):
+        xs = x[Lin.starts[s]:Lin.starts[s] + tin[s]].t()[None].double()
+        ref = F.conv1d(xs, w.double().cuda(), b.double().cuda(), stride=stride, padding=pad)[0].t()
+        got = C_[Lout.starts[s]:Lout.starts[s] + tout[s]]
+        assert relerr(got, ref) < 3e-5, f"{impl} seq{s}: {relerr(got, ref)}"
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("causal", [False, True])
+def test_flash_attention_varlen(impl, causal):
+    from gpu_util import run_attention, relerr
+    g = torch.Generator().manual_seed(3)
+    lens, H = [5, 64, 130, 257], 8
+    from chatterbox_b200.engine import PackedLayout
+    L0 = PackedLayout(lens, torch.device("cuda"))
+    q, k, v = (torch.randn(L0.rows, H * 64, generator=g).cuda() for _ in range(3))
+    O, L = run_attention(_eng(), q, k, v, lens, H, 0.125, causal=causal, impl=impl)
+    for s, n in enumerate(lens):
+        sl = slice(L.starts[s], L.starts[s] + n)
+        sp = lambda t: t[sl].view(n, H, 64).transpose(0, 1)[None].double()
+        ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v), is_causal=causal)[0].transpose(0, 1).reshape(n, H * 64)
+        err = relerr(O[sl], ref)
+        assert err < 3e-5, f"{impl} causal={causal} seq{s} len{n}: {err}"
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_flash_attention_relpos_bias(impl):
+    """bias[h][i][center - i + j] addressing == espnet rel_shift (transformer/attention.py:225-247)."""
+    from gpu_util import run_attention, relerr
+    from oracle.flow_ref import rel_shift
+    g = torch.Generator().manual_seed(4)
+    T, H = 150, 8
+    lens = [T]
+    from chatterbox_b200.engine import PackedLayout
+    L0 = PackedLayout(lens, torch.device("cuda"))
+    q, k, v = (torch.randn(L0.rows, H * 64, generator=g).cuda() for _ in range(3))
+    Tmax = 170                                    # table built for a longer sequence
+    raw = torch.randn(H, L0.rows, 2 * Tmax - 1, generator=g).cuda()
+    O, L = run_attention(_eng(), q, k, v, lens, H, 0.125, bias=raw, bias_rel=True, bias_center=Tmax - 1, impl=impl)
+    sp = lambda t: t[:T].view(T, H, 64).transpose(0, 1)[None].double()
+    raw_T = raw[:, :T, Tmax - T:Tmax + T - 1].cpu()[None]         # the (2T-1)-wide slice the reference would see
+    bd = rel_shift(raw_T).cuda().double()
+    scores = (sp(q) @ sp(k).transpose(-1, -2) + bd) * 0.125
+    ref = (scores.softmax(-1) @ sp(v))[0].transpose(0, 1).reshape(T, H * 64)
+    err = relerr(O[:T], ref)
+    assert err < 3e-5, f"{impl}: {err}"
