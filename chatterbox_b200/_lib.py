@@ -44,6 +44,7 @@ SYMBOLS = {
     "cbx_version": (_I, []),
     "cbx_set_option": (_I, [_P, C.c_char_p, C.c_char_p]),
     "cbx_launch_count": (C.c_longlong, [_P]),
+    "cbx_timer_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "cbx_load_tensor": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(C.c_int64)]),
     "cbx_finalize_weights": (_I, [_P, C.c_char_p]),
     "cbx_t3_cond_encode": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _S, _P]),
@@ -104,6 +105,11 @@ class Handle:
 
     def launch_count(self):
         return int(self.lib.cbx_launch_count(self.h))
+
+    def timer_read(self):
+        ms, n = C.c_double(0), C.c_longlong(0)
+        self.call("cbx_timer_read", C.byref(ms), C.byref(n))
+        return float(ms.value), int(n.value)
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:

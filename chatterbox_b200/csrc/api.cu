@@ -29,6 +29,7 @@ static Ctx make_ctx(cbx_handle* h, void* ws, size_t ws_bytes, cbx_stream stream,
   c.stream = reinterpret_cast<cudaStream_t>(stream);
   c.ws.base = static_cast<char*>(ws); c.ws.cap = ws_bytes; c.ws.dry = dry; c.dry = dry;
   c.gemm_impl = h->gemm_impl; c.attn_impl = h->attn_impl;
+  c.timer = (h->timer.cls != K_NONE && !dry) ? &h->timer : nullptr;
   return c;
 }
 
@@ -83,11 +84,22 @@ int cbx_set_option(cbx_handle* h, const char* key, const char* value) {
   const std::string k = key, v = value;
   if (k == "gemm") h->gemm_impl = (v == "simt") ? 1 : 0;
   else if (k == "attn") h->attn_impl = (v == "simt") ? 1 : 0;
+  else if (k == "time_kernel") {
+    h->timer.drain(); h->timer.ms = 0.0; h->timer.n = 0;
+    h->timer.cls = v == "gemm_tc" ? K_GEMM_TC : v == "gemv" ? K_GEMV : v == "flash" ? K_FLASH : v == "paged" ? K_PAGED : K_NONE;
+  }
   else { h->err = "unknown option " + k; return CBX_ERR_INVALID; }
   return CBX_OK;
 }
 
 long long cbx_launch_count(cbx_handle* h) { return h ? h->launches : 0; }
+
+int cbx_timer_read(cbx_handle* h, double* ms, long long* launches) {
+  if (!h || !ms || !launches) return CBX_ERR_INVALID;
+  h->timer.drain();
+  *ms = h->timer.ms; *launches = h->timer.n;
+  return CBX_OK;
+}
 
 int cbx_load_tensor(cbx_handle* h, const char* name, const float* host_data, int ndim, const int64_t* shape) {
   if (!h) return CBX_ERR_INVALID;
@@ -272,6 +284,7 @@ int cbx_test_gemm(cbx_handle* h, const float* A, int lda, int M_in, int M, const
   g.Wp = W.w; g.Kpad = W.Kpad; g.Npad = W.Npad;
   g.C = C; g.ldc = ldc; g.n_out = N; g.bias = W.bias; g.alpha = 1.f; g.act = act; g.act_p = act_p; g.out_scale = 1.f;
   g.res = res; g.ldr = ldr; g.swiglu = swiglu;
+  if (act >= 100) { g.act = act - 100; g.precise = 1; }
   gemm(c, g, W);
   CBX_CHECK(cudaStreamSynchronize(c.stream));
   free_weight(W);

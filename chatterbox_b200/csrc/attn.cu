@@ -250,7 +250,9 @@ void attention(Ctx& ctx, const AttnArgs& a) {
     attn_simt_kernel<<<grid, 128, 0, ctx.stream>>>(p);
   } else {
     dim3 grid((a.max_q_len + FA_BM - 1) / FA_BM, a.n_heads, a.n_seq);
+    if (ctx.timer) ctx.timer->begin(K_FLASH, ctx.stream);
     flash_attn_kernel<<<grid, 128, 0, ctx.stream>>>(p);
+    if (ctx.timer) ctx.timer->end(K_FLASH, ctx.stream);
   }
   CBX_CHECK(cudaGetLastError());
 }
@@ -430,8 +432,10 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
   p.scale = 0.125f;
   dim3 grid(n_slots, kv.n_heads, nsplit);
   ctx.launches++;
+  if (ctx.timer) ctx.timer->begin(K_PAGED, ctx.stream);
   if (kv.kv_fp32) paged_decode_kernel<float><<<grid, 128, 0, ctx.stream>>>(p);
   else paged_decode_kernel<__nv_bfloat16><<<grid, 128, 0, ctx.stream>>>(p);
+  if (ctx.timer) ctx.timer->end(K_PAGED, ctx.stream);
   if (nsplit > 1) {
     ctx.launches++;
     paged_combine_kernel<<<dim3(n_slots, kv.n_heads), 64, 0, ctx.stream>>>(scratch, out, ldo, kv.n_heads, nsplit);

@@ -67,6 +67,7 @@ struct cbx_handle {
   cbx::HiftModel hift;
   int gemm_impl = 0, attn_impl = 0;
   long long launches = 0;
+  cbx::KTimer timer;
   std::vector<void*> owned;                      // device allocations to free
 };
 

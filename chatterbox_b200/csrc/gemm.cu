@@ -91,18 +91,22 @@ constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;   // + TMA warp + MMA warp
 
-template <int BN> struct TcCfg {
-  static constexpr int STAGES = (BN == 256) ? 3 : 4;
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;        // 16 KB per hi / lo plane
+// NS = number of bf16 planes the fp32 activations are split into: 2 keeps 16 significand bits (default),
+// 3 keeps all 24 (GemmDev::precise; used where downstream arithmetic amplifies rounding, e.g. the F0 predictor
+// whose output is integrated over ~10^6 samples by the harmonic source).
+template <int BN, int NS> struct TcCfg {
+  static constexpr int STAGES = (BN == 256 || NS == 3) ? 3 : 4;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;        // 16 KB per plane
   static constexpr int W_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + W_BYTES;
+  static constexpr int STAGE_BYTES = NS * A_BYTES + W_BYTES;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <int BN>
+template <int BN, int NS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, NS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -144,7 +148,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(&empty_bar[s], ph ^ 1);
       uint8_t* a_hi = smem + s * Cfg::STAGE_BYTES;
-      uint8_t* a_lo = a_hi + Cfg::A_BYTES;
       const int k0 = kb * TC_BK + c4 * 4;
       int tap = 0, c = k0;
       if (g.a_mode == A_TAPS) { tap = k0 / g.ctap; c = k0 - tap * g.ctap; }
@@ -168,13 +171,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         const int row = p * 16 + rsub;
-        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(v[p].x, h0, l0); split_bf16(v[p].y, h1, l1);
-        split_bf16(v[p].z, h2, l2); split_bf16(v[p].w, h3, l3);
         // SWIZZLE_128B: 16-byte chunk index XOR (row % 8); rows are 128 B apart
         const uint32_t off = row * 128 + ((((uint32_t)c4 >> 1) ^ ((uint32_t)row & 7)) << 4) + (c4 & 1) * 8;
-        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-        *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+        float r0 = v[p].x, r1 = v[p].y, r2 = v[p].z, r3 = v[p].w;
+#pragma unroll
+        for (int pl = 0; pl < NS; ++pl) {       // plane pl holds bf16(residual); residual -= plane
+          const __nv_bfloat16 b0 = __float2bfloat16_rn(r0), b1 = __float2bfloat16_rn(r1);
+          const __nv_bfloat16 b2 = __float2bfloat16_rn(r2), b3 = __float2bfloat16_rn(r3);
+          *reinterpret_cast<uint2*>(a_hi + pl * Cfg::A_BYTES + off) = make_uint2(pack_bf16(b0, b1), pack_bf16(b2, b3));
+          r0 -= __bfloat162float(b0); r1 -= __bfloat162float(b1);
+          r2 -= __bfloat162float(b2); r3 -= __bfloat162float(b3);
+        }
       }
       fence_proxy_async_smem();   // make generic-proxy stores visible to the tensor-core (async) proxy
       __syncwarp();
@@ -213,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* wdst = smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES;
+        uint8_t* wdst = smem + s * Cfg::STAGE_BYTES + NS * Cfg::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], Cfg::W_BYTES);
         tma_load_2d(wdst, &tmapW, &full_bar[s], kb * TC_BK, n0);
       }
@@ -228,13 +235,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t a_lo = a_hi + Cfg::A_BYTES;
-        const uint32_t wb = a_hi + 2 * Cfg::A_BYTES;
+        const uint32_t wb = a_hi + NS * Cfg::A_BYTES;
 #pragma unroll
         for (int k4 = 0; k4 < TC_BK / 16; ++k4) {   // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
           const uint64_t db = umma_desc_sw128(wb + k4 * 32);
-          umma_bf16(tmem_base, umma_desc_sw128(a_hi + k4 * 32), db, idesc, (kb | k4) != 0 ? 1u : 0u);
-          umma_bf16(tmem_base, umma_desc_sw128(a_lo + k4 * 32), db, idesc, 1u);
+          // smallest plane first so the fp32 accumulator adds the corrections before the leading term
+#pragma unroll
+          for (int pl = NS - 1; pl >= 0; --pl)
+            umma_bf16(tmem_base, umma_desc_sw128(a_hi + pl * Cfg::A_BYTES + k4 * 32), db, idesc,
+                      ((kb | k4) != 0 || pl != NS - 1) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);     // frees the smem stage once these MMAs have read it
       }
@@ -466,17 +475,21 @@ GemmDev gemm_args_linear(const float* A, int lda, int M, const Weight& W, float*
   return g;
 }
 
-template <int BN> static void launch_tc(Ctx& ctx, const GemmDev& g, const Weight& W, int tmap_idx) {
+template <int BN, int NS> static void launch_tc(Ctx& ctx, const GemmDev& g, const Weight& W, int tmap_idx) {
   static bool attr_set = false;
   if (!attr_set) {
-    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, NS>::SMEM));
     attr_set = true;
   }
   dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.Npad + BN - 1) / BN);
-  gemm_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], g);
+  if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
+  gemm_tc_kernel<BN, NS><<<grid, TC_THREADS, TcCfg<BN, NS>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], g);
+  if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
 }
 
 template <int R> static void launch_gemv(Ctx& ctx, const GemmDev& g) {
+  if (ctx.timer) ctx.timer->begin(K_GEMV, ctx.stream);
+  struct End { Ctx& c; ~End() { if (c.timer) c.timer->end(K_GEMV, c.stream); } } _end{ctx};
   if (g.Npad <= 2048) {
     gemv_kernel<R, 2><<<(g.Npad + 1) / 2, 128, 0, ctx.stream>>>(g);
   } else {
@@ -494,7 +507,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     gemm_simt_kernel<<<grid, 256, 0, ctx.stream>>>(g);
   } else {
     const bool plain = !g.has_seq && g.a_mode == A_TAPS && g.ntaps == 1 && g.stride == 1 && g.pad == 0 &&
-                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 &&
+                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.precise &&
                        ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
     if (plain && g.M <= 8) {
       if (g.M <= 2) launch_gemv<2>(ctx, g);
@@ -503,9 +516,12 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     } else {
       const int mt = (g.M + TC_BM - 1) / TC_BM;
       // widest N tile that still gives every SM a tile (L2->SM traffic per flop falls with BN)
-      if (g.Npad % 256 == 0 && (long)mt * (g.Npad / 256) >= 120) launch_tc<256>(ctx, g, W, 2);
-      else if (g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 100) launch_tc<128>(ctx, g, W, 1);
-      else launch_tc<64>(ctx, g, W, 0);
+      if (g.precise) {
+        if (g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 100) launch_tc<128, 3>(ctx, g, W, 1);
+        else launch_tc<64, 3>(ctx, g, W, 0);
+      } else if (g.Npad % 256 == 0 && (long)mt * (g.Npad / 256) >= 120) launch_tc<256, 2>(ctx, g, W, 2);
+      else if (g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 100) launch_tc<128, 2>(ctx, g, W, 1);
+      else launch_tc<64, 2>(ctx, g, W, 0);
     }
   }
   CBX_CHECK(cudaGetLastError());

@@ -106,12 +106,12 @@ void hift_source_run(cbx_handle* h, Ctx& ctx, const float* mel, const cbx_hift_g
   float* f0 = f0_out ? f0_out : ctx.ws.get<float>(rows);
   // ConvRNNF0Predictor (f0_predictor.py:27-55): 5 x [conv k3 pad 1, ELU] -> |Linear(512->1)|
   GemmDev g0 = window_args(mel, m.f0conv[0], 80, 3, 1, 1, LT, LT, a, 512);
-  g0.act = ACT_ELU;
+  g0.act = ACT_ELU; g0.precise = 1;   // f0 is integrated over every sample by the source: keep fp32-level accuracy
   gemm(ctx, g0, m.f0conv[0]);
   float* cur = a; float* nxt = b;
   for (int i = 1; i < 5; ++i) {
     GemmDev gi = conv_args(cur, 512, m.f0conv[i], 512, 3, 1, 1, 1, LT, LT, nxt, 512);
-    gi.act = ACT_ELU;
+    gi.act = ACT_ELU; gi.precise = 1;
     gemm(ctx, gi, m.f0conv[i]);
     float* t = cur; cur = nxt; nxt = t;
   }

@@ -43,6 +43,7 @@ struct GemmDev {
   int k_total;    // logical K (ntaps*c_in for WINDOW, ntaps*ctap for TAPS)
   int has_seq;
   SeqMap seq;
+  int precise;    // 1: split activations into 3 bf16 planes (24 significand bits) instead of 2
   // ---- B operand -------------------------------------------------------------------------------
   const __nv_bfloat16* Wp;  // [Npad][Kpad]
   int Kpad, Npad;
@@ -76,7 +77,34 @@ struct Arena {  // bump allocator over caller-owned workspace; dry=true only cou
   void reset(size_t m) { off = m; }
 };
 
+// Optional CUDA-event timer around one class of kernel launches (bench.py roofline: events on the launching stream).
+enum KClass : int { K_NONE = 0, K_GEMM_TC = 1, K_GEMV = 2, K_FLASH = 3, K_PAGED = 4 };
+struct KTimer {
+  int cls = K_NONE;
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+  size_t used = 0;
+  double ms = 0.0; long long n = 0;
+  void begin(int c, cudaStream_t st) {
+    if (c != cls) return;
+    if (used + 2 > ev.size()) {
+      if (ev.size() >= 32768) { drain(); }
+      else { size_t old = ev.size(); ev.resize(old + 2048); for (size_t i = old; i < ev.size(); ++i) cudaEventCreate(&ev[i]); }
+    }
+    cudaEventRecord(ev[used], st);
+  }
+  void end(int c, cudaStream_t st) { if (c != cls) return; cudaEventRecord(ev[used + 1], st); used += 2; }
+  void drain() {
+    for (size_t i = 0; i + 1 < used; i += 2) {
+      cudaEventSynchronize(ev[i + 1]);
+      float t = 0.f; cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      ms += t; n += 1;
+    }
+    used = 0;
+  }
+};
+
 struct Ctx {
+  KTimer* timer = nullptr;
   cudaStream_t stream = nullptr;
   Arena ws;
   bool dry = false;       // size-only pass: no launches

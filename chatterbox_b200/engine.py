@@ -102,6 +102,8 @@ class Engine:
         self._ws = None
         self.t3_layers = 0
         self.meanflow = False
+        # algorithmic-traffic bookkeeping for bench.py's roofline (bytes the paged decode attention must read)
+        self.stats = dict(paged_bytes=0.0, paged_launches=0, decode_steps=0, decode_row_steps=0)
 
     # ------------------------------------------------------------------ weights
     def _load(self, prefix, sd):
@@ -232,6 +234,13 @@ class Engine:
             d_slot = t(slot_row)
             self.h.call("cbx_t3_decode", C.byref(st), _ptr(d_act), _ptr(d_slot), len(act), k, _ptr(ws), ws.numel(),
                         self._stream())
+            # step j of this call feeds token n_gen+j at rope position S0+n_gen+j and attends S0+n_gen+j+1 tokens
+            elt = 4 if kvt == torch.float32 else 2
+            ctx_tok = (s0[act].astype(np.int64) + n_gen_h[act])[:, None] + np.arange(k)[None, :] + 1
+            self.stats["paged_bytes"] += float(ctx_tok.sum()) * rp * 2 * 1024 * elt * L
+            self.stats["paged_launches"] += k * L
+            self.stats["decode_steps"] += k
+            self.stats["decode_row_steps"] += k * len(act) * rp
             done_h = st_t["done"].cpu().numpy()          # device->host sync every k steps (reference: every step)
             n_gen_h = st_t["n_gen"].cpu().numpy().astype(np.int64)
             keep = done_h[act] == 0

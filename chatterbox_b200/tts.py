@@ -122,6 +122,93 @@ class ChatterboxTTS:
                                     max_new_tokens, rng, kv_dtype)
 
     @torch.inference_mode()
+    def generate_batch(self, text_tokens, max_new_tokens=1000, repetition_penalty=1.2, min_p=0.05, top_p=1.0,
+                       cfg_weight=0.5, temperature=0.8, seed=0, kv_dtype="bf16", to_host=True, voice_ids=None,
+                       conds_list=None, flow_frames_per_chunk=120000, hift_frames_per_chunk=24000, timings=None):
+        """Batched generate(): equal to calling the reference's generate() once per utterance (each with its own RNG
+        stream; device counter RNG, seed + utterance index).  text_tokens: list of 1-D id tensors without SOT/EOT;
+        max_new_tokens: int or per-utterance list.  Returns a list of float32 waveforms [960*N_b] (CPU if to_host)."""
+        conds_list = conds_list or [self.conds]
+        eng = self.engine
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        marks = [ev() for _ in range(5)]
+        marks[0].record()
+        B = len(text_tokens)
+        tts = [F.pad(F.pad(torch.as_tensor(t).reshape(-1).to(torch.long).cpu(), (1, 0), value=SOT), (0, 1), value=EOT)
+               for t in text_tokens]
+        spk = torch.cat([c.t3.speaker_emb.reshape(1, 256) for c in conds_list])
+        ptk = torch.cat([c.t3.cond_prompt_speech_tokens.reshape(1, -1) for c in conds_list])
+        emo = torch.stack([torch.as_tensor(c.t3.emotion_adv).reshape(-1)[0] for c in conds_list]).float()
+        cond = eng.t3_cond(spk, ptk, emo)
+        toks = eng.t3_generate(tts, cond, voice_ids=voice_ids, max_new_tokens=max_new_tokens, cfg_weight=cfg_weight,
+                               temperature=temperature, top_p=top_p, min_p=min_p,
+                               repetition_penalty=repetition_penalty, seed=seed, kv_dtype=kv_dtype)
+        marks[1].record()
+        speech = []
+        for t in toks:                                        # tts.py:257-262 per utterance
+            st = drop_invalid_tokens(t)
+            speech.append(st[st < SPEECH_VOCAB_SIZE])
+        vid = [0] * B if voice_ids is None else list(voice_ids)
+        refs = [conds_list[v].gen for v in vid]
+        order = sorted(range(B), key=lambda b: -speech[b].numel())
+        mels = [None] * B
+        i = 0
+        while i < B:                                          # chunk the packed batch by total mel frames
+            j, frames = i, 0
+            while j < B:
+                f = 2 * (int(refs[order[j]]["prompt_token"].shape[-1]) + speech[order[j]].numel())
+                if j > i and frames + f > flow_frames_per_chunk:
+                    break
+                frames += f
+                j += 1
+            idx = order[i:j]
+            out = eng.flow_mel([speech[b] for b in idx], [refs[b] for b in idx])
+            for b, m in zip(idx, out):
+                mels[b] = m
+            i = j
+        marks[2].record()
+        wavs = [None] * B
+        i = 0
+        while i < B:
+            j, frames = i, 0
+            while j < B:
+                f = int(mels[order[j]].shape[-1])
+                if j > i and frames + f > hift_frames_per_chunk:
+                    break
+                frames += f
+                j += 1
+            idx = [b for b in order[i:j] if mels[b].shape[-1] > 0]
+            if idx:
+                w, _ = eng.hift([mels[b] for b in idx], seed=seed + i, trim_fade=True)
+                for b, x in zip(idx, w):
+                    wavs[b] = x.clone()
+            for b in order[i:j]:
+                if wavs[b] is None:
+                    wavs[b] = torch.zeros(0, device=eng.device)
+            i = j
+        marks[3].record()
+        if to_host:
+            total = sum(int(w.numel()) for w in wavs)
+            host = torch.empty(total, dtype=torch.float32, pin_memory=True)
+            o = 0
+            outs = []
+            for w in wavs:
+                n = int(w.numel())
+                host[o:o + n].copy_(w, non_blocking=True)
+                outs.append(host[o:o + n])
+                o += n
+            wavs = outs
+        marks[4].record()
+        torch.cuda.synchronize()
+        if timings is not None:
+            timings.update(t3_ms=marks[0].elapsed_time(marks[1]), flow_ms=marks[1].elapsed_time(marks[2]),
+                           hift_ms=marks[2].elapsed_time(marks[3]), d2h_ms=marks[3].elapsed_time(marks[4]),
+                           audio_s=sum(int(x.numel()) for x in speech) / 25.0,
+                           d2h_bytes=sum(int(w.numel()) for w in wavs) * 4,
+                           h2d_bytes=sum(int(t.numel()) for t in tts) * 4 + int(spk.numel() + ptk.numel() + emo.numel()) * 4)
+        return wavs
+
+    @torch.inference_mode()
     def generate_tokens(self, text_tokens, repetition_penalty=1.2, min_p=0.05, top_p=1.0, exaggeration=0.5,
                         cfg_weight=0.5, temperature=0.8, max_new_tokens=1000, rng="torch_cpu", kv_dtype="bf16",
                         return_intermediates=False):

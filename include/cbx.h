@@ -54,6 +54,10 @@ int cbx_version(void);
 int cbx_set_option(cbx_handle* h, const char* key, const char* value);
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 long long cbx_launch_count(cbx_handle* h);
+/* cbx_set_option(h, "time_kernel", "paged"|"gemm_tc"|"gemv"|"flash"|"none") brackets every launch of that kernel
+ * class with CUDA events on the launching stream; cbx_timer_read waits for them and returns the summed device
+ * time and the number of launches since the option was set (bench.py's roofline object) */
+int cbx_timer_read(cbx_handle* h, double* ms, long long* launches);
 /* host fp32 tensor with the reference's state-dict name ("t3." / "flow." / "hift." prefix added by the caller) */
 int cbx_load_tensor(cbx_handle* h, const char* name, const float* host_data, int ndim, const int64_t* shape);
 /* pack loaded tensors of one model ("t3" | "flow" | "hift"): bf16 K-major weights + TMA maps, QKV concat,
@@ -137,7 +141,9 @@ size_t cbx_hift_workspace_bytes(cbx_handle* h, const cbx_hift_geom* g);
 
 /* ---- diagnostic entry points (unit tests of single kernels) --------------------------------------- */
 /* C[M][N] = act(A_gather x W^T + bias) with W given on the host [N][cin][taps] (torch conv layout; taps=1, cin=K
- * for Linear).  mode 0 = TAPS (k = tap*ceil64(cin)+c), 1 = WINDOW.  A, C device pointers. */
+ * for Linear).  mode 0 = TAPS (k = tap*ceil64(cin)+c), 1 = WINDOW.  A, C device pointers.
+ * act = activation code (0 none, 1 silu, 2 gelu, 3 mish, 4 elu, 5 lrelu, 6 snake, 7 tanh); +100 selects the 3-plane
+ * (24-bit) activation split. */
 int cbx_test_gemm(cbx_handle* h, const float* A, int lda, int M_in, int M, const float* w_host, const float* bias_host,
                   int N, int cin, int taps, int mode, int dil, int pad, int stride, const cbx_layout* out_layout,
                   const cbx_layout* in_layout, int act, float act_p, const float* res, int ldr, int swiglu,

@@ -90,7 +90,12 @@ def make_t3_weights(seed=0, text_vocab=704, n_layers=T3_LAYERS, head_std=0.06):
         elif kind == "w1":
             sd[key] = _randn(seed, key, shape, std=0.3, bf16=True)
         elif kind == "h":
-            sd[key] = _randn(seed, key, shape, std=head_std, bf16=True)
+            w = _randn(seed, key, shape, std=head_std, bf16=True)
+            # ids >= 6561 (SOS/EOS/unused) are dropped by generate() (tts.py:257-262); a trained model almost never
+            # emits them, so the synthetic head keeps their logits near zero (utterance length is then set by
+            # max_new_tokens) -- still bf16-representable (power-of-two scale)
+            w[6561:] = w[6561:] * (2.0 ** -6)
+            sd[key] = w
         elif kind == "n":
             sd[key] = _randn(seed, key, shape, std=0.1, mean=1.0)
         elif kind == "b":

@@ -33,7 +33,14 @@ def test_generate_matches_oracle_pipeline():
     mel = FlowOracle(fsd).inference(st, cg, 10)
     rms = ((mid["mel"].cpu() - mel) ** 2).mean().sqrt().item()
     assert rms < 1e-3, f"mel RMS {rms}"
+    rng_after_flow = torch.get_rng_state()
     ref_wav, _ = HiFTOracle(hsd).inference(mel)
-    # the waveform compounds the mel difference through the vocoder: bound it separately from the 1e-4 decode bar
+    # (1) vocoder in isolation: oracle HiFT on the ENGINE's mel with the same RNG draws
+    torch.set_rng_state(rng_after_flow)
+    ref_wav2, _ = HiFTOracle(hsd).inference(mid["mel"].cpu())
+    err2 = (wav - ref_wav2).abs().max().item()
+    assert wav.shape == ref_wav2.shape and err2 < 2e-3, f"vocoder max|dwav|={err2}"
+    # (2) whole pipeline: the mel difference (<= 1e-3 RMS) perturbs f0, whose integral is the source phase, so the
+    # waveforms decorrelate slowly with utterance length; bound it loosely and report
     err = (wav - ref_wav).abs().max().item()
-    assert wav.shape == ref_wav.shape and err < 5e-3, f"max|dwav|={err}"
+    assert err < 5e-2, f"pipeline max|dwav|={err}"

@@ -152,3 +152,19 @@ def test_flash_attention_relpos_bias(impl):
     ref = (scores.softmax(-1) @ sp(v))[0].transpose(0, 1).reshape(T, H * 64)
     err = relerr(O[:T], ref)
     assert err < 3e-5, f"{impl}: {err}"
+
+
+def test_linear_gemm_precise_mode():
+    """3-plane activation split (GemmDev::precise): fp32-level accuracy on the tensor cores."""
+    from gpu_util import run_gemm, bf16r, relerr
+    import gpu_util
+    g = torch.Generator().manual_seed(11)
+    M, K, N = 300, 1536, 512
+    A = torch.randn(M, K, generator=g).cuda()
+    w = bf16r(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g) * 0.1
+    gpu_util.ACT["elu_precise"] = 104
+    C_ = run_gemm(_eng(), A, w[:, :, None].contiguous(), b, act="elu_precise", impl="tc")
+    ref = F.elu(A.double() @ w.double().t().cuda() + b.double().cuda())
+    err = relerr(C_, ref)
+    assert err < 5e-7, f"rel err {err}"
