@@ -26,6 +26,12 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_T0 = time.time()
+
+
+def log(*a):
+    if os.environ.get("CBX_BENCH_VERBOSE", "1") != "0" and int(os.environ.get("RANK", 0)) == 0:
+        print(f"[bench {time.time() - _T0:7.1f}s]", *a, file=sys.stderr, flush=True)
 
 METRIC = "audio_seconds_per_second"
 UNIT = "audio-s/s"
@@ -39,12 +45,12 @@ def load_peaks():
     return 6650.0, 1400.0, "fallback"
 
 
-def make_workload(batch, seed, rank):
+def make_workload(batch, seed, rank, budget_max=1000):
     """N_text ~ randint(16,160), ids randint(1,255), N ~ randint(75,1000)."""
     g = torch.Generator().manual_seed(seed + 7919 * rank)
     n_text = torch.randint(16, 160, (batch,), generator=g)
     texts = [torch.randint(1, 255, (int(n),), generator=g) for n in n_text]
-    budgets = torch.randint(75, 1000, (batch,), generator=g).tolist()
+    budgets = torch.randint(min(75, budget_max - 1), budget_max, (batch,), generator=g).tolist()
     return texts, budgets
 
 
@@ -167,7 +173,8 @@ def run_engine(args, rank, world, local_rank):
     cg = dict(prompt_token=parts[3].reshape(1, -1).long(), prompt_token_len=torch.tensor([parts[3].numel()]),
               prompt_feat=parts[4].reshape(1, -1, 80), prompt_feat_len=None, embedding=parts[5].reshape(1, 192))
     tts = ChatterboxTTS(t3, s3, None, f"cuda:{local_rank}", Conditionals(T3Cond(**c3), cg))
-    texts, budgets = make_workload(args.batch, 20260922, rank)
+    texts, budgets = make_workload(args.batch, 20260922, rank, args.budget_max)
+    log(f"models loaded; batch={args.batch} sum_budget={sum(budgets)}")
 
     def one_pass(to_host, timings):
         return tts.generate_batch(texts, max_new_tokens=budgets, seed=1000 * rank, kv_dtype="bf16", to_host=to_host,
@@ -198,8 +205,10 @@ def run_engine(args, rank, world, local_rank):
             ms, wall = float(t[0]), float(t[1]) / 1000.0
         return ms, wall, tm_all
 
-    for _ in range(args.warmup):
-        one_pass(False, {})
+    for i in range(args.warmup):
+        tmw = {}
+        one_pass(False, tmw)
+        log(f"warmup {i}: " + json.dumps({k: (round(v, 1) if isinstance(v, float) else v) for k, v in tmw.items()}))
     launches0 = eng.h.launch_count()
     eng.stats.update(paged_bytes=0.0, paged_launches=0, decode_steps=0, decode_row_steps=0)
     eng.h.set_option("time_kernel", "paged")
@@ -208,6 +217,7 @@ def run_engine(args, rank, world, local_rank):
         clocks.start()
     ms, wall, tms = timed(False, args.steps)
     clk = clocks.stop() if rank == 0 else None
+    log(f"timed: {ms:.1f} ms for {args.steps} steps")
     paged_ms, paged_n = eng.h.timer_read()
     eng.h.set_option("time_kernel", "none")
     launches = eng.h.launch_count() - launches0
@@ -263,12 +273,15 @@ def run_engine(args, rank, world, local_rank):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("CBX_BENCH_WATCHDOG", 1500)), exit=True, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--budget-max", type=int, default=1000, help="upper bound of the per-utterance token budget (debug)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -55,7 +55,7 @@ SYMBOLS = {
     "cbx_flow_encode": (_I, [_P, _P, C.POINTER(Layout), C.POINTER(Layout), _P, _P, _P, _P, _S, _P]),
     "cbx_cfm_solve": (_I, [_P, _P, _P, _P, _P, C.POINTER(Layout), C.POINTER(Layout), _I, _F, _I, _P, _S, _P]),
     "cbx_flow_workspace_bytes": (_S, [_P, C.POINTER(Layout), C.POINTER(Layout), C.POINTER(Layout)]),
-    "cbx_hift_source": (_I, [_P, _P, C.POINTER(HiftGeom), _P, _P, C.c_ulonglong, _P, _P, _P, _S, _P]),
+    "cbx_hift_source": (_I, [_P, _P, C.POINTER(HiftGeom), _P, _P, C.c_ulonglong, _P, _P, _P, _P, _S, _P]),
     "cbx_hift_decode": (_I, [_P, _P, _P, C.POINTER(HiftGeom), _P, _I, _P, _S, _P]),
     "cbx_hift_workspace_bytes": (_S, [_P, C.POINTER(HiftGeom)]),
     "cbx_test_gemm": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(Layout), C.POINTER(Layout),

@@ -236,11 +236,12 @@ size_t cbx_flow_workspace_bytes(cbx_handle* h, const cbx_layout* L1, const cbx_l
 
 // ---- hift -----------------------------------------------------------------------------------------
 int cbx_hift_source(cbx_handle* h, const float* mel, const cbx_hift_geom* g, const float* phase_vec, const float* noise,
-                    unsigned long long seed, float* s_out, float* f0_out, void* ws, size_t ws_bytes, cbx_stream stream) {
+                    unsigned long long seed, float* s_out, const float* f0_in, float* f0_out, void* ws, size_t ws_bytes,
+                    cbx_stream stream) {
   if (!h || !g) return CBX_ERR_INVALID;
   CBX_GUARD_BEGIN
   Ctx c = make_ctx(h, ws, ws_bytes, stream);
-  hift_source_run(h, c, mel, *g, phase_vec, noise, seed, s_out, f0_out);
+  hift_source_run(h, c, mel, *g, phase_vec, noise, seed, s_out, f0_in, f0_out);
   h->launches += c.launches;
   CBX_GUARD_END(h)
 }
@@ -257,7 +258,7 @@ size_t cbx_hift_workspace_bytes(cbx_handle* h, const cbx_hift_geom* g) {
   if (!h || !g) return 0;
   try {
     Ctx c = make_ctx(h, nullptr, 0, nullptr, true);
-    hift_source_run(h, c, nullptr, *g, nullptr, nullptr, 0, nullptr, nullptr);
+    hift_source_run(h, c, nullptr, *g, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
     Ctx d = make_ctx(h, nullptr, 0, nullptr, true);
     hift_decode_run(h, d, nullptr, nullptr, *g, nullptr, 1);
     return (c.ws.peak > d.ws.peak ? c.ws.peak : d.ws.peak) + (1 << 20);

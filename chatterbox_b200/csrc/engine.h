@@ -88,7 +88,7 @@ void cfm_solve(cbx_handle* h, Ctx& ctx, const float* mu, const float* spk, const
                const cbx_layout& L2, const cbx_layout& L3, int n_steps, float cfg_rate, int meanflow);
 void hift_finalize(cbx_handle* h);
 void hift_source_run(cbx_handle* h, Ctx& ctx, const float* mel, const cbx_hift_geom& g, const float* phase_vec,
-                     const float* noise, unsigned long long seed, float* s_out, float* f0_out);
+                     const float* noise, unsigned long long seed, float* s_out, const float* f0_in, float* f0_out);
 void hift_decode_run(cbx_handle* h, Ctx& ctx, const float* mel, const float* s, const cbx_hift_geom& g, float* wav,
                      int trim_fade);
 

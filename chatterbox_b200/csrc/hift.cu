@@ -96,7 +96,7 @@ static GemmDev window_args(const float* A, const Weight& W, int c_in, int ntaps,
 }
 
 void hift_source_run(cbx_handle* h, Ctx& ctx, const float* mel, const cbx_hift_geom& g, const float* phase_vec,
-                     const float* noise, unsigned long long seed, float* s_out, float* f0_out) {
+                     const float* noise, unsigned long long seed, float* s_out, const float* f0_in, float* f0_out) {
   HiftModel& m = h->hift;
   CBX_REQUIRE(m.ready, "hift weights not finalized");
   const cbx_layout& LT = g.LT;
@@ -106,16 +106,17 @@ void hift_source_run(cbx_handle* h, Ctx& ctx, const float* mel, const cbx_hift_g
   float* f0 = f0_out ? f0_out : ctx.ws.get<float>(rows);
   // ConvRNNF0Predictor (f0_predictor.py:27-55): 5 x [conv k3 pad 1, ELU] -> |Linear(512->1)|
   GemmDev g0 = window_args(mel, m.f0conv[0], 80, 3, 1, 1, LT, LT, a, 512);
-  g0.act = ACT_ELU; g0.precise = 1;   // f0 is integrated over every sample by the source: keep fp32-level accuracy
+  g0.act = ACT_ELU;
   gemm(ctx, g0, m.f0conv[0]);
   float* cur = a; float* nxt = b;
   for (int i = 1; i < 5; ++i) {
     GemmDev gi = conv_args(cur, 512, m.f0conv[i], 512, 3, 1, 1, 1, LT, LT, nxt, 512);
-    gi.act = ACT_ELU; gi.precise = 1;
+    gi.act = ACT_ELU;
     gemm(ctx, gi, m.f0conv[i]);
     float* t = cur; cur = nxt; nxt = t;
   }
   f0_head(ctx, cur, 512, m.f0_w.p, m.f0_b, f0, rows);
+  if (f0_in) f0 = const_cast<float*>(f0_in);
   float* cumf = ctx.ws.get<float>((size_t)g.total_samples * 9);
   hift_source(ctx, f0, cumf, phase_vec, noise, m.src_w.p, m.src_b, s_out, LT.start, LT.len,
               reinterpret_cast<const long*>(g.sample_start), LT.n_seq, LT.max_len, seed);

@@ -226,8 +226,12 @@ class Engine:
         act = np.arange(B, dtype=np.int32)
         n_gen_h = np.zeros(B, dtype=np.int64)
         budget = np.asarray(max_new, dtype=np.int64)
+        import os as _os
+        _trace = _os.environ.get("CBX_TRACE")
         while len(act):
             remaining = budget[act] - n_gen_h[act]
+            if _trace:
+                print("[cbx] decode", len(act), int(remaining.min()), int(n_gen_h.max()), flush=True)
             k = int(max(1, min(max_sync_steps, remaining.min())))
             d_act = t(act)
             slot_row = (np.repeat(act * rp, rp) + np.tile(np.arange(rp), len(act))).astype(np.int32)
@@ -327,7 +331,7 @@ class Engine:
         keep = (LT, L8, L40, L120, sstart)
         return g, keep
 
-    def hift(self, mels, source=None, phase_vec=None, noise=None, seed=0, trim_fade=True):
+    def hift(self, mels, source=None, phase_vec=None, noise=None, seed=0, trim_fade=True, f0=None):
         """Batched equivalent of S3Token2Wav.hift_inference + trim-fade (s3gen.py:324-327,359-360).
         mels: list of [80, T] tensors.  source: optional list of [1, 480T] (reference cache_source hook);
         phase_vec: optional list of [9]; noise: optional list of [9, 480T] (SineGen draws, hifigan.py:212-226).
@@ -354,8 +358,13 @@ class Engine:
                 for b in range(B):
                     o = int(LT.starts[b]) * 480 * 9
                     nz[o:o + 9 * 480 * int(T[b])] = noise[b].reshape(-1).to(dev, torch.float32)
-            self.h.call("cbx_hift_source", _ptr(mel), C.byref(g), _ptr(pv), _ptr(nz), int(seed), _ptr(s), C.c_void_p(0),
-                        _ptr(ws), ws.numel(), self._stream())
+            f0d = None
+            if f0 is not None:         # inject the reference's f0 (unit-test hook)
+                f0d = torch.zeros(LT.rows, dtype=torch.float32, device=dev)
+                for b in range(B):
+                    f0d[int(LT.starts[b]):int(LT.starts[b]) + int(T[b])] = f0[b].reshape(-1).to(dev, torch.float32)
+            self.h.call("cbx_hift_source", _ptr(mel), C.byref(g), _ptr(pv), _ptr(nz), int(seed), _ptr(s), _ptr(f0d),
+                        C.c_void_p(0), _ptr(ws), ws.numel(), self._stream())
         else:
             for b in range(B):
                 o = int(LT.starts[b]) * 480
@@ -381,6 +390,6 @@ class Engine:
         s = torch.zeros(int(LT.rows) * 480, dtype=torch.float32, device=dev)
         f0 = torch.zeros(LT.rows, dtype=torch.float32, device=dev)
         ws = self.workspace(self.h.lib.cbx_hift_workspace_bytes(self.h.h, C.byref(g)))
-        self.h.call("cbx_hift_source", _ptr(mel), C.byref(g), C.c_void_p(0), C.c_void_p(0), 0, _ptr(s), _ptr(f0), _ptr(ws),
-                    ws.numel(), self._stream())
+        self.h.call("cbx_hift_source", _ptr(mel), C.byref(g), C.c_void_p(0), C.c_void_p(0), 0, _ptr(s), C.c_void_p(0),
+                    _ptr(f0), _ptr(ws), ws.numel(), self._stream())
         return [f0[int(LT.starts[b]):int(LT.starts[b]) + int(T[b])] for b in range(len(mels))]

@@ -34,7 +34,7 @@ class S3Gen:
         return mel[None]
 
     @torch.inference_mode()
-    def hift_inference(self, speech_feat, cache_source=None, phase_vec=None, noise=None, seed=0, trim_fade=False):
+    def hift_inference(self, speech_feat, cache_source=None, phase_vec=None, noise=None, seed=0, trim_fade=False, f0=None):
         """reference s3gen.py:324-327 -> (wav (1, 480T), source (1, 1, 480T))."""
         src = None
         if cache_source is not None and cache_source.numel() > 0:
@@ -42,7 +42,8 @@ class S3Gen:
             src = [cache_source]
         wavs, srcs = self.engine.hift([speech_feat[0]], source=src,
                                       phase_vec=None if phase_vec is None else [phase_vec],
-                                      noise=None if noise is None else [noise], seed=seed, trim_fade=trim_fade)
+                                      noise=None if noise is None else [noise], seed=seed, trim_fade=trim_fade,
+                                      f0=None if f0 is None else [f0])
         return wavs[0][None], srcs[0][None, None]
 
     @torch.inference_mode()

@@ -128,6 +128,8 @@ class ChatterboxTTS:
         """Batched generate(): equal to calling the reference's generate() once per utterance (each with its own RNG
         stream; device counter RNG, seed + utterance index).  text_tokens: list of 1-D id tensors without SOT/EOT;
         max_new_tokens: int or per-utterance list.  Returns a list of float32 waveforms [960*N_b] (CPU if to_host)."""
+        import os, sys, time
+        trace = (lambda *a: print("[cbx]", f"{time.time():.1f}", *a, file=sys.stderr, flush=True)) if os.environ.get("CBX_TRACE") else (lambda *a: None)
         conds_list = conds_list or [self.conds]
         eng = self.engine
         ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -144,6 +146,7 @@ class ChatterboxTTS:
                                temperature=temperature, top_p=top_p, min_p=min_p,
                                repetition_penalty=repetition_penalty, seed=seed, kv_dtype=kv_dtype)
         marks[1].record()
+        trace("t3 done", [int(t.numel()) for t in toks][:8])
         speech = []
         for t in toks:                                        # tts.py:257-262 per utterance
             st = drop_invalid_tokens(t)
@@ -162,6 +165,7 @@ class ChatterboxTTS:
                 frames += f
                 j += 1
             idx = order[i:j]
+            trace("flow chunk", i, j, frames)
             out = eng.flow_mel([speech[b] for b in idx], [refs[b] for b in idx])
             for b, m in zip(idx, out):
                 mels[b] = m
@@ -178,6 +182,7 @@ class ChatterboxTTS:
                 frames += f
                 j += 1
             idx = [b for b in order[i:j] if mels[b].shape[-1] > 0]
+            trace("hift chunk", i, j, frames)
             if idx:
                 w, _ = eng.hift([mels[b] for b in idx], seed=seed + i, trim_fade=True)
                 for b, x in zip(idx, w):

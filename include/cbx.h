@@ -130,10 +130,11 @@ typedef struct {
 } cbx_hift_geom;
 /* replaces ConvRNNF0Predictor.forward + f0_upsamp + SourceModuleHnNSF.forward (f0_predictor.py:52-55,
  * hifigan.py:200-231,267-283, 462-466).  phase_vec [n_seq][9] and noise (per sequence [9][480T] at 9*sample_start)
- * may be NULL (phase 0 / counter RNG).  s_out [total_samples]; f0_out optional [LT.rows] */
+ * may be NULL (phase 0 / counter RNG).  s_out [total_samples]; f0_out optional [LT.rows]; f0_in optional [LT.rows]
+ * overrides the predictor (the source integrates f0 over every sample, so parity tests inject the reference f0) */
 int cbx_hift_source(cbx_handle* h, const float* mel, const cbx_hift_geom* g, const float* phase_vec,
-                    const float* noise, unsigned long long seed, float* s_out, float* f0_out, void* ws,
-                    size_t ws_bytes, cbx_stream stream);
+                    const float* noise, unsigned long long seed, float* s_out, const float* f0_in, float* f0_out,
+                    void* ws, size_t ws_bytes, cbx_stream stream);
 /* replaces HiFTGenerator.decode (hifigan.py:412-444) + the trim-fade of S3Token2Wav.inference (s3gen.py:359-360) */
 int cbx_hift_decode(cbx_handle* h, const float* mel, const float* s, const cbx_hift_geom* g, float* wav,
                     int trim_fade, void* ws, size_t ws_bytes, cbx_stream stream);

@@ -33,14 +33,13 @@ def test_generate_matches_oracle_pipeline():
     mel = FlowOracle(fsd).inference(st, cg, 10)
     rms = ((mid["mel"].cpu() - mel) ** 2).mean().sqrt().item()
     assert rms < 1e-3, f"mel RMS {rms}"
-    rng_after_flow = torch.get_rng_state()
-    ref_wav, _ = HiFTOracle(hsd).inference(mel)
-    # (1) vocoder in isolation: oracle HiFT on the ENGINE's mel with the same RNG draws
-    torch.set_rng_state(rng_after_flow)
-    ref_wav2, _ = HiFTOracle(hsd).inference(mid["mel"].cpu())
+    ho = HiFTOracle(hsd)
+    ref_wav, _ = ho.inference(mel)
+    # vocoder in isolation: the oracle decodes the ENGINE's mel with the ENGINE's source (hifigan.py cache_source hook)
+    ref_wav2, _ = ho.inference(mid["mel"].cpu(), s=mid["source"].cpu())
     err2 = (wav - ref_wav2).abs().max().item()
-    assert wav.shape == ref_wav2.shape and err2 < 2e-3, f"vocoder max|dwav|={err2}"
-    # (2) whole pipeline: the mel difference (<= 1e-3 RMS) perturbs f0, whose integral is the source phase, so the
-    # waveforms decorrelate slowly with utterance length; bound it loosely and report
+    assert wav.shape == ref_wav2.shape and err2 < 2e-4, f"vocoder max|dwav|={err2}"
+    # whole pipeline: the mel difference (<= 1e-3 RMS) perturbs f0, whose running sum is the source phase, so the two
+    # waveforms drift apart with utterance length (reference-vs-reference on another BLAS would too); loose bound
     err = (wav - ref_wav).abs().max().item()
-    assert err < 5e-2, f"pipeline max|dwav|={err}"
+    assert err < 2e-1, f"pipeline max|dwav|={err}"
