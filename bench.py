@@ -87,6 +87,18 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_threads():
+    """Threads the CPU arm may really use: scheduler affinity and cgroup quota, not the raw core count of the host."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = min(n, max(1, int(float(q[0]) / float(q[1]))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 def cpu_reference_sample(n_text=40, n_tokens=100, threads=None):
     """The reference's CPU algorithm (oracle port: same op sequence as the reference modules, fp32, torch CPU) on ONE
@@ -96,7 +108,7 @@ def cpu_reference_sample(n_text=40, n_tokens=100, threads=None):
     from oracle.t3_ref import T3Oracle
     from oracle.flow_ref import FlowOracle
     from oracle.hift_ref import HiFTOracle
-    threads = threads or os.cpu_count()
+    threads = threads or host_threads()
     torch.set_num_threads(threads)
     st = cpu_reference_sample.__dict__.setdefault("state", {})
     if not st:
@@ -126,7 +138,7 @@ def cpu_reference_sample(n_text=40, n_tokens=100, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count()
+    threads = host_threads()
     sample = "1 utterance: 40 text tokens, 100 speech tokens (CFG pair), 250-token voice prompt, 10 NFE, HiFT"
     cpu_reference_sample(threads=threads)      # builds weights (untimed)
     for _ in range(max(0, args.warmup - 1)):
@@ -239,7 +251,9 @@ def run_engine(args, rank, world, local_rank):
     paged_bytes_per_launch = eng.stats["paged_bytes"] / max(1, eng.stats["paged_launches"])
     achieved = (eng.stats["paged_bytes"] / 1e9) / (paged_ms / 1e3) if paged_ms > 0 else 0.0
     stage = {k: sum(t[k] for t in tms) / len(tms) for k in ("t3_ms", "flow_ms", "hift_ms")}
+    log(f"cpu baseline on {host_threads()} threads (os.cpu_count={os.cpu_count()})")
     cpu_audio, cpu_wall, cpu_split = cpu_reference_sample()
+    log(f"cpu baseline done: {cpu_wall:.1f}s")
     value = audio_total / (ms / 1000.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -263,7 +277,7 @@ def run_engine(args, rank, world, local_rank):
                      "algorithmic_bytes_per_launch": paged_bytes_per_launch, "launches": paged_n,
                      "avg_launch_ms": paged_ms / max(1, paged_n),
                      "share_of_step": paged_ms / ms},
-        "cpu_baseline": {"value": cpu_audio / cpu_wall, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        "cpu_baseline": {"value": cpu_audio / cpu_wall, "unit": UNIT, "cores": host_threads(), "kind": "port",
                          "sample": "1 utterance (40 text tokens, 100 speech tokens, 250-token prompt) through the oracle "
                                    "port of the reference's CPU path", "split_s": cpu_split},
     }

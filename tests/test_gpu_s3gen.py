@@ -77,8 +77,10 @@ def test_f0_predictor_matches_oracle(golden_dir):
     for case in g["cases"]:
         f0 = s3.engine.hift_f0([case["mel"][0]])[0].cpu()
         ref = ho.f0_predictor(case["mel"])[0]
-        err = ((f0 - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
-        assert err < 3e-5, f"f0 rel err {err}"       # two different fp32 accumulation orders over K=1536
+        # |Linear(512->1)| of a 5-conv stack: the synthetic classifier (weights ~8, bias 25) sums ~+-200 Hz of
+        # cancelling terms, so fp32 accumulation-order noise (1e-6 relative of that) is ~2e-4 Hz absolute
+        err = (f0 - ref).abs().max().item()
+        assert err < 2e-3, f"f0 abs err {err} Hz"
 
 
 def test_hift_source_matches_reference(golden_dir):
