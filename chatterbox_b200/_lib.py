@@ -61,6 +61,7 @@ SYMBOLS = {
     "cbx_test_gemm": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(Layout), C.POINTER(Layout),
                            _I, _F, _P, _I, _I, _P, _I, _P]),
     "cbx_test_attention": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, C.POINTER(Layout), _F, _I, _P, C.c_longlong, _I, _I, _I, _P]),
+    "cbx_test_attention_tc": (_I, [_P, _P, _P, _I, C.POINTER(Layout), _F, _P, _S, _P]),
 }
 
 _lib = None

@@ -308,4 +308,26 @@ int cbx_test_attention(cbx_handle* h, const float* Q, const float* K, const floa
   CBX_GUARD_END(h)
 }
 
+int cbx_test_attention_tc(cbx_handle* h, const float* qkv, float* O, int n_heads, const cbx_layout* L, float scale,
+                          void* ws, size_t ws_bytes, cbx_stream stream) {
+  if (!h || !L) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  const int ld = 3 * n_heads * 64;
+  __nv_bfloat16* hi = c.ws.get<__nv_bfloat16>((size_t)L->rows * ld);
+  __nv_bfloat16* lo = c.ws.get<__nv_bfloat16>((size_t)L->rows * ld);
+  pack_hilo(c, qkv, ld, L->rows, ld, hi, lo, L->rows, ld);
+  CUtensorMap tmh, tml;
+  make_plane_tmap(&tmh, hi, L->rows, ld);
+  make_plane_tmap(&tml, lo, L->rows, ld);
+  AttnTcArgs a;
+  a.tm_hi = &tmh; a.tm_lo = &tml; a.q_col = 0; a.k_col = n_heads * 64; a.v_col = 2 * n_heads * 64; a.O = O;
+  a.ldo = n_heads * 64; a.n_seq = L->n_seq; a.n_heads = n_heads; a.q_start = L->start; a.q_len = L->len;
+  a.kv_start = L->start; a.kv_len = L->len; a.max_q_len = L->max_len; a.scale = scale;
+  attention_tc(c, a);
+  CBX_CHECK(cudaStreamSynchronize(c.stream));
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+
 }  // extern "C"

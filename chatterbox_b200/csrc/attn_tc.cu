@@ -1,0 +1,278 @@
+// tcgen05 flash attention for the CFM estimator blocks (non-causal, key-length mask, head_dim 64).
+//
+// One CTA = 128 queries x 1 head of one sequence; key blocks of 64.  Operands are the bf16 hi/lo planes the QKV
+// GEMM epilogue writes ([rows][1536] bf16 each), moved by TMA (SWIZZLE_128B):
+//   S = Q K^T      tcgen05.mma M128 N64 K64, 3 terms (hi.hi + hi.lo + lo.hi)  -> TMEM (double buffered)
+//   softmax        4 warps, one query row per thread (tcgen05.ld 64 columns), online max / sum in fp32,
+//                  P split into bf16 hi/lo and written to swizzled smem as the next A operand
+//   PV = P V       tcgen05.mma M128 N64 K64, V consumed in its natural [key][d] layout as an MN-major B operand
+//   O accumulate   in registers (O = O * exp(m_old - m_new) + PV), normalised and stored as fp32
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = softmax / correction / epilogue.
+#include "ops.h"
+
+namespace cbx {
+
+constexpr int AT_BM = 128, AT_BN = 64, AT_STAGES = 3;
+constexpr int AT_TILE = AT_BN * 128;                 // 64 rows x 128 B = 8 KB (one plane of a 64-row tile)
+constexpr int AT_Q_BYTES = 2 * 2 * AT_TILE;          // 128 rows x 2 planes = 32 KB
+constexpr int AT_KV_STAGE = 4 * AT_TILE;             // K hi, K lo, V hi, V lo = 32 KB
+constexpr int AT_P_BYTES = 2 * 2 * AT_TILE;          // P hi, P lo (128 rows each) = 32 KB
+constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * AT_KV_STAGE + AT_P_BYTES + 1024 + 256;
+constexpr int AT_THREADS = 192;
+
+struct AttnTcDev {
+  float* O; int ldo;
+  const int* q_start; const int* q_len; const int* kv_start; const int* kv_len;
+  float scale_log2e;      // softmax scale * log2(e)
+  int q_col, k_col, v_col;   // column offsets of head 0 inside the packed planes
+};
+
+// MN-major SWIZZLE_128B descriptor (B operand stored [k][n], n contiguous, 64 n = one 128-byte row):
+// 8 k-rows per 1024-byte atom, atoms along k are SBO = 1024 B apart (cute/arch/mma_sm100_desc.hpp).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 16;     // leading byte offset: next 64-wide n atom (unused, N = 64)
+  d |= (uint64_t)(1024 >> 4) << 32;     // stride byte offset: next group of 8 k rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const AttnTcDev p) {
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
+  const int q0 = blockIdx.x * AT_BM;
+  if (q0 >= qlen) return;
+  const int qrow0 = p.q_start[seq] + q0, krow0 = p.kv_start[seq];
+  const int nblk = (kvlen + AT_BN - 1) / AT_BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [hi: 128 rows][lo: 128 rows]
+  uint8_t* sKV = sQ + AT_Q_BYTES;                       // stages of [Khi][Klo][Vhi][Vlo]
+  uint8_t* sP = sKV + AT_STAGES * AT_KV_STAGE;          // [hi: 128 rows][lo: 128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* kv_full = bars + 1;             // [STAGES]
+  uint64_t* kv_empty = kv_full + AT_STAGES; // [STAGES]
+  uint64_t* s_full = kv_empty + AT_STAGES;  // [2]
+  uint64_t* s_empty = s_full + 2;           // [2]
+  uint64_t* p_full = s_empty + 2;           // 1
+  uint64_t* pv_full = p_full + 1;           // 1
+  uint64_t* pv_empty = pv_full + 1;         // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
+    mbar_init(p_full, 4); mbar_init(pv_full, 1); mbar_init(pv_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_hi); tma_prefetch_desc(&tm_lo); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS0 = tmem_base, tS1 = tmem_base + 64, tPV = tmem_base + 128;
+
+  if (warp == 0) {
+    // ===================== TMA producer ===============================================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
+      const int qc = p.q_col + head * 64;
+      tma_load_2d(sQ, &tm_hi, q_full, qc, qrow0);
+      tma_load_2d(sQ + AT_TILE, &tm_hi, q_full, qc, qrow0 + 64);
+      tma_load_2d(sQ + 2 * AT_TILE, &tm_lo, q_full, qc, qrow0);
+      tma_load_2d(sQ + 3 * AT_TILE, &tm_lo, q_full, qc, qrow0 + 64);
+      const int kc = p.k_col + head * 64, vc = p.v_col + head * 64;
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % AT_STAGES;
+        mbar_wait(&kv_empty[s], ((j / AT_STAGES) & 1) ^ 1);
+        uint8_t* st = sKV + s * AT_KV_STAGE;
+        mbar_arrive_expect_tx(&kv_full[s], AT_KV_STAGE);
+        const int r = krow0 + j * AT_BN;
+        tma_load_2d(st, &tm_hi, &kv_full[s], kc, r);
+        tma_load_2d(st + AT_TILE, &tm_lo, &kv_full[s], kc, r);
+        tma_load_2d(st + 2 * AT_TILE, &tm_hi, &kv_full[s], vc, r);
+        tma_load_2d(st + 3 * AT_TILE, &tm_lo, &kv_full[s], vc, r);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN);                 // A K-major, B K-major
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BM, 64) | (1u << 16);      // B (= V) MN-major
+      const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 2 * AT_TILE;
+      const uint32_t p_hi = smem_u32(sP), p_lo = p_hi + 2 * AT_TILE;
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int j) {
+        const int s = j % AT_STAGES;
+        mbar_wait(&kv_full[s], (j / AT_STAGES) & 1);
+        mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t k_hi = smem_u32(sKV + s * AT_KV_STAGE), k_lo = k_hi + AT_TILE;
+        const uint32_t d = (j & 1) ? tS1 : tS0;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t dkh = umma_desc_sw128(k_hi + k4 * 32), dkl = umma_desc_sw128(k_lo + k4 * 32);
+          const uint64_t dqh = umma_desc_sw128(q_hi + k4 * 32), dql = umma_desc_sw128(q_lo + k4 * 32);
+          umma_bf16(d, dql, dkh, idesc_s, k4 != 0 ? 1u : 0u);
+          umma_bf16(d, dqh, dkl, idesc_s, 1u);
+          umma_bf16(d, dqh, dkh, idesc_s, 1u);
+        }
+        umma_commit(&s_full[j & 1]);
+      };
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) issue_s(j + 1);            // S of the next block overlaps the softmax of this one
+        const int s = j % AT_STAGES;
+        mbar_wait(p_full, j & 1);                    // P_j is in smem
+        mbar_wait(pv_empty, (j & 1) ^ 1);            // PV accumulator of block j-1 has been read
+        tcgen05_fence_after();
+        const uint32_t v_hi = smem_u32(sKV + s * AT_KV_STAGE + 2 * AT_TILE), v_lo = v_hi + AT_TILE;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {             // 16 keys per step: 32 B along P rows, 2048 B along V rows
+          const uint64_t dvh = umma_desc_sw128_mn(v_hi + k4 * 2048), dvl = umma_desc_sw128_mn(v_lo + k4 * 2048);
+          const uint64_t dph = umma_desc_sw128(p_hi + k4 * 32), dpl = umma_desc_sw128(p_lo + k4 * 32);
+          umma_bf16(tPV, dpl, dvh, idesc_pv, k4 != 0 ? 1u : 0u);
+          umma_bf16(tPV, dph, dvl, idesc_pv, 1u);
+          umma_bf16(tPV, dph, dvh, idesc_pv, 1u);
+        }
+        umma_commit(pv_full);                        // PV_j ready, P smem free
+        umma_commit(&kv_empty[s]);                   // K/V stage free
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue (128 threads, one query row each) ============
+    const int quarter = warp & 3;                     // TMEM lane quarter of this warp
+    const int row = quarter * 32 + lane;              // query row inside the tile
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f, c_prev = 1.f;
+    uint8_t* prow_hi = sP + row * 128;
+    uint8_t* prow_lo = sP + 2 * AT_TILE + row * 128;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tcgen05_fence_after();
+      uint32_t r0[32], r1[32];
+      const uint32_t ts = ((j & 1) ? tS1 : tS0) + lane_off;
+      tmem_ld_32x32(ts, r0);
+      tmem_ld_32x32(ts + 32, r1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[j & 1]);
+      // scores in the log2 domain; keys beyond the sequence are masked
+      const int kbase = j * AT_BN;
+      float mx = m;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float a = __uint_as_float(r0[i]) * p.scale_log2e, b = __uint_as_float(r1[i]) * p.scale_log2e;
+        if (kbase + i >= kvlen) a = -INFINITY;
+        if (kbase + 32 + i >= kvlen) b = -INFINITY;
+        r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(b);
+        mx = fmaxf(mx, fmaxf(a, b));
+      }
+      const float c = (m == -INFINITY) ? 1.f : exp2f(m - mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float a = exp2f(__uint_as_float(r0[i]) - mx), b = exp2f(__uint_as_float(r1[i]) - mx);
+        sum += a + b;
+        r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(b);
+      }
+      l = l * c + sum;
+      m = mx;
+      // fold the previous block's PV into O (it was computed relative to the previous max)
+      if (j > 0) {
+        mbar_wait(pv_full, (j - 1) & 1);
+        tcgen05_fence_after();
+        uint32_t v0[32];
+        tmem_ld_32x32(tPV + lane_off, v0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = o[i] * c_prev + __uint_as_float(v0[i]);
+        tmem_ld_32x32(tPV + lane_off + 32, v0);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pv_empty);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[32 + i] = o[32 + i] * c_prev + __uint_as_float(v0[i]);
+      }
+      c_prev = c;
+      // P_j -> bf16 hi/lo planes in swizzled smem (row-major 128 B rows, 16-byte chunk XOR row%8)
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = ch * 8 + e * 2;
+          const float a = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
+          const float b = __uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]);
+          __nv_bfloat16 ah, al, bh, bl;
+          split_bf16(a, ah, al); split_bf16(b, bh, bl);
+          hi[e] = pack_bf16(ah, bh); lo[e] = pack_bf16(al, bl);
+        }
+        const uint32_t off = ((uint32_t)(ch ^ (row & 7))) << 4;
+        *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(prow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // last block's PV
+    {
+      mbar_wait(pv_full, (nblk - 1) & 1);
+      tcgen05_fence_after();
+      uint32_t v0[32];
+      tmem_ld_32x32(tPV + lane_off, v0);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = o[i] * c_prev + __uint_as_float(v0[i]);
+      tmem_ld_32x32(tPV + lane_off + 32, v0);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[32 + i] = o[32 + i] * c_prev + __uint_as_float(v0[i]);
+    }
+    if (q0 + row < qlen) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      float* dst = p.O + (long)(qrow0 + row) * p.ldo + head * 64;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+// ---- host --------------------------------------------------------------------------------------------
+void make_plane_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long rows, int cols);   // gemm.cu
+
+void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
+  if (ctx.dry) return;
+  static bool attr = false;
+  if (!attr) { CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr = true; }
+  AttnTcDev p;
+  p.O = a.O; p.ldo = a.ldo; p.q_start = a.q_start; p.q_len = a.q_len; p.kv_start = a.kv_start; p.kv_len = a.kv_len;
+  p.scale_log2e = a.scale * 1.4426950408889634f;
+  p.q_col = a.q_col; p.k_col = a.k_col; p.v_col = a.v_col;
+  dim3 grid((a.max_q_len + AT_BM - 1) / AT_BM, a.n_heads, a.n_seq);
+  ctx.launches++;
+  if (ctx.timer) ctx.timer->begin(K_FLASH, ctx.stream);
+  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
+  if (ctx.timer) ctx.timer->end(K_FLASH, ctx.stream);
+  CBX_CHECK(cudaGetLastError());
+}
+
+}  // namespace cbx

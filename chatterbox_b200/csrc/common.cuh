@@ -192,7 +192,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_MISH = 3, ACT_ELU = 4, ACT_LRELU = 5, ACT_SNAKE = 6,
                  ACT_TANH = 7 };
 
-__device__ __forceinline__ float act_apply(int act, float v, float p) {
+// transcendental activations stay out of line: inlining them into unrolled epilogues blows the kernels up to
+// hundreds of KB and the SM then stalls on instruction fetch (ncu: stalled_no_instructions ~40%)
+static __device__ __noinline__ float act_apply_slow(int act, float v, float p) {
   switch (act) {
     case ACT_SILU: return v / (1.0f + expf(-v));
     case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
@@ -201,7 +203,6 @@ __device__ __forceinline__ float act_apply(int act, float v, float p) {
       return v * tanhf(sp);
     }
     case ACT_ELU: return v > 0.0f ? v : expm1f(v);
-    case ACT_LRELU: return v > 0.0f ? v : v * p;
     case ACT_SNAKE: {  // x + 1/(a+1e-9) * sin(a x)^2
       float s = sinf(v * p);
       return v + (1.0f / (p + 1e-9f)) * (s * s);
@@ -209,6 +210,11 @@ __device__ __forceinline__ float act_apply(int act, float v, float p) {
     case ACT_TANH: return tanhf(v);
     default: return v;
   }
+}
+__device__ __forceinline__ float act_apply(int act, float v, float p) {
+  if (act == ACT_NONE) return v;
+  if (act == ACT_LRELU) return v > 0.0f ? v : v * p;
+  return act_apply_slow(act, v, p);
 }
 
 }  // namespace cbx

@@ -250,7 +250,7 @@ void flow_encode(cbx_handle* h, Ctx& ctx, const int* tokens, const cbx_layout& L
 }
 
 // ---- CFM estimator ---------------------------------------------------------------------------------
-struct EstBufs { float *h1, *h2, *hn, *qkv, *att, *ff; };
+struct EstBufs { float *h1, *h2, *hn, *qkv, *att, *ff; __nv_bfloat16 *qkv_hi, *qkv_lo; CUtensorMap tm_hi, tm_lo; bool tc; };
 
 static void cfm_resnet(Ctx& ctx, CfmResnet& r, const float* in, int lda, int cin, float* out, int ldo, const float* tvec,
                        const cbx_layout& L, EstBufs& b) {
@@ -266,12 +266,24 @@ static void cfm_resnet(Ctx& ctx, CfmResnet& r, const float* in, int lda, int cin
 static void cfm_tfmr(Ctx& ctx, CfmTfmr& t, float* x, int ldx, const cbx_layout& L, EstBufs& b) {
   const int rows = L.rows;
   layernorm(ctx, x, ldx, t.ln1_w.p, t.ln1_b.p, b.hn, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
-  gemm(ctx, gemm_args_linear(b.hn, 256, rows, t.qkv, b.qkv, 1536), t.qkv);
-  AttnArgs a;
-  a.Q = b.qkv; a.K = b.qkv + 512; a.V = b.qkv + 1024; a.ldq = a.ldk = a.ldv = 1536; a.O = b.att; a.ldo = 512;
-  a.n_seq = L.n_seq; a.n_heads = 8; a.q_start = L.start; a.q_len = L.len; a.kv_start = L.start; a.kv_len = L.len;
-  a.max_q_len = L.max_len; a.scale = 0.125f; a.causal = 0;
-  attention(ctx, a);
+  if (b.tc) {
+    // QKV GEMM writes bf16 hi/lo planes; tcgen05 attention reads them through TMA
+    GemmDev gq = gemm_args_linear(b.hn, 256, rows, t.qkv, nullptr, 0);
+    gq.Chi = b.qkv_hi; gq.Clo = b.qkv_lo; gq.ldcb = 1536;
+    gemm(ctx, gq, t.qkv);
+    AttnTcArgs a;
+    a.tm_hi = &b.tm_hi; a.tm_lo = &b.tm_lo; a.q_col = 0; a.k_col = 512; a.v_col = 1024; a.O = b.att; a.ldo = 512;
+    a.n_seq = L.n_seq; a.n_heads = 8; a.q_start = L.start; a.q_len = L.len; a.kv_start = L.start; a.kv_len = L.len;
+    a.max_q_len = L.max_len; a.scale = 0.125f;
+    attention_tc(ctx, a);
+  } else {
+    gemm(ctx, gemm_args_linear(b.hn, 256, rows, t.qkv, b.qkv, 1536), t.qkv);
+    AttnArgs a;
+    a.Q = b.qkv; a.K = b.qkv + 512; a.V = b.qkv + 1024; a.ldq = a.ldk = a.ldv = 1536; a.O = b.att; a.ldo = 512;
+    a.n_seq = L.n_seq; a.n_heads = 8; a.q_start = L.start; a.q_len = L.len; a.kv_start = L.start; a.kv_len = L.len;
+    a.max_q_len = L.max_len; a.scale = 0.125f; a.causal = 0;
+    attention(ctx, a);
+  }
   GemmDev go = gemm_args_linear(b.att, 512, rows, t.out, x, ldx);
   go.res = x; go.ldr = ldx;
   gemm(ctx, go, t.out);
@@ -348,6 +360,10 @@ void cfm_solve(cbx_handle* h, Ctx& ctx, const float* mu, const float* spk, const
   b.h1 = ctx.ws.get<float>((size_t)rows3 * 256); b.h2 = ctx.ws.get<float>((size_t)rows3 * 256);
   b.hn = ctx.ws.get<float>((size_t)rows3 * 256); b.qkv = ctx.ws.get<float>((size_t)rows3 * 1536);
   b.att = ctx.ws.get<float>((size_t)rows3 * 512); b.ff = ctx.ws.get<float>((size_t)rows3 * 1024);
+  b.tc = (ctx.attn_impl == 0 && ctx.gemm_impl == 0);
+  b.qkv_hi = reinterpret_cast<__nv_bfloat16*>(b.qkv);                 // the planes reuse the fp32 qkv buffer
+  b.qkv_lo = b.qkv_hi + (size_t)rows3 * 1536;
+  if (b.tc && !ctx.dry) { make_plane_tmap(&b.tm_hi, b.qkv_hi, rows3, 1536); make_plane_tmap(&b.tm_lo, b.qkv_lo, rows3, 1536); }
   SeqMap sm3 = seqmap(L3, L3);
 
   for (int k = 0; k < n_steps; ++k) {

@@ -46,7 +46,7 @@ __device__ __forceinline__ RowGeom row_geom(const GemmDev& g, int row) {
 }
 
 // one A element (used by the SIMT reference and by the scalar tails of the producers)
-__device__ __forceinline__ float load_a_elem(const GemmDev& g, const RowGeom& rg, int k) {
+static __device__ __noinline__ float load_a_elem(const GemmDev& g, const RowGeom& rg, int k) {
   if (!rg.valid) return 0.0f;
   if (g.a_mode == A_TAPS) {
     int tap = k / g.ctap, c = k - tap * g.ctap;
@@ -62,19 +62,27 @@ __device__ __forceinline__ float load_a_elem(const GemmDev& g, const RowGeom& rg
 }
 
 // epilogue for one output element (non-swiglu)
-__device__ __forceinline__ void epilogue_store(const GemmDev& g, int row, int n, float acc, bool row_valid) {
+static __device__ __noinline__ void epilogue_store(const GemmDev& g, int row, int n, float acc, bool row_valid) {
   if (n >= g.n_out) return;
   float v = acc * g.alpha + (g.bias ? g.bias[n] : 0.0f);
   v = act_apply(g.act, v, g.act_vec ? g.act_vec[n] : g.act_p);
   if (g.res) v += g.res[(long)row * g.ldr + n];
   v *= g.out_scale;
+  if (g.Chi) {                       // bf16 hi/lo planes (operands of the tcgen05 attention)
+    if (!row_valid) v = 0.0f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    g.Chi[(long)row * g.ldcb + n] = h;
+    g.Clo[(long)row * g.ldcb + n] = l;
+    if (!g.C) return;
+  }
   float* cp = g.C + (long)row * g.ldc + n;
   if (g.accumulate) v += *cp;
   if (!row_valid) v = 0.0f;
   *cp = v;
   if (g.C2) g.C2[(long)row * g.ldc2 + n] = row_valid ? act_apply(g.act2, v, g.act2_vec ? g.act2_vec[n] : g.act2_p) : 0.0f;
 }
-__device__ __forceinline__ void epilogue_store_swiglu(const GemmDev& g, int row, int n_even, float a0, float a1,
+static __device__ __noinline__ void epilogue_store_swiglu(const GemmDev& g, int row, int n_even, float a0, float a1,
                                                       bool row_valid) {
   if (n_even >= g.n_out) return;
   float v0 = a0 * g.alpha + (g.bias ? g.bias[n_even] : 0.0f);
@@ -143,15 +151,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
     for (int p = 0; p < 8; ++p) rg[p] = row_geom(g, m0 + p * 16 + rsub);
     const bool vec_ok = (g.a_mode == A_TAPS) && ((g.lda & 3) == 0) && ((g.c_in & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* a_hi = smem + s * Cfg::STAGE_BYTES;
+    // gather one K block (8 rows x 4 floats per thread) into registers
+    auto load_block = [&](int kb, float4 (&v)[8]) {
       const int k0 = kb * TC_BK + c4 * 4;
       int tap = 0, c = k0;
       if (g.a_mode == A_TAPS) { tap = k0 / g.ctap; c = k0 - tap * g.ctap; }
-      float4 v[8];
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         const RowGeom& r = rg[p];
@@ -168,6 +172,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
         }
         v[p] = x;
       }
+    };
+    float4 v[8], vn[8];
+    load_block(0, v);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      if (kb + 1 < KB) load_block(kb + 1, vn);     // next block's loads are in flight while this one is converted
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* a_hi = smem + s * Cfg::STAGE_BYTES;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         const int row = p * 16 + rsub;
@@ -186,6 +199,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
       fence_proxy_async_smem();   // make generic-proxy stores visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
+#pragma unroll
+      for (int p = 0; p < 8; ++p) v[p] = vn[p];
     }
     // ===================== epilogue: TMEM -> registers -> global =====================================
     mbar_wait(accum_bar, 0);
@@ -203,12 +218,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
       tmem_ld_wait();
       if (in_range) {
         if (g.swiglu) {
-#pragma unroll
+#pragma unroll 1
           for (int j = 0; j < 32; j += 2)
             if (n0 + col + j < g.n_out)
               epilogue_store_swiglu(g, row, n0 + col + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), er.valid);
-        } else {
+        } else if (g.Chi && !g.C && !g.res && g.act == ACT_NONE && n0 + col + 32 <= g.n_out && (g.ldcb & 7) == 0) {
+          uint32_t hi[16], lo[16];
 #pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float v0 = __uint_as_float(r[j]) * g.alpha + (g.bias ? g.bias[n0 + col + j] : 0.f);
+            float v1 = __uint_as_float(r[j + 1]) * g.alpha + (g.bias ? g.bias[n0 + col + j + 1] : 0.f);
+            if (!er.valid) { v0 = 0.f; v1 = 0.f; }
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v0, h0, l0); split_bf16(v1, h1, l1);
+            hi[j >> 1] = pack_bf16(h0, h1); lo[j >> 1] = pack_bf16(l0, l1);
+          }
+          uint4* dh = reinterpret_cast<uint4*>(g.Chi + (long)row * g.ldcb + n0 + col);
+          uint4* dl = reinterpret_cast<uint4*>(g.Clo + (long)row * g.ldcb + n0 + col);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            dh[q4] = make_uint4(hi[4 * q4], hi[4 * q4 + 1], hi[4 * q4 + 2], hi[4 * q4 + 3]);
+            dl[q4] = make_uint4(lo[4 * q4], lo[4 * q4 + 1], lo[4 * q4 + 2], lo[4 * q4 + 3]);
+          }
+        } else if (!g.Chi && !g.C2 && !g.accumulate && n0 + col + 32 <= g.n_out && (g.ldc & 3) == 0 &&
+                   (!g.res || (g.ldr & 3) == 0)) {
+          // plain fp32 output: v = act(acc*alpha + bias) (+ res), 16-byte stores
+          float* cp = g.C + (long)row * g.ldc + n0 + col;
+          const float* rp = g.res ? g.res + (long)row * g.ldr + n0 + col : nullptr;
+#pragma unroll 2
+          for (int j = 0; j < 32; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int n = n0 + col + j + e;
+              float x = __uint_as_float(r[j + e]) * g.alpha + (g.bias ? g.bias[n] : 0.0f);
+              x = act_apply(g.act, x, g.act_vec ? g.act_vec[n] : g.act_p);
+              v[e] = x;
+            }
+            if (rp) { const float4 q = *reinterpret_cast<const float4*>(rp + j); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
+            float4 o = make_float4(v[0] * g.out_scale, v[1] * g.out_scale, v[2] * g.out_scale, v[3] * g.out_scale);
+            if (!er.valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(cp + j) = o;
+          }
+        } else {
+#pragma unroll 1
           for (int j = 0; j < 32; ++j) epilogue_store(g, row, n0 + col + j, __uint_as_float(r[j]), er.valid);
         }
       }
@@ -410,6 +463,19 @@ void make_tmaps_for(Weight& W) {
   }
 }
 
+// 2-D map over a [rows][cols] bf16 plane, box 64 x 64, SWIZZLE_128B (tcgen05 attention operands)
+void make_plane_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long rows, int cols) {
+  PFN_encodeTiled enc = get_encode_fn();
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cbx: cuTensorMapEncodeTiled (plane) failed");
+}
+
 static inline uint16_t f2bf16_host(float f) {   // round-to-nearest-even
   uint32_t u; memcpy(&u, &f, 4);
   if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
@@ -507,7 +573,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     gemm_simt_kernel<<<grid, 256, 0, ctx.stream>>>(g);
   } else {
     const bool plain = !g.has_seq && g.a_mode == A_TAPS && g.ntaps == 1 && g.stride == 1 && g.pad == 0 &&
-                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.precise &&
+                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.precise && !g.Chi &&
                        ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
     if (plain && g.M <= 8) {
       if (g.M <= 2) launch_gemv<2>(ctx, g);

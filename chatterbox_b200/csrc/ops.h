@@ -58,6 +58,7 @@ struct GemmDev {
   float out_scale;                              // v *= out_scale (after act/res)
   int swiglu;                                   // columns (2j,2j+1) -> out[j] = silu(v0)*v1
   float* C2; int ldc2; int act2; float act2_p; const float* act2_vec;  // optional 2nd output act2(v)
+  __nv_bfloat16* Chi; __nv_bfloat16* Clo; int ldcb;   // optional bf16 hi/lo planes of v (C may then be null)
 };
 
 struct Arena {  // bump allocator over caller-owned workspace; dry=true only counts
@@ -142,6 +143,17 @@ struct AttnArgs {
   int bias_rel = 0; int bias_center = 0;    // bias_rel: column = bias_center - i + j (espnet rel_shift)
 };
 void attention(Ctx& ctx, const AttnArgs& a);
+// tcgen05 variant (non-causal, no bias): operands are bf16 hi/lo planes [rows][ld] addressed through TMA maps
+struct AttnTcArgs {
+  const CUtensorMap* tm_hi; const CUtensorMap* tm_lo;
+  int q_col, k_col, v_col;                    // column of head 0 of Q / K / V inside the planes
+  float* O; int ldo;
+  int n_seq, n_heads;
+  const int* q_start; const int* q_len; const int* kv_start; const int* kv_len;
+  int max_q_len; float scale;
+};
+void attention_tc(Ctx& ctx, const AttnTcArgs& a);
+void make_plane_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long rows, int cols);
 void attention_generic(Ctx& ctx, const float* Q, const float* K, const float* V, float* O, int n_q, int n_kv,
                        int n_heads, int head_dim, int ldq, int ldk, int ldv, int ldo, float scale);
 

@@ -154,6 +154,10 @@ int cbx_test_attention(cbx_handle* h, const float* Q, const float* K, const floa
                        int n_heads, const cbx_layout* L, float scale, int causal, const float* bias, long long bias_head_stride,
                        int bias_ld, int bias_rel, int bias_center, cbx_stream stream);
 
+/* tcgen05 attention (CFM path): qkv fp32 [rows][3*n_heads*64] (q | k | v), split to bf16 hi/lo planes in ws */
+int cbx_test_attention_tc(cbx_handle* h, const float* qkv, float* O, int n_heads, const cbx_layout* L, float scale,
+                          void* ws, size_t ws_bytes, cbx_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

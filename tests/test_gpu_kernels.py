@@ -182,3 +182,27 @@ def test_linear_gemm_wide_tile_bn256():
     ref = A.double() @ w.double().t().cuda()
     err = relerr(C_, ref)
     assert err < 2e-5, f"rel err {err}"
+
+
+def test_tcgen05_attention_matches_sdpa():
+    """CFM-path attention on the tcgen05 tensor cores (TMA operands, S/PV in TMEM) vs fp64 SDPA, packed varlen."""
+    import ctypes as C
+    from gpu_util import relerr
+    from chatterbox_b200.engine import PackedLayout, _ptr
+    eng = _eng()
+    g = torch.Generator().manual_seed(21)
+    lens, H = [5, 64, 130, 300, 777], 8
+    L = PackedLayout(lens, torch.device("cuda"))
+    qkv = torch.randn(L.rows, 3 * H * 64, generator=g).cuda()
+    O = torch.zeros(L.rows, H * 64, device="cuda")
+    ws = torch.empty(L.rows * 3 * H * 64 * 4 + (1 << 20), dtype=torch.uint8, device="cuda")
+    eng.h.call("cbx_test_attention_tc", _ptr(qkv), _ptr(O), H, C.byref(L.c), 0.125, _ptr(ws), ws.numel(),
+               C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    for s, n in enumerate(lens):
+        sl = slice(L.starts[s], L.starts[s] + n)
+        sp = lambda t: t[sl].view(n, H, 64).transpose(0, 1)[None].double()
+        q, k, v = qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]
+        ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v))[0].transpose(0, 1).reshape(n, H * 64)
+        err = relerr(O[sl], ref)
+        assert err < 3e-5, f"seq{s} len{n}: {err}"
