@@ -171,19 +171,9 @@ def run_engine(args, rank, world, local_rank):
     t3 = T3(eng, W.make_t3_weights(0))
     s3 = S3Gen(eng, W.make_flow_weights(0), W.make_hift_weights(0))
     # voice conditionals: rank 0 owns them, NCCL-broadcast to the other ranks (north_star "speaker-embedding broadcast")
-    c3, cg = W.make_conds(1234)
-    blob = [c3["speaker_emb"].reshape(-1).float(), c3["cond_prompt_speech_tokens"].reshape(-1).float(),
-            c3["emotion_adv"].reshape(-1).float(), cg["prompt_token"].reshape(-1).float(),
-            cg["prompt_feat"].reshape(-1).float(), cg["embedding"].reshape(-1).float()]
-    sizes = [int(b.numel()) for b in blob]
-    flat = torch.cat(blob).cuda() if rank == 0 else torch.zeros(sum(sizes), device="cuda")
-    if world > 1:
-        dist.broadcast(flat, src=0)
-    parts = torch.split(flat.cpu(), sizes)
-    c3 = dict(speaker_emb=parts[0].reshape(1, 256), cond_prompt_speech_tokens=parts[1].reshape(1, -1).long(),
-              emotion_adv=parts[2].reshape(1, 1, 1))
-    cg = dict(prompt_token=parts[3].reshape(1, -1).long(), prompt_token_len=torch.tensor([parts[3].numel()]),
-              prompt_feat=parts[4].reshape(1, -1, 80), prompt_feat_len=None, embedding=parts[5].reshape(1, 192))
+    from chatterbox_b200.dist import broadcast_conditionals
+    c3, cg = W.make_conds(1234) if rank == 0 else (None, None)
+    c3, cg = broadcast_conditionals(c3, cg, torch.device("cuda", local_rank), src=0)
     tts = ChatterboxTTS(t3, s3, None, f"cuda:{local_rank}", Conditionals(T3Cond(**c3), cg))
     texts, budgets = make_workload(args.batch, 20260922, rank, args.budget_max)
     log(f"models loaded; batch={args.batch} sum_budget={sum(budgets)}")

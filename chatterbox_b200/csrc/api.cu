@@ -285,8 +285,17 @@ int cbx_test_gemm(cbx_handle* h, const float* A, int lda, int M_in, int M, const
   g.Wp = W.w; g.Kpad = W.Kpad; g.Npad = W.Npad;
   g.C = C; g.ldc = ldc; g.n_out = N; g.bias = W.bias; g.alpha = 1.f; g.act = act; g.act_p = act_p; g.out_scale = 1.f;
   g.res = res; g.ldr = ldr; g.swiglu = swiglu;
-  if (act >= 100) { g.act = act - 100; g.precise = 1; }
+  long long* dbgbuf = nullptr;
+  if (act >= 1000) { g.act = act - 1000; CBX_CHECK(cudaMalloc(&dbgbuf, 64 * 8)); CBX_CHECK(cudaMemset(dbgbuf, 0, 64 * 8)); g.dbg = dbgbuf; }
   gemm(c, g, W);
+  if (dbgbuf) {
+    long long hbuf[64]; CBX_CHECK(cudaMemcpy(hbuf, dbgbuf, sizeof(hbuf), cudaMemcpyDeviceToHost)); cudaFree(dbgbuf);
+    const long long t0 = hbuf[5];
+    printf("[gemm dbg] M=%d N=%d K=%d: setup_done=%lld prod_done=%lld accum_ready=%lld epi_done=%lld exit=%lld\n", M, N, cin * taps,
+           hbuf[0] - t0, hbuf[1] - t0, hbuf[2] - t0, hbuf[3] - t0, hbuf[4] - t0);
+    for (int kb = 0; kb < 8; ++kb) printf("   kb%d: prod_start=%lld prod_arrive=%lld mma_issue=%lld\n", kb, hbuf[8 + 2 * kb] - t0, hbuf[9 + 2 * kb] - t0, hbuf[32 + kb] - t0);
+    fflush(stdout);
+  }
   CBX_CHECK(cudaStreamSynchronize(c.stream));
   free_weight(W);
   h->launches += c.launches;

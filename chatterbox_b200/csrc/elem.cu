@@ -163,6 +163,23 @@ __global__ void pack_hilo_kernel(const float* src, int ld, int N, int K, __nv_bf
   split_bf16(v, h, l);
   hi[i] = h; lo[i] = l;
 }
+// fp32 [N][K] -> one bf16 matrix [Npad][2K] = [hi | lo] (so that x.[hi|lo]^T with x repeated twice along K is x.W^T)
+__global__ void pack_hilo_cat_kernel(const float* src, int ld, int N, int K, __nv_bfloat16* out, int Npad) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)Npad * K) return;
+  const int n = (int)(i / K), k = (int)(i - (long)n * K);
+  float v = (n < N) ? src[(long)n * ld + k] : 0.f;
+  __nv_bfloat16 h, l;
+  split_bf16(v, h, l);
+  out[(long)n * 2 * K + k] = h;
+  out[(long)n * 2 * K + K + k] = l;
+}
+void pack_hilo_cat(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat16* out, int Npad) {
+  if (ctx.dry) return;
+  ctx.launches++;
+  pack_hilo_cat_kernel<<<(unsigned)(((long)Npad * K + 255) / 256), 256, 0, ctx.stream>>>(src, ld, N, K, out, Npad);
+  CBX_CHECK(cudaGetLastError());
+}
 void pack_hilo(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat16* hi, __nv_bfloat16* lo, int Npad, int Kpad) {
   if (ctx.dry) return;
   ctx.launches++;

@@ -145,14 +145,12 @@ static void encoder_layer(cbx_handle* h, Ctx& ctx, EncLayer& L, float* x, const 
   add_pos_bias(ctx, qkv, 1536, L.bias_u.p, L.bias_v.p, qu, qv, rows);
   // matrix_bd = (q + v) . P^T per head, P as an on-the-fly hi/lo bf16 "weight"  (attention.py:314-318)
   const int Npad = (NP + 63) / 64 * 64;
-  __nv_bfloat16* Phi = ctx.ws.get<__nv_bfloat16>((size_t)8 * Npad * 64);
-  __nv_bfloat16* Plo = ctx.ws.get<__nv_bfloat16>((size_t)8 * Npad * 64);
+  __nv_bfloat16* Pcat = ctx.ws.get<__nv_bfloat16>((size_t)8 * Npad * 128);      // per head [Npad][hi(64) | lo(64)]
   // chunk the sequences so the materialised bias stays below ~1.5 GB
   const long budget_rows = std::max<long>(kTileM, (long)(1.5e9 / ((double)8 * Npad * 4)) / kTileM * kTileM);
   const int chunk_rows_cap = (int)std::min<long>(rows, budget_rows);
   float* bd = ctx.ws.get<float>((size_t)8 * chunk_rows_cap * Npad);
-  for (int hd = 0; hd < 8; ++hd)
-    pack_hilo(ctx, P + hd * 64, 512, NP, 64, Phi + (size_t)hd * Npad * 64, Plo + (size_t)hd * Npad * 64, Npad, 64);
+  for (int hd = 0; hd < 8; ++hd) pack_hilo_cat(ctx, P + hd * 64, 512, NP, 64, Pcat + (size_t)hd * Npad * 128, Npad);
   int s0 = 0;
   while (s0 < lay.n_seq) {
     int s1 = s0; long r0 = lay.h_start[s0], r1 = r0;
@@ -164,15 +162,14 @@ static void encoder_layer(cbx_handle* h, Ctx& ctx, EncLayer& L, float* x, const 
     const int crow = (int)(r1 - r0);
     CBX_REQUIRE(crow <= chunk_rows_cap, "sequence longer than the rel-pos bias chunk");
     for (int hd = 0; hd < 8; ++hd) {
-      for (int part = 0; part < 2; ++part) {
-        Weight W;
-        W.w = (part == 0 ? Phi : Plo) + (size_t)hd * Npad * 64;
-        W.N = NP; W.K = 64; W.Npad = Npad; W.Kpad = 64; W.bias = nullptr;
-        if (!ctx.dry) make_tmaps_for(W);
-        GemmDev g = gemm_args_linear(qv + r0 * 512 + hd * 64, 512, crow, W, bd + (size_t)hd * crow * Npad, Npad);
-        g.bias = nullptr; g.accumulate = part;
-        gemm(ctx, g, W);
-      }
+      // one GEMM with K = 128: the 64 q_v channels are fed twice (tap stride 0) against [P_hi | P_lo]
+      Weight W;
+      W.w = Pcat + (size_t)hd * Npad * 128;
+      W.N = NP; W.K = 128; W.Npad = Npad; W.Kpad = 128; W.bias = nullptr;
+      if (!ctx.dry) make_tmaps_for(W);
+      GemmDev g = gemm_args_linear(qv + r0 * 512 + hd * 64, 512, crow, W, bd + (size_t)hd * crow * Npad, Npad);
+      g.bias = nullptr; g.ntaps = 2; g.ctap = 64; g.c_in = 64; g.dil = 0; g.k_total = 128;
+      gemm(ctx, g, W);
     }
     AttnArgs a;
     a.Q = qu; a.K = qkv + 512; a.V = qkv + 1024; a.ldq = 512; a.ldk = a.ldv = 1536; a.O = att; a.ldo = 512;

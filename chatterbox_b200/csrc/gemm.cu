@@ -94,188 +94,239 @@ static __device__ __noinline__ void epilogue_store_swiglu(const GemmDev& g, int 
 
 // ================================================================================================
 // tcgen05 kernel
+//   warp 8  : TMA producer  -- W tile (bf16, SWIZZLE_128B) and, when the A operand is a plain strided fp32 matrix
+//             (Linear / conv taps), the raw fp32 A tile [128 rows][64 floats] of the current tap
+//   warps 0-7: converters   -- fp32 tile -> bf16 hi/lo planes IN PLACE in the swizzled UMMA layout (zeroing rows whose
+//             tap falls outside their sequence); or, for window/strided convs, a register gather straight from global
+//   warp 9  : MMA issuer    -- one thread, tcgen05.mma M128 x N{64,128,256} x K16, 2 MMAs (hi, lo) per K step, TMEM
+//   warps 0-7 again: epilogue -- tcgen05.ld -> smem transpose -> coalesced bias/activation/residual/stores
 // ================================================================================================
 constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;   // + TMA warp + MMA warp
 
-// NS = number of bf16 planes the fp32 activations are split into: 2 keeps 16 significand bits (default),
-// 3 keeps all 24 (GemmDev::precise; used where downstream arithmetic amplifies rounding, e.g. the F0 predictor
-// whose output is integrated over ~10^6 samples by the harmonic source).
-template <int BN, int NS> struct TcCfg {
-  static constexpr int STAGES = (BN == 256 || NS == 3) ? 3 : 4;
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;        // 16 KB per plane
+template <int BN> struct TcCfg {
+  static constexpr int STAGES = (BN == 256) ? 3 : 4;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;        // fp32 tile == two bf16 planes of 16 KB (converted in place)
   static constexpr int W_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = NS * A_BYTES + W_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <int BN, int NS>
+// fp32 pair -> bf16x2 hi plane word and lo plane word (one F2FP each; bf16 -> fp32 is a shift)
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float fa = __uint_as_float(hi << 16), fb = __uint_as_float(hi & 0xFFFF0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - fa, b - fb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
-  using Cfg = TcCfg<BN, NS>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA, const GemmDev g) {
+  using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;                 // [STAGES]  8 producer-warp arrivals + 1 TMA arrive(expect_tx)
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]  1 arrival (tcgen05.commit)
-  uint64_t* accum_bar = bars + 2 * STAGES;   // accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* tma_full = bars;                  // [STAGES] TMA bytes landed (W, and the fp32 A tile in TMA mode)
+  uint64_t* conv_full = bars + STAGES;        // [STAGES] 8 converter-warp arrivals: bf16 planes ready
+  uint64_t* empty_bar = bars + 2 * STAGES;    // [STAGES] 1 arrival (tcgen05.commit): stage consumed
+  uint64_t* accum_bar = bars + 3 * STAGES;    // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * BN;
+  const int n0 = blockIdx.x * BN;             // N tiles fastest: CTAs sharing an A tile run together (L2 reuse)
+  const int m0 = blockIdx.y * TC_BM;
   const int KB = g.Kpad / TC_BK;
+  const bool dbg = g.dbg && blockIdx.y == gridDim.y / 2 && blockIdx.x == 0;
+  if (dbg && threadIdx.x == 0) g.dbg[5] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCER_WARPS + 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&conv_full[s], TC_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
     mbar_init(accum_bar, 1);
     fence_mbar_init();
   }
   if (warp == TC_PRODUCER_WARPS + 1) tmem_alloc<BN>(tmem_slot);   // MMA warp owns TMEM
-  if (warp == TC_PRODUCER_WARPS && lane == 0) tma_prefetch_desc(&tmapW);
+  if (warp == TC_PRODUCER_WARPS && lane == 0) { tma_prefetch_desc(&tmapW); if (g.a_tma) tma_prefetch_desc(&tmapA); }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) g.dbg[0] = clock64();
 
   if (warp < TC_PRODUCER_WARPS) {
-    // ===================== A producers: gather fp32 -> bf16 hi/lo -> swizzled smem ====================
     const int t = threadIdx.x;            // 0..255
     const int c4 = t & 15;                // float4 chunk inside the 64-wide K block
     const int rsub = t >> 4;              // 0..15
     RowGeom rg[8];
 #pragma unroll
     for (int p = 0; p < 8; ++p) rg[p] = row_geom(g, m0 + p * 16 + rsub);
-    const bool vec_ok = (g.a_mode == A_TAPS) && ((g.lda & 3) == 0) && ((g.c_in & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
-    // gather one K block (8 rows x 4 floats per thread) into registers
-    auto load_block = [&](int kb, float4 (&v)[8]) {
-      const int k0 = kb * TC_BK + c4 * 4;
-      int tap = 0, c = k0;
-      if (g.a_mode == A_TAPS) { tap = k0 / g.ctap; c = k0 - tap * g.ctap; }
+    if (g.a_tma) {
+      // ===================== converters: smem fp32 tile -> bf16 hi/lo planes, in place ===================
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
+        const int tap = (kb * TC_BK) / g.ctap;
+        if (dbg && threadIdx.x == 0 && kb < 8) g.dbg[8 + 2 * kb] = clock64();
+        mbar_wait(&tma_full[s], ph);
+        float4 v[8];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const RowGeom& r = rg[p];
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r.valid) {
-          if (vec_ok) {
-            long ir = r.in_row0 + (long)tap * g.dil;
-            if (tap < g.ntaps && c < g.c_in && ir >= r.lo && ir < r.hi)
-              x = __ldg(reinterpret_cast<const float4*>(g.A + ir * g.lda + c));
-          } else {
-            x.x = load_a_elem(g, r, k0 + 0); x.y = load_a_elem(g, r, k0 + 1);
-            x.z = load_a_elem(g, r, k0 + 2); x.w = load_a_elem(g, r, k0 + 3);
-          }
+        for (int p = 0; p < 8; ++p) {
+          const int row = p * 16 + rsub;
+          v[p] = *reinterpret_cast<const float4*>(a_st + row * 256 + c4 * 16);
+          const long ir = rg[p].in_row0 + (long)tap * g.dil;
+          if (!rg[p].valid || ir < rg[p].lo || ir >= rg[p].hi) v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        v[p] = x;
-      }
-    };
-    float4 v[8], vn[8];
-    load_block(0, v);
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      if (kb + 1 < KB) load_block(kb + 1, vn);     // next block's loads are in flight while this one is converted
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* a_hi = smem + s * Cfg::STAGE_BYTES;
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // every converter has read its part of the fp32 tile
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int row = p * 16 + rsub;
-        // SWIZZLE_128B: 16-byte chunk index XOR (row % 8); rows are 128 B apart
-        const uint32_t off = row * 128 + ((((uint32_t)c4 >> 1) ^ ((uint32_t)row & 7)) << 4) + (c4 & 1) * 8;
-        float r0 = v[p].x, r1 = v[p].y, r2 = v[p].z, r3 = v[p].w;
-#pragma unroll
-        for (int pl = 0; pl < NS; ++pl) {       // plane pl holds bf16(residual); residual -= plane
-          const __nv_bfloat16 b0 = __float2bfloat16_rn(r0), b1 = __float2bfloat16_rn(r1);
-          const __nv_bfloat16 b2 = __float2bfloat16_rn(r2), b3 = __float2bfloat16_rn(r3);
-          *reinterpret_cast<uint2*>(a_hi + pl * Cfg::A_BYTES + off) = make_uint2(pack_bf16(b0, b1), pack_bf16(b2, b3));
-          r0 -= __bfloat162float(b0); r1 -= __bfloat162float(b1);
-          r2 -= __bfloat162float(b2); r3 -= __bfloat162float(b3);
+        for (int p = 0; p < 8; ++p) {
+          const int row = p * 16 + rsub;
+          const uint32_t off = row * 128 + ((((uint32_t)c4 >> 1) ^ ((uint32_t)row & 7)) << 4) + (c4 & 1) * 8;
+          uint32_t h0, l0, h1, l1;
+          split_pair(v[p].x, v[p].y, h0, l0);
+          split_pair(v[p].z, v[p].w, h1, l1);
+          *reinterpret_cast<uint2*>(a_st + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(a_st + 16384 + off) = make_uint2(l0, l1);
         }
+        fence_proxy_async_smem();   // make generic-proxy stores visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_full[s]);
+        if (dbg && threadIdx.x == 0 && kb < 8) g.dbg[9 + 2 * kb] = clock64();
       }
-      fence_proxy_async_smem();   // make generic-proxy stores visible to the tensor-core (async) proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
+    } else {
+      // ===================== register gather (window / strided convs, unaligned operands) ==============
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
+        const int k0 = kb * TC_BK + c4 * 4;
+        float4 v[8];
+#pragma unroll 1
+        for (int p = 0; p < 8; ++p) {
+          v[p].x = load_a_elem(g, rg[p], k0 + 0); v[p].y = load_a_elem(g, rg[p], k0 + 1);
+          v[p].z = load_a_elem(g, rg[p], k0 + 2); v[p].w = load_a_elem(g, rg[p], k0 + 3);
+        }
+        mbar_wait(&empty_bar[s], ph ^ 1);
 #pragma unroll
-      for (int p = 0; p < 8; ++p) v[p] = vn[p];
+        for (int p = 0; p < 8; ++p) {
+          const int row = p * 16 + rsub;
+          const uint32_t off = row * 128 + ((((uint32_t)c4 >> 1) ^ ((uint32_t)row & 7)) << 4) + (c4 & 1) * 8;
+          uint32_t h0, l0, h1, l1;
+          split_pair(v[p].x, v[p].y, h0, l0);
+          split_pair(v[p].z, v[p].w, h1, l1);
+          *reinterpret_cast<uint2*>(a_st + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(a_st + 16384 + off) = make_uint2(l0, l1);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_full[s]);
+      }
     }
-    // ===================== epilogue: TMEM -> registers -> global =====================================
+    // ===================== epilogue: TMEM -> smem transpose -> coalesced global ==========================
+    if (dbg && threadIdx.x == 0) g.dbg[1] = clock64();
     mbar_wait(accum_bar, 0);
     tcgen05_fence_after();
+    if (dbg && threadIdx.x == 0) g.dbg[2] = clock64();
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = warp >> 2;             // column half
-    const int row = m0 + q * 32 + lane;
-    const RowGeom er = row_geom(g, row);
-    const bool in_range = row < g.M;
+    const int row_own = m0 + q * 32 + lane; // the row whose accumulator this thread loads
+    const RowGeom er = row_geom(g, row_own);
+    const int myvalid = (er.valid && row_own < g.M) ? 1 : 0;
+    float* st = reinterpret_cast<float*>(smem + warp * (32 * 33 * 4));   // pipeline buffers are idle now
+    const int rows_here = min(32, g.M - (m0 + q * 32));
 #pragma unroll 1
     for (int cc = 0; cc < BN / 2; cc += 32) {
       const int col = half * (BN / 2) + cc;
+      if (n0 + col >= g.n_out) break;
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
       tmem_ld_wait();
-      if (in_range) {
-        if (g.swiglu) {
-#pragma unroll 1
-          for (int j = 0; j < 32; j += 2)
-            if (n0 + col + j < g.n_out)
-              epilogue_store_swiglu(g, row, n0 + col + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), er.valid);
-        } else if (g.Chi && !g.C && !g.res && g.act == ACT_NONE && n0 + col + 32 <= g.n_out && (g.ldcb & 7) == 0) {
-          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float v0 = __uint_as_float(r[j]) * g.alpha + (g.bias ? g.bias[n0 + col + j] : 0.f);
-            float v1 = __uint_as_float(r[j + 1]) * g.alpha + (g.bias ? g.bias[n0 + col + j + 1] : 0.f);
-            if (!er.valid) { v0 = 0.f; v1 = 0.f; }
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v0, h0, l0); split_bf16(v1, h1, l1);
-            hi[j >> 1] = pack_bf16(h0, h1); lo[j >> 1] = pack_bf16(l0, l1);
+      for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      if (g.swiglu) {
+        // columns (2j, 2j+1) = (gate_j, up_j) -> out[j] = silu(gate) * up ; lanes 0..15 own one output column each
+        const int nin = n0 + col + 2 * lane;
+        const int nout = (n0 + col) / 2 + lane;
+        const bool colok = lane < 16 && nin < g.n_out;
+        const float b0 = (colok && g.bias) ? g.bias[nin] : 0.f, b1 = (colok && g.bias) ? g.bias[nin + 1] : 0.f;
+        for (int rr = 0; rr < rows_here; ++rr) {
+          const int rv = __shfl_sync(0xffffffffu, myvalid, rr);
+          if (colok) {
+            const float v0 = st[rr * 33 + 2 * lane] * g.alpha + b0, v1 = st[rr * 33 + 2 * lane + 1] * g.alpha + b1;
+            float v = (v0 / (1.0f + expf(-v0))) * v1;
+            if (!rv) v = 0.f;
+            g.C[(long)(m0 + q * 32 + rr) * g.ldc + nout] = v;
           }
-          uint4* dh = reinterpret_cast<uint4*>(g.Chi + (long)row * g.ldcb + n0 + col);
-          uint4* dl = reinterpret_cast<uint4*>(g.Clo + (long)row * g.ldcb + n0 + col);
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            dh[q4] = make_uint4(hi[4 * q4], hi[4 * q4 + 1], hi[4 * q4 + 2], hi[4 * q4 + 3]);
-            dl[q4] = make_uint4(lo[4 * q4], lo[4 * q4 + 1], lo[4 * q4 + 2], lo[4 * q4 + 3]);
+        }
+      } else {
+        const int n = n0 + col + lane;
+        const bool colok = n < g.n_out;
+        const float bias = (colok && g.bias) ? g.bias[n] : 0.f;
+        const float ap = (colok && g.act_vec) ? g.act_vec[n] : g.act_p;
+        const float ap2 = (colok && g.act2_vec) ? g.act2_vec[n] : g.act2_p;
+        for (int rr = 0; rr < rows_here; ++rr) {
+          const int rv = __shfl_sync(0xffffffffu, myvalid, rr);
+          if (!colok) continue;
+          const long grow = m0 + q * 32 + rr;
+          float v = st[rr * 33 + lane] * g.alpha + bias;
+          switch (g.act) {                      // one inline copy of each activation (no per-element call)
+            case ACT_NONE: break;
+            case ACT_GELU: v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); break;
+            case ACT_SILU: v = v / (1.0f + expf(-v)); break;
+            case ACT_LRELU: v = v > 0.f ? v : v * ap; break;
+            case ACT_SNAKE: { const float sn = sinf(v * ap); v = v + (1.0f / (ap + 1e-9f)) * (sn * sn); } break;
+            case ACT_ELU: v = v > 0.f ? v : expm1f(v); break;
+            default: v = act_apply_slow(g.act, v, ap); break;
           }
-        } else if (!g.Chi && !g.C2 && !g.accumulate && n0 + col + 32 <= g.n_out && (g.ldc & 3) == 0 &&
-                   (!g.res || (g.ldr & 3) == 0)) {
-          // plain fp32 output: v = act(acc*alpha + bias) (+ res), 16-byte stores
-          float* cp = g.C + (long)row * g.ldc + n0 + col;
-          const float* rp = g.res ? g.res + (long)row * g.ldr + n0 + col : nullptr;
-#pragma unroll 2
-          for (int j = 0; j < 32; j += 4) {
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int n = n0 + col + j + e;
-              float x = __uint_as_float(r[j + e]) * g.alpha + (g.bias ? g.bias[n] : 0.0f);
-              x = act_apply(g.act, x, g.act_vec ? g.act_vec[n] : g.act_p);
-              v[e] = x;
-            }
-            if (rp) { const float4 q = *reinterpret_cast<const float4*>(rp + j); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
-            float4 o = make_float4(v[0] * g.out_scale, v[1] * g.out_scale, v[2] * g.out_scale, v[3] * g.out_scale);
-            if (!er.valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(cp + j) = o;
+          if (g.res) v += g.res[grow * g.ldr + n];
+          v *= g.out_scale;
+          if (!rv) v = 0.f;
+          if (g.Chi) {
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            g.Chi[grow * g.ldcb + n] = h;
+            g.Clo[grow * g.ldcb + n] = l;
           }
-        } else {
-#pragma unroll 1
-          for (int j = 0; j < 32; ++j) epilogue_store(g, row, n0 + col + j, __uint_as_float(r[j]), er.valid);
+          if (g.C) {
+            float* cp = g.C + grow * g.ldc + n;
+            if (g.accumulate && rv) v += *cp;
+            *cp = v;
+          }
+          if (g.C2) g.C2[grow * g.ldc2 + n] = rv ? act_apply(g.act2, v, ap2) : 0.f;
         }
       }
+      __syncwarp();
     }
+    if (dbg && threadIdx.x == 0) g.dbg[3] = clock64();
   } else if (warp == TC_PRODUCER_WARPS) {
-    // ===================== TMA producer for W tiles ===================================================
+    // ===================== TMA producer =================================================================
     if (lane == 0) {
+      long in_row0 = 0;
+      if (g.a_tma) {                       // input row feeding tap 0 of the tile's first output row
+        if (g.has_seq) {
+          const int sq = g.seq.tile_seq[m0 / kTileM];
+          if (sq >= 0) in_row0 = (long)g.seq.in_start[sq] + (long)(m0 - g.seq.out_start[sq]) - g.pad;
+        } else {
+          in_row0 = (long)m0 - g.pad;
+        }
+      }
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* wdst = smem + s * Cfg::STAGE_BYTES + NS * Cfg::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::W_BYTES);
-        tma_load_2d(wdst, &tmapW, &full_bar[s], kb * TC_BK, n0);
+        uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&tma_full[s], g.a_tma ? (Cfg::A_BYTES + Cfg::W_BYTES) : Cfg::W_BYTES);
+        tma_load_2d(a_st + Cfg::A_BYTES, &tmapW, &tma_full[s], kb * TC_BK, n0);
+        if (g.a_tma) {
+          const int k0 = kb * TC_BK;
+          const int tap = k0 / g.ctap, c = k0 - tap * g.ctap;
+          tma_load_2d(a_st, &tmapA, &tma_full[s], c, (int)(in_row0 + (long)tap * g.dil));
+        }
       }
     }
   } else {
@@ -285,18 +336,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&tma_full[s], ph);      // W tile landed
+        mbar_wait(&conv_full[s], ph);     // bf16 planes of A written
         tcgen05_fence_after();
+        if (dbg && kb < 8) g.dbg[32 + kb] = clock64();
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t wb = a_hi + NS * Cfg::A_BYTES;
+        const uint32_t a_lo = a_hi + 16384;
+        const uint32_t wb = a_hi + Cfg::A_BYTES;
 #pragma unroll
         for (int k4 = 0; k4 < TC_BK / 16; ++k4) {   // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
           const uint64_t db = umma_desc_sw128(wb + k4 * 32);
-          // smallest plane first so the fp32 accumulator adds the corrections before the leading term
-#pragma unroll
-          for (int pl = NS - 1; pl >= 0; --pl)
-            umma_bf16(tmem_base, umma_desc_sw128(a_hi + pl * Cfg::A_BYTES + k4 * 32), db, idesc,
-                      ((kb | k4) != 0 || pl != NS - 1) ? 1u : 0u);
+          // small plane first so the fp32 accumulator adds the correction before the leading term
+          umma_bf16(tmem_base, umma_desc_sw128(a_lo + k4 * 32), db, idesc, (kb | k4) != 0 ? 1u : 0u);
+          umma_bf16(tmem_base, umma_desc_sw128(a_hi + k4 * 32), db, idesc, 1u);
         }
         umma_commit(&empty_bar[s]);     // frees the smem stage once these MMAs have read it
       }
@@ -306,6 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const GemmDev g) {
   tcgen05_fence_before();
   __syncthreads();
   if (warp == TC_PRODUCER_WARPS + 1) tmem_dealloc<BN>(tmem_base);
+  if (dbg && threadIdx.x == 0) g.dbg[4] = clock64();
 }
 
 // ================================================================================================
@@ -541,15 +594,33 @@ GemmDev gemm_args_linear(const float* A, int lda, int M, const Weight& W, float*
   return g;
 }
 
-template <int BN, int NS> static void launch_tc(Ctx& ctx, const GemmDev& g, const Weight& W, int tmap_idx) {
+static void make_a_tmap(CUtensorMap* tm, const GemmDev& g) {
+  PFN_encodeTiled enc = get_encode_fn();
+  // [M_in rows][c_in cols] fp32 view of the activation matrix; columns >= c_in and rows outside [0, M_in) read as zero
+  cuuint64_t dims[2] = {(cuuint64_t)g.c_in, (cuuint64_t)g.M_in};
+  cuuint64_t strides[1] = {(cuuint64_t)g.lda * 4};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g.A), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cbx: cuTensorMapEncodeTiled (A operand) failed");
+}
+
+template <int BN> static void launch_tc(Ctx& ctx, GemmDev g, const Weight& W, int tmap_idx) {
   static bool attr_set = false;
   if (!attr_set) {
-    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, NS>::SMEM));
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
     attr_set = true;
   }
-  dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.Npad + BN - 1) / BN);
+  // TMA-fed A operand: plain strided fp32 rows (Linear, stride-1 conv taps)
+  g.a_tma = (g.a_mode == A_TAPS && g.stride == 1 && (g.lda % 4) == 0 && (g.c_in % 4) == 0 &&
+             (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && g.M_in > 0) ? 1 : 0;
+  CUtensorMap tmA;
+  if (g.a_tma) make_a_tmap(&tmA, g); else tmA = W.tmap[tmap_idx];
+  dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM);
   if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
-  gemm_tc_kernel<BN, NS><<<grid, TC_THREADS, TcCfg<BN, NS>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], g);
+  gemm_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], tmA, g);
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
 }
 
@@ -573,7 +644,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     gemm_simt_kernel<<<grid, 256, 0, ctx.stream>>>(g);
   } else {
     const bool plain = !g.has_seq && g.a_mode == A_TAPS && g.ntaps == 1 && g.stride == 1 && g.pad == 0 &&
-                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.precise && !g.Chi &&
+                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.Chi &&
                        ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
     if (plain && g.M <= 8) {
       if (g.M <= 2) launch_gemv<2>(ctx, g);
@@ -582,12 +653,9 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     } else {
       const int mt = (g.M + TC_BM - 1) / TC_BM;
       // widest N tile that still gives every SM a tile (L2->SM traffic per flop falls with BN)
-      if (g.precise) {
-        if (g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 100) launch_tc<128, 3>(ctx, g, W, 1);
-        else launch_tc<64, 3>(ctx, g, W, 0);
-      } else if (g.Npad % 256 == 0 && (long)mt * (g.Npad / 256) >= 120) launch_tc<256, 2>(ctx, g, W, 2);
-      else if (g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 100) launch_tc<128, 2>(ctx, g, W, 1);
-      else launch_tc<64, 2>(ctx, g, W, 0);
+      if (g.Npad % 256 == 0 && (long)mt * (g.Npad / 256) >= 120) launch_tc<256>(ctx, g, W, 2);
+      else if (g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 100) launch_tc<128>(ctx, g, W, 1);
+      else launch_tc<64>(ctx, g, W, 0);
     }
   }
   CBX_CHECK(cudaGetLastError());

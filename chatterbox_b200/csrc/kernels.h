@@ -25,6 +25,7 @@ void copy2d(Ctx& ctx, const float* src, int lds, float* dst, int ldd, long rows,
 void gather_rows(Ctx& ctx, const float* table, int ld, const int* ids, float* out, int ldo, int rows, int dim,
                  const float* add_table, int add_ld, const int* add_ids, int id_limit);
 void pack_hilo(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat16* hi, __nv_bfloat16* lo, int Npad, int Kpad);
+void pack_hilo_cat(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat16* out, int Npad);
 void t3_embed(Ctx& ctx, float* out, int n_tok, const int* tok_row, const int* tok_pos, const float* cond,
               const int* row_voice, int len_cond, const int* text_flat, const int* text_start, const int* n_text,
               const int* row_uncond, const float* text_emb, int text_vocab, const float* text_pos,

@@ -43,7 +43,7 @@ struct GemmDev {
   int k_total;    // logical K (ntaps*c_in for WINDOW, ntaps*ctap for TAPS)
   int has_seq;
   SeqMap seq;
-  int precise;    // 1: split activations into 3 bf16 planes (24 significand bits) instead of 2
+  int a_tma;      // set by the launcher: A tile is fetched by TMA (plain strided fp32 rows)
   // ---- B operand -------------------------------------------------------------------------------
   const __nv_bfloat16* Wp;  // [Npad][Kpad]
   int Kpad, Npad;
@@ -59,6 +59,7 @@ struct GemmDev {
   int swiglu;                                   // columns (2j,2j+1) -> out[j] = silu(v0)*v1
   float* C2; int ldc2; int act2; float act2_p; const float* act2_vec;  // optional 2nd output act2(v)
   __nv_bfloat16* Chi; __nv_bfloat16* Clo; int ldcb;   // optional bf16 hi/lo planes of v (C may then be null)
+  long long* dbg;   // optional [64] clock64 timestamps of CTA (0,0) (kernel anatomy debugging)
 };
 
 struct Arena {  // bump allocator over caller-owned workspace; dry=true only counts
