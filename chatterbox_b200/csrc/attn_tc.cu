@@ -49,7 +49,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   const int nblk = (kvlen + AT_BN - 1) / AT_BN;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the __shared__ address space (LDS/STS instead of generic LD/ST): offset the shared pointer, do not round-trip through an integer
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                   // [hi: 128 rows][lo: 128 rows]
   uint8_t* sKV = sQ + AT_Q_BYTES;                       // stages of [Khi][Klo][Vhi][Vlo]
   uint8_t* sP = sKV + AT_STAGES * AT_KV_STAGE;          // [hi: 128 rows][lo: 128 rows]

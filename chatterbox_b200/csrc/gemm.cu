@@ -129,7 +129,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the __shared__ address space (LDS/STS instead of generic LD/ST): offset the shared pointer, do not round-trip through an integer
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* tma_full = bars;                  // [STAGES] TMA bytes landed (W, and the fp32 A tile in TMA mode)
   uint64_t* conv_full = bars + STAGES;        // [STAGES] 8 converter-warp arrivals: bf16 planes ready
@@ -254,8 +255,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         const int nout = (n0 + col) / 2 + lane;
         const bool colok = lane < 16 && nin < g.n_out;
         const float b0 = (colok && g.bias) ? g.bias[nin] : 0.f, b1 = (colok && g.bias) ? g.bias[nin + 1] : 0.f;
+        const unsigned vmask = __ballot_sync(0xffffffffu, myvalid != 0);
+#pragma unroll 4
         for (int rr = 0; rr < rows_here; ++rr) {
-          const int rv = __shfl_sync(0xffffffffu, myvalid, rr);
+          const bool rv = (vmask >> rr) & 1u;
           if (colok) {
             const float v0 = st[rr * 33 + 2 * lane] * g.alpha + b0, v1 = st[rr * 33 + 2 * lane + 1] * g.alpha + b1;
             float v = (v0 / (1.0f + expf(-v0))) * v1;
@@ -269,35 +272,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         const float bias = (colok && g.bias) ? g.bias[n] : 0.f;
         const float ap = (colok && g.act_vec) ? g.act_vec[n] : g.act_p;
         const float ap2 = (colok && g.act2_vec) ? g.act2_vec[n] : g.act2_p;
-        for (int rr = 0; rr < rows_here; ++rr) {
-          const int rv = __shfl_sync(0xffffffffu, myvalid, rr);
-          if (!colok) continue;
-          const long grow = m0 + q * 32 + rr;
-          float v = st[rr * 33 + lane] * g.alpha + bias;
-          switch (g.act) {                      // one inline copy of each activation (no per-element call)
-            case ACT_NONE: break;
-            case ACT_GELU: v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); break;
-            case ACT_SILU: v = v / (1.0f + expf(-v)); break;
-            case ACT_LRELU: v = v > 0.f ? v : v * ap; break;
-            case ACT_SNAKE: { const float sn = sinf(v * ap); v = v + (1.0f / (ap + 1e-9f)) * (sn * sn); } break;
-            case ACT_ELU: v = v > 0.f ? v : expm1f(v); break;
-            default: v = act_apply_slow(g.act, v, ap); break;
+        const unsigned vmask = __ballot_sync(0xffffffffu, myvalid != 0);     // bit rr = row rr of this warp is a real row
+        for (int r0 = 0; r0 < rows_here; r0 += 4) {                           // 4 rows per trip: loads first, then math/stores
+          float xv[4], rres[4], cold[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int rr = r0 + u;
+            const long grow = m0 + q * 32 + rr;
+            const bool ok = colok && rr < rows_here;
+            xv[u] = ok ? st[rr * 33 + lane] : 0.f;
+            rres[u] = (ok && g.res) ? g.res[grow * g.ldr + n] : 0.f;
+            cold[u] = (ok && g.accumulate && g.C) ? g.C[grow * g.ldc + n] : 0.f;
           }
-          if (g.res) v += g.res[grow * g.ldr + n];
-          v *= g.out_scale;
-          if (!rv) v = 0.f;
-          if (g.Chi) {
-            __nv_bfloat16 h, l;
-            split_bf16(v, h, l);
-            g.Chi[grow * g.ldcb + n] = h;
-            g.Clo[grow * g.ldcb + n] = l;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int rr = r0 + u;
+            if (!colok || rr >= rows_here) continue;
+            const long grow = m0 + q * 32 + rr;
+            const bool rv = (vmask >> rr) & 1u;
+            float v = xv[u] * g.alpha + bias;
+            switch (g.act) {                      // one inline copy of each activation (no per-element call)
+              case ACT_NONE: break;
+              case ACT_GELU: v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); break;
+              case ACT_SILU: v = v / (1.0f + expf(-v)); break;
+              case ACT_LRELU: v = v > 0.f ? v : v * ap; break;
+              case ACT_SNAKE: { const float sn = sinf(v * ap); v = v + (1.0f / (ap + 1e-9f)) * (sn * sn); } break;
+              case ACT_ELU: v = v > 0.f ? v : expm1f(v); break;
+              default: v = act_apply_slow(g.act, v, ap); break;
+            }
+            v += rres[u];
+            v *= g.out_scale;
+            if (!rv) v = 0.f;
+            if (g.Chi) {
+              __nv_bfloat16 h, l;
+              split_bf16(v, h, l);
+              g.Chi[grow * g.ldcb + n] = h;
+              g.Clo[grow * g.ldcb + n] = l;
+            }
+            if (g.C) {
+              if (rv) v += cold[u];
+              g.C[grow * g.ldc + n] = v;
+            }
+            if (g.C2) g.C2[grow * g.ldc2 + n] = rv ? act_apply(g.act2, v, ap2) : 0.f;
           }
-          if (g.C) {
-            float* cp = g.C + grow * g.ldc + n;
-            if (g.accumulate && rv) v += *cp;
-            *cp = v;
-          }
-          if (g.C2) g.C2[grow * g.ldc2 + n] = rv ? act_apply(g.act2, v, ap2) : 0.f;
         }
       }
       __syncwarp();
