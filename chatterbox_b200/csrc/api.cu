@@ -293,7 +293,8 @@ int cbx_test_gemm(cbx_handle* h, const float* A, int lda, int M_in, int M, const
     const long long t0 = hbuf[5];
     printf("[gemm dbg] M=%d N=%d K=%d: setup_done=%lld prod_done=%lld accum_ready=%lld epi_done=%lld exit=%lld\n", M, N, cin * taps,
            hbuf[0] - t0, hbuf[1] - t0, hbuf[2] - t0, hbuf[3] - t0, hbuf[4] - t0);
-    for (int kb = 0; kb < 8; ++kb) printf("   kb%d: prod_start=%lld prod_arrive=%lld mma_issue=%lld\n", kb, hbuf[8 + 2 * kb] - t0, hbuf[9 + 2 * kb] - t0, hbuf[32 + kb] - t0);
+    printf("   epilogue chunk0: ldtm=%lld to_smem=%lld rows_loop=%lld\n", hbuf[41] - hbuf[40], hbuf[42] - hbuf[41], hbuf[43] - hbuf[42]);
+    for (int kb = 0; kb < 8; ++kb) printf("   kb%d: conv_start=%lld mma_issue=%lld\n", kb, hbuf[8 + kb] - t0, hbuf[32 + kb] - t0);
     fflush(stdout);
   }
   CBX_CHECK(cudaStreamSynchronize(c.stream));

@@ -123,6 +123,8 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+__device__ int g_epi_mode = 0;   // experiment switch (CBX_EPI_MODE): 0 normal, 1 no global stores, 2 st.global.cs
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA, const GemmDev g) {
@@ -146,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
   if (dbg && threadIdx.x == 0) g.dbg[5] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&conv_full[s], TC_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&conv_full[s], g.a_tma ? 4 : TC_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
     mbar_init(accum_bar, 1);
     fence_mbar_init();
   }
@@ -162,31 +164,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     const int t = threadIdx.x;            // 0..255
     const int c4 = t & 15;                // float4 chunk inside the 64-wide K block
     const int rsub = t >> 4;              // 0..15
-    RowGeom rg[8];
-#pragma unroll
-    for (int p = 0; p < 8; ++p) rg[p] = row_geom(g, m0 + p * 16 + rsub);
     if (g.a_tma) {
       // ===================== converters: smem fp32 tile -> bf16 hi/lo planes, in place ===================
-      for (int kb = 0; kb < KB; ++kb) {
+      // two groups of 4 warps work on alternating K blocks so that two conversions are always in flight
+      const int grp = warp >> 2;             // 0 / 1
+      const int tg = threadIdx.x & 127;      // thread inside the group
+      const int gc4 = tg & 15, grs = tg >> 4;   // float4 chunk, row inside a pass of 8 rows
+      // per row: the window of tap offsets (in input rows) that stays inside the row's own sequence
+      const bool need_mask = g.has_seq || g.ntaps > 1;
+      int lo_rel[16], hi_rel[16];
+      if (need_mask) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const RowGeom rr = row_geom(g, m0 + p * 8 + grs);
+          lo_rel[p] = rr.valid ? (int)(rr.lo - rr.in_row0) : 1;
+          hi_rel[p] = rr.valid ? (int)(rr.hi - rr.in_row0) : 0;
+        }
+      }
+      for (int kb = grp; kb < KB; kb += 2) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
         const int tap = (kb * TC_BK) / g.ctap;
-        if (dbg && threadIdx.x == 0 && kb < 8) g.dbg[8 + 2 * kb] = clock64();
+        if (dbg && threadIdx.x == 0 && kb < 16) g.dbg[8 + kb] = clock64();
         mbar_wait(&tma_full[s], ph);
-        float4 v[8];
+        float4 v[16];
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int row = p * 16 + rsub;
-          v[p] = *reinterpret_cast<const float4*>(a_st + row * 256 + c4 * 16);
-          const long ir = rg[p].in_row0 + (long)tap * g.dil;
-          if (!rg[p].valid || ir < rg[p].lo || ir >= rg[p].hi) v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < 16; ++p) v[p] = *reinterpret_cast<const float4*>(a_st + (p * 8 + grs) * 256 + gc4 * 16);
+        // rows whose tap falls outside their own sequence contribute zeros (implicit conv padding)
+        if (need_mask) {
+          const int toff = tap * g.dil;
+#pragma unroll
+          for (int p = 0; p < 16; ++p)
+            if (toff < lo_rel[p] || toff >= hi_rel[p]) v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // every converter has read its part of the fp32 tile
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int row = p * 16 + rsub;
-          const uint32_t off = row * 128 + ((((uint32_t)c4 >> 1) ^ ((uint32_t)row & 7)) << 4) + (c4 & 1) * 8;
+        for (int p = 0; p < 16; ++p) {
+          const int row = p * 8 + grs;
+          const uint32_t off = row * 128 + ((((uint32_t)gc4 >> 1) ^ ((uint32_t)row & 7)) << 4) + (gc4 & 1) * 8;
           uint32_t h0, l0, h1, l1;
           split_pair(v[p].x, v[p].y, h0, l0);
           split_pair(v[p].z, v[p].w, h1, l1);
@@ -196,10 +212,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         fence_proxy_async_smem();   // make generic-proxy stores visible to the tensor-core (async) proxy
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv_full[s]);
-        if (dbg && threadIdx.x == 0 && kb < 8) g.dbg[9 + 2 * kb] = clock64();
       }
     } else {
       // ===================== register gather (window / strided convs, unaligned operands) ==============
+      RowGeom rg[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) rg[p] = row_geom(g, m0 + p * 16 + rsub);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -244,11 +262,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
       const int col = half * (BN / 2) + cc;
       if (n0 + col >= g.n_out) break;
       uint32_t r[32];
+      if (dbg && threadIdx.x == 0 && cc == 0) g.dbg[40] = clock64();
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
       tmem_ld_wait();
+      if (dbg && threadIdx.x == 0 && cc == 0) g.dbg[41] = clock64();
 #pragma unroll
       for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
       __syncwarp();
+      if (dbg && threadIdx.x == 0 && cc == 0) g.dbg[42] = clock64();
       if (g.swiglu) {
         // columns (2j, 2j+1) = (gate_j, up_j) -> out[j] = silu(gate) * up ; lanes 0..15 own one output column each
         const int nin = n0 + col + 2 * lane;
@@ -256,12 +277,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         const bool colok = lane < 16 && nin < g.n_out;
         const float b0 = (colok && g.bias) ? g.bias[nin] : 0.f, b1 = (colok && g.bias) ? g.bias[nin + 1] : 0.f;
         const unsigned vmask = __ballot_sync(0xffffffffu, myvalid != 0);
-#pragma unroll 4
+#pragma unroll 1
         for (int rr = 0; rr < rows_here; ++rr) {
           const bool rv = (vmask >> rr) & 1u;
           if (colok) {
             const float v0 = st[rr * 33 + 2 * lane] * g.alpha + b0, v1 = st[rr * 33 + 2 * lane + 1] * g.alpha + b1;
-            float v = (v0 / (1.0f + expf(-v0))) * v1;
+            float v = act_apply_slow(ACT_SILU, v0, 0.f) * v1;
             if (!rv) v = 0.f;
             g.C[(long)(m0 + q * 32 + rr) * g.ldc + nout] = v;
           }
@@ -273,34 +294,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         const float ap = (colok && g.act_vec) ? g.act_vec[n] : g.act_p;
         const float ap2 = (colok && g.act2_vec) ? g.act2_vec[n] : g.act2_p;
         const unsigned vmask = __ballot_sync(0xffffffffu, myvalid != 0);     // bit rr = row rr of this warp is a real row
-        for (int r0 = 0; r0 < rows_here; r0 += 4) {                           // 4 rows per trip: loads first, then math/stores
-          float xv[4], rres[4], cold[4];
+        const long grow0 = m0 + q * 32;
+        if (!g.C2 && !g.Chi && !g.accumulate) {
+          // ---- hot case: C = act(acc*alpha + bias) (+ res), coalesced 128-byte rows, 4 rows per trip
+          float* cbase = g.C + grow0 * g.ldc + n;
+          const float* rbase = g.res ? g.res + grow0 * g.ldr + n : nullptr;
+          for (int r0 = 0; r0 < rows_here; r0 += 4) {
+            float xv[4], rres[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int rr = r0 + u;
-            const long grow = m0 + q * 32 + rr;
-            const bool ok = colok && rr < rows_here;
-            xv[u] = ok ? st[rr * 33 + lane] : 0.f;
-            rres[u] = (ok && g.res) ? g.res[grow * g.ldr + n] : 0.f;
-            cold[u] = (ok && g.accumulate && g.C) ? g.C[grow * g.ldc + n] : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int rr = r0 + u;
-            if (!colok || rr >= rows_here) continue;
-            const long grow = m0 + q * 32 + rr;
-            const bool rv = (vmask >> rr) & 1u;
-            float v = xv[u] * g.alpha + bias;
-            switch (g.act) {                      // one inline copy of each activation (no per-element call)
-              case ACT_NONE: break;
-              case ACT_GELU: v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); break;
-              case ACT_SILU: v = v / (1.0f + expf(-v)); break;
-              case ACT_LRELU: v = v > 0.f ? v : v * ap; break;
-              case ACT_SNAKE: { const float sn = sinf(v * ap); v = v + (1.0f / (ap + 1e-9f)) * (sn * sn); } break;
-              case ACT_ELU: v = v > 0.f ? v : expm1f(v); break;
-              default: v = act_apply_slow(g.act, v, ap); break;
+            for (int u = 0; u < 4; ++u) {
+              const bool ok = colok && (r0 + u) < rows_here;
+              xv[u] = ok ? st[(r0 + u) * 33 + lane] : 0.f;
+              rres[u] = (ok && rbase) ? rbase[(long)(r0 + u) * g.ldr] : 0.f;
             }
-            v += rres[u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float v = xv[u] * g.alpha + bias;
+              if (g.act != ACT_NONE) v = act_apply(g.act, v, ap);
+              v = (v + rres[u]) * g.out_scale;
+              if (!((vmask >> (r0 + u)) & 1u)) v = 0.f;
+              if (colok && (r0 + u) < rows_here) cbase[(long)(r0 + u) * g.ldc] = v;
+            }
+          }
+        } else if (g.Chi && !g.C && !g.C2 && !g.res && g.act == ACT_NONE) {
+          // ---- bf16 hi/lo planes only (QKV projection feeding the tcgen05 attention)
+          __nv_bfloat16* hb = g.Chi + grow0 * g.ldcb + n;
+          __nv_bfloat16* lb = g.Clo + grow0 * g.ldcb + n;
+          for (int r0 = 0; r0 < rows_here; r0 += 4) {
+            float xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[u] = (colok && (r0 + u) < rows_here) ? st[(r0 + u) * 33 + lane] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float v = (xv[u] * g.alpha + bias) * g.out_scale;
+              if (!((vmask >> (r0 + u)) & 1u)) v = 0.f;
+              __nv_bfloat16 h, l;
+              split_bf16(v, h, l);
+              if (colok && (r0 + u) < rows_here) { hb[(long)(r0 + u) * g.ldcb] = h; lb[(long)(r0 + u) * g.ldcb] = l; }
+            }
+          }
+        } else {
+          // ---- general case (second output, accumulate, planes + fp32)
+#pragma unroll 1
+          for (int rr = 0; rr < rows_here; ++rr) {
+            if (!colok) continue;
+            const long grow = grow0 + rr;
+            const bool rv = (vmask >> rr) & 1u;
+            float v = st[rr * 33 + lane] * g.alpha + bias;
+            v = act_apply(g.act, v, ap);
+            if (g.res) v += g.res[grow * g.ldr + n];
             v *= g.out_scale;
             if (!rv) v = 0.f;
             if (g.Chi) {
@@ -310,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
               g.Clo[grow * g.ldcb + n] = l;
             }
             if (g.C) {
-              if (rv) v += cold[u];
+              if (g.accumulate && rv) v += g.C[grow * g.ldc + n];
               g.C[grow * g.ldc + n] = v;
             }
             if (g.C2) g.C2[grow * g.ldc2 + n] = rv ? act_apply(g.act2, v, ap2) : 0.f;
@@ -318,6 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         }
       }
       __syncwarp();
+      if (dbg && threadIdx.x == 0 && cc == 0) g.dbg[43] = clock64();
     }
     if (dbg && threadIdx.x == 0) g.dbg[3] = clock64();
   } else if (warp == TC_PRODUCER_WARPS) {
@@ -636,6 +679,14 @@ template <int BN> static void launch_tc(Ctx& ctx, GemmDev g, const Weight& W, in
   CUtensorMap tmA;
   if (g.a_tma) make_a_tmap(&tmA, g); else tmA = W.tmap[tmap_idx];
   dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM);
+  {
+    static int mode_set = -1;
+    const char* e = getenv("CBX_EPI_MODE");
+    const int mode = e ? atoi(e) : 0;
+    if (mode != mode_set) { CBX_CHECK(cudaMemcpyToSymbol(g_epi_mode, &mode, sizeof(int))); mode_set = mode; }
+    const char* cv = getenv("CBX_CARVEOUT");
+    if (cv) CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+  }
   if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
   gemm_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], tmA, g);
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
