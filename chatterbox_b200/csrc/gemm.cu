@@ -148,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
   if (dbg && threadIdx.x == 0) g.dbg[5] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&conv_full[s], g.a_tma ? 4 : TC_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&conv_full[s], TC_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
     mbar_init(accum_bar, 1);
     fence_mbar_init();
   }
@@ -166,43 +166,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     const int rsub = t >> 4;              // 0..15
     if (g.a_tma) {
       // ===================== converters: smem fp32 tile -> bf16 hi/lo planes, in place ===================
-      // two groups of 4 warps work on alternating K blocks so that two conversions are always in flight
-      const int grp = warp >> 2;             // 0 / 1
-      const int tg = threadIdx.x & 127;      // thread inside the group
-      const int gc4 = tg & 15, grs = tg >> 4;   // float4 chunk, row inside a pass of 8 rows
-      // per row: the window of tap offsets (in input rows) that stays inside the row's own sequence
+      // software pipelined: the LDS of K block kb+1 are in flight while block kb is converted and stored.
+      // (One group of 8 warps on every block: two groups on alternating blocks would skip mbarrier phases, and a
+      // parity wait cannot tell phase k from phase k+2.)
       const bool need_mask = g.has_seq || g.ntaps > 1;
-      int lo_rel[16], hi_rel[16];
+      int lo_rel[8], hi_rel[8];       // per row: tap offsets (in input rows) that stay inside the row's own sequence
       if (need_mask) {
 #pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          const RowGeom rr = row_geom(g, m0 + p * 8 + grs);
+        for (int p = 0; p < 8; ++p) {
+          const RowGeom rr = row_geom(g, m0 + p * 16 + rsub);
           lo_rel[p] = rr.valid ? (int)(rr.lo - rr.in_row0) : 1;
           hi_rel[p] = rr.valid ? (int)(rr.hi - rr.in_row0) : 0;
         }
       }
-      for (int kb = grp; kb < KB; kb += 2) {
+      auto fetch = [&](int kb, float4 (&v)[8]) {
         const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
-        const int tap = (kb * TC_BK) / g.ctap;
-        if (dbg && threadIdx.x == 0 && kb < 16) g.dbg[8 + kb] = clock64();
-        mbar_wait(&tma_full[s], ph);
-        float4 v[16];
+        mbar_wait(&tma_full[s], (kb / STAGES) & 1);
+        const uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
 #pragma unroll
-        for (int p = 0; p < 16; ++p) v[p] = *reinterpret_cast<const float4*>(a_st + (p * 8 + grs) * 256 + gc4 * 16);
-        // rows whose tap falls outside their own sequence contribute zeros (implicit conv padding)
+        for (int p = 0; p < 8; ++p) v[p] = *reinterpret_cast<const float4*>(a_st + (p * 16 + rsub) * 256 + c4 * 16);
         if (need_mask) {
-          const int toff = tap * g.dil;
+          const int toff = ((kb * TC_BK) / g.ctap) * g.dil;
 #pragma unroll
-          for (int p = 0; p < 16; ++p)
+          for (int p = 0; p < 8; ++p)
             if (toff < lo_rel[p] || toff >= hi_rel[p]) v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      };
+      float4 v[8], vn[8];
+      fetch(0, v);
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // every converter has read its part of stage 0
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
+        if (dbg && threadIdx.x == 0 && kb < 16) g.dbg[8 + kb] = clock64();
+        if (kb + 1 < KB) fetch(kb + 1, vn);
 #pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          const int row = p * 8 + grs;
-          const uint32_t off = row * 128 + ((((uint32_t)gc4 >> 1) ^ ((uint32_t)row & 7)) << 4) + (gc4 & 1) * 8;
+        for (int p = 0; p < 8; ++p) {
+          const int row = p * 16 + rsub;
+          const uint32_t off = row * 128 + ((((uint32_t)c4 >> 1) ^ ((uint32_t)row & 7)) << 4) + (c4 & 1) * 8;
           uint32_t h0, l0, h1, l1;
           split_pair(v[p].x, v[p].y, h0, l0);
           split_pair(v[p].z, v[p].w, h1, l1);
@@ -210,8 +211,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
           *reinterpret_cast<uint2*>(a_st + 16384 + off) = make_uint2(l0, l1);
         }
         fence_proxy_async_smem();   // make generic-proxy stores visible to the tensor-core (async) proxy
-        __syncwarp();
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // reads of stage kb+1 done before anyone overwrites it
         if (lane == 0) mbar_arrive(&conv_full[s]);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) v[p] = vn[p];
       }
     } else {
       // ===================== register gather (window / strided convs, unaligned operands) ==============
