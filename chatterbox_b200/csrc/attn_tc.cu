@@ -27,6 +27,20 @@ struct AttnTcDev {
   int q_col, k_col, v_col;   // column offsets of head 0 inside the packed planes
 };
 
+__device__ __forceinline__ float fast_exp2(float x) {      // ex2.approx: 2 ulp, -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// fp32 pair -> bf16x2 hi word and lo word (one F2FP each)
+__device__ __forceinline__ void split_pair_at(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float fa = __uint_as_float(hi << 16), fb = __uint_as_float(hi & 0xFFFF0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - fa, b - fb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // MN-major SWIZZLE_128B descriptor (B operand stored [k][n], n contiguous, 64 n = one 128-byte row):
 // 8 k-rows per 1024-byte atom, atoms along k are SBO = 1024 B apart (cute/arch/mma_sm100_desc.hpp).
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
@@ -173,19 +187,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       // scores in the log2 domain; keys beyond the sequence are masked
       const int kbase = j * AT_BN;
       float mx = m;
+      if (kbase + AT_BN > kvlen) {                 // only the last key block needs the length mask
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float a = __uint_as_float(r0[i]) * p.scale_log2e, b = __uint_as_float(r1[i]) * p.scale_log2e;
-        if (kbase + i >= kvlen) a = -INFINITY;
-        if (kbase + 32 + i >= kvlen) b = -INFINITY;
-        r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(b);
-        mx = fmaxf(mx, fmaxf(a, b));
+        for (int i = 0; i < 32; ++i) {
+          if (kbase + i >= kvlen) r0[i] = 0xff800000u;        // -inf
+          if (kbase + 32 + i >= kvlen) r1[i] = 0xff800000u;
+        }
       }
-      const float c = (m == -INFINITY) ? 1.f : exp2f(m - mx);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+      // raw scores are unscaled; the (positive) scale commutes with max, so scale once here
+      const float mxs = mx * p.scale_log2e;
+      const float c = (m == -INFINITY) ? 1.f : fast_exp2(m * p.scale_log2e - mxs);
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float a = exp2f(__uint_as_float(r0[i]) - mx), b = exp2f(__uint_as_float(r1[i]) - mx);
+        const float a = fast_exp2(fmaf(__uint_as_float(r0[i]), p.scale_log2e, -mxs));
+        const float b = fast_exp2(fmaf(__uint_as_float(r1[i]), p.scale_log2e, -mxs));
         sum += a + b;
         r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(b);
       }
@@ -218,9 +236,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           const int i = ch * 8 + e * 2;
           const float a = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
           const float b = __uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]);
-          __nv_bfloat16 ah, al, bh, bl;
-          split_bf16(a, ah, al); split_bf16(b, bh, bl);
-          hi[e] = pack_bf16(ah, bh); lo[e] = pack_bf16(al, bl);
+          split_pair_at(a, b, hi[e], lo[e]);
         }
         const uint32_t off = ((uint32_t)(ch ^ (row & 7))) << 4;
         *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

@@ -299,22 +299,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         const unsigned vmask = __ballot_sync(0xffffffffu, myvalid != 0);     // bit rr = row rr of this warp is a real row
         const long grow0 = m0 + q * 32;
         if (!g.C2 && !g.Chi && !g.accumulate) {
-          // ---- hot case: C = act(acc*alpha + bias) (+ res), coalesced 128-byte rows, 4 rows per trip
+          // ---- hot case: C = act(acc*alpha + bias) (+ res), coalesced 128-byte rows
+          const bool pre = g.act != ACT_NONE && colok;
+          if (pre) {
+            // activation pass in place on the staged tile: ONE inline copy of each activation in a rolled loop
+            // (calls from the store loop spill its live registers; inlining into the unrolled loop thrashes the I-cache)
+#pragma unroll 1
+            for (int rr = 0; rr < rows_here; ++rr) {
+              float v = st[rr * 33 + lane] * g.alpha + bias;
+              switch (g.act) {
+                case ACT_GELU: v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); break;
+                case ACT_SILU: v = v / (1.0f + expf(-v)); break;
+                case ACT_LRELU: v = v > 0.f ? v : v * ap; break;
+                case ACT_SNAKE: { const float sn = sinf(v * ap); v = v + (1.0f / (ap + 1e-9f)) * (sn * sn); } break;
+                case ACT_ELU: v = v > 0.f ? v : expm1f(v); break;
+                default: v = act_apply_slow(g.act, v, ap); break;
+              }
+              st[rr * 33 + lane] = v;
+            }
+          }
+          const float a_mul = pre ? 1.0f : g.alpha, a_add = pre ? 0.0f : bias;
           float* cbase = g.C + grow0 * g.ldc + n;
           const float* rbase = g.res ? g.res + grow0 * g.ldr + n : nullptr;
-          for (int r0 = 0; r0 < rows_here; r0 += 4) {
-            float xv[4], rres[4];
+          for (int r0 = 0; r0 < rows_here; r0 += 8) {
+            float xv[8], rres[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
               const bool ok = colok && (r0 + u) < rows_here;
               xv[u] = ok ? st[(r0 + u) * 33 + lane] : 0.f;
               rres[u] = (ok && rbase) ? rbase[(long)(r0 + u) * g.ldr] : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float v = xv[u] * g.alpha + bias;
-              if (g.act != ACT_NONE) v = act_apply(g.act, v, ap);
-              v = (v + rres[u]) * g.out_scale;
+            for (int u = 0; u < 8; ++u) {
+              float v = (xv[u] * a_mul + a_add + rres[u]) * g.out_scale;
               if (!((vmask >> (r0 + u)) & 1u)) v = 0.f;
               if (colok && (r0 + u) < rows_here) cbase[(long)(r0 + u) * g.ldc] = v;
             }
@@ -323,12 +340,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
           // ---- bf16 hi/lo planes only (QKV projection feeding the tcgen05 attention)
           __nv_bfloat16* hb = g.Chi + grow0 * g.ldcb + n;
           __nv_bfloat16* lb = g.Clo + grow0 * g.ldcb + n;
-          for (int r0 = 0; r0 < rows_here; r0 += 4) {
-            float xv[4];
+          for (int r0 = 0; r0 < rows_here; r0 += 8) {
+            float xv[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) xv[u] = (colok && (r0 + u) < rows_here) ? st[(r0 + u) * 33 + lane] : 0.f;
+            for (int u = 0; u < 8; ++u) xv[u] = (colok && (r0 + u) < rows_here) ? st[(r0 + u) * 33 + lane] : 0.f;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
               float v = (xv[u] * g.alpha + bias) * g.out_scale;
               if (!((vmask >> (r0 + u)) & 1u)) v = 0.f;
               __nv_bfloat16 h, l;
