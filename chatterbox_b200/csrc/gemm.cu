@@ -105,8 +105,10 @@ constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;   // + TMA warp + MMA warp
 
-template <int BN> struct TcCfg {
-  static constexpr int STAGES = (BN == 256) ? 3 : 4;
+// DUAL = 1: shallow 2-stage pipeline but two CTAs per SM, so one CTA's epilogue (LSU / ALU) runs under the other's
+// main loop (TMA / tensor pipe) without a persistent-kernel restructure.
+template <int BN, int DUAL = 0> struct TcCfg {
+  static constexpr int STAGES = DUAL ? 2 : ((BN == 256) ? 3 : 4);
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;        // fp32 tile == two bf16 planes of 16 KB (converted in place)
   static constexpr int W_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
@@ -123,12 +125,10 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-__device__ int g_epi_mode = 0;   // experiment switch (CBX_EPI_MODE): 0 normal, 1 no global stores, 2 st.global.cs
-
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, int DUAL>
+__global__ void __launch_bounds__(TC_THREADS, DUAL ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA, const GemmDev g) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, DUAL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // keep the __shared__ address space (LDS/STS instead of generic LD/ST): offset the shared pointer, do not round-trip through an integer
@@ -687,10 +687,10 @@ static void make_a_tmap(CUtensorMap* tm, const GemmDev& g) {
   if (r != CUDA_SUCCESS) throw std::runtime_error("cbx: cuTensorMapEncodeTiled (A operand) failed");
 }
 
-template <int BN> static void launch_tc(Ctx& ctx, GemmDev g, const Weight& W, int tmap_idx) {
+template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Weight& W, int tmap_idx) {
   static bool attr_set = false;
   if (!attr_set) {
-    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, DUAL>::SMEM));
     attr_set = true;
   }
   // TMA-fed A operand: plain strided fp32 rows (Linear, stride-1 conv taps)
@@ -699,16 +699,8 @@ template <int BN> static void launch_tc(Ctx& ctx, GemmDev g, const Weight& W, in
   CUtensorMap tmA;
   if (g.a_tma) make_a_tmap(&tmA, g); else tmA = W.tmap[tmap_idx];
   dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM);
-  {
-    static int mode_set = -1;
-    const char* e = getenv("CBX_EPI_MODE");
-    const int mode = e ? atoi(e) : 0;
-    if (mode != mode_set) { CBX_CHECK(cudaMemcpyToSymbol(g_epi_mode, &mode, sizeof(int))); mode_set = mode; }
-    const char* cv = getenv("CBX_CARVEOUT");
-    if (cv) CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
-  }
   if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
-  gemm_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], tmA, g);
+  gemm_tc_kernel<BN, DUAL><<<grid, TC_THREADS, TcCfg<BN, DUAL>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], tmA, g);
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
 }
 
@@ -741,9 +733,11 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     } else {
       const int mt = (g.M + TC_BM - 1) / TC_BM;
       // widest N tile that still gives every SM a tile (L2->SM traffic per flop falls with BN)
-      if (g.Npad % 256 == 0 && (long)mt * (g.Npad / 256) >= 120) launch_tc<256>(ctx, g, W, 2);
-      else if (g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 100) launch_tc<128>(ctx, g, W, 1);
-      else launch_tc<64>(ctx, g, W, 0);
+      static const int tile_mode = getenv("CBX_TILE") ? atoi(getenv("CBX_TILE")) : 0;   // 0 auto, 1 no dual (experiments)
+      if (tile_mode == 0 && g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 2 * 148) launch_tc<128, 1>(ctx, g, W, 1);
+      else if (g.Npad % 256 == 0 && (long)mt * (g.Npad / 256) >= 120) launch_tc<256, 0>(ctx, g, W, 2);
+      else if (g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 100) launch_tc<128, 0>(ctx, g, W, 1);
+      else launch_tc<64, 0>(ctx, g, W, 0);
     }
   }
   CBX_CHECK(cudaGetLastError());

@@ -15,3 +15,23 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def _usable_threads():
+    """Threads this container may really use (affinity + cgroup quota), not the host's core count: asking torch for
+    128 threads inside a 16-CPU cgroup makes every CPU oracle call crawl."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = min(n, max(1, int(float(q[0]) / float(q[1]))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
+try:
+    import torch
+    torch.set_num_threads(_usable_threads())
+except Exception:
+    pass

@@ -189,3 +189,18 @@ def test_tcgen05_attention_matches_sdpa():
         ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v))[0].transpose(0, 1).reshape(n, H * 64)
         err = relerr(O[sl], ref)
         assert err < 3e-5, f"seq{s} len{n}: {err}"
+
+
+def test_linear_gemm_dual_cta_tiles():
+    """enough 128x128 tiles for the two-CTAs-per-SM configuration (2-stage pipeline, GELU epilogue + residual)."""
+    from gpu_util import run_gemm, bf16r, relerr
+    g = torch.Generator().manual_seed(13)
+    M, K, N = 8192, 256, 1024
+    A = torch.randn(M, K, generator=g).cuda()
+    w = bf16r(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g) * 0.1
+    res = torch.randn(M, N, generator=g).cuda()
+    C_ = run_gemm(_eng(), A, w[:, :, None].contiguous(), b, act="gelu", res=res, impl="tc")
+    ref = F.gelu((A.double() @ w.double().t().cuda() + b.double().cuda()).float()) + res
+    err = relerr(C_, ref)
+    assert err < 3e-5, f"rel err {err}"

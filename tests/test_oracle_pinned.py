@@ -13,7 +13,6 @@ from oracle.t3_ref import T3Oracle
 from oracle.flow_ref import FlowOracle
 from oracle.hift_ref import HiFTOracle
 
-torch.set_num_threads(max(1, os.cpu_count() or 1))
 
 
 def test_t3_oracle_matches_reference_tokens_and_logits(golden_dir):
