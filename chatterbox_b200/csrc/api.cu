@@ -85,7 +85,7 @@ int cbx_set_option(cbx_handle* h, const char* key, const char* value) {
   if (k == "gemm") h->gemm_impl = (v == "simt") ? 1 : 0;
   else if (k == "attn") h->attn_impl = (v == "simt") ? 1 : 0;
   else if (k == "time_kernel") {
-    h->timer.drain(); h->timer.ms = 0.0; h->timer.n = 0;
+    h->timer.drain(); h->timer.ms = 0.0; h->timer.n = 0; h->timer.work = 0.0;
     h->timer.cls = v == "gemm_tc" ? K_GEMM_TC : v == "gemv" ? K_GEMV : v == "flash" ? K_FLASH : v == "paged" ? K_PAGED : K_NONE;
   }
   else { h->err = "unknown option " + k; return CBX_ERR_INVALID; }
@@ -94,10 +94,11 @@ int cbx_set_option(cbx_handle* h, const char* key, const char* value) {
 
 long long cbx_launch_count(cbx_handle* h) { return h ? h->launches : 0; }
 
-int cbx_timer_read(cbx_handle* h, double* ms, long long* launches) {
+int cbx_timer_read(cbx_handle* h, double* ms, long long* launches, double* work) {
   if (!h || !ms || !launches) return CBX_ERR_INVALID;
   h->timer.drain();
   *ms = h->timer.ms; *launches = h->timer.n;
+  if (work) *work = h->timer.work;
   return CBX_OK;
 }
 

@@ -699,6 +699,7 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
   CUtensorMap tmA;
   if (g.a_tma) make_a_tmap(&tmA, g); else tmA = W.tmap[tmap_idx];
   dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM);
+  if (ctx.timer && ctx.timer->cls == K_GEMM_TC) ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
   if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
   gemm_tc_kernel<BN, DUAL><<<grid, TC_THREADS, TcCfg<BN, DUAL>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], tmA, g);
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
@@ -734,9 +735,15 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
       const int mt = (g.M + TC_BM - 1) / TC_BM;
       // widest N tile that still gives every SM a tile (L2->SM traffic per flop falls with BN)
       static const int tile_mode = getenv("CBX_TILE") ? atoi(getenv("CBX_TILE")) : 0;   // 0 auto, 1 no dual (experiments)
-      if (tile_mode == 0 && g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 2 * 148) launch_tc<128, 1>(ctx, g, W, 1);
-      else if (g.Npad % 256 == 0 && (long)mt * (g.Npad / 256) >= 120) launch_tc<256, 0>(ctx, g, W, 2);
-      else if (g.Npad % 128 == 0 && (long)mt * (g.Npad / 128) >= 100) launch_tc<128, 0>(ctx, g, W, 1);
+      const long t64 = (long)mt * (g.Npad / 64);
+      const long t128 = (g.Npad % 128 == 0) ? (long)mt * (g.Npad / 128) : 0;
+      const long t256 = (g.Npad % 256 == 0) ? (long)mt * (g.Npad / 256) : 0;
+      // fewest waves first: two CTAs per SM when there are >= 2 tiles per SM, else the widest tile that still spreads
+      // over at least half of the SMs (per-tile time is latency-bound, so fewer, fatter tiles beat a second wave)
+      if (tile_mode == 0 && t128 >= 2 * 148) launch_tc<128, 1>(ctx, g, W, 1);
+      else if (t256 >= 120) launch_tc<256, 0>(ctx, g, W, 2);
+      else if (t128 >= 74) launch_tc<128, 0>(ctx, g, W, 1);
+      else if (tile_mode == 0 && t64 >= 2 * 148) launch_tc<64, 1>(ctx, g, W, 0);
       else launch_tc<64, 0>(ctx, g, W, 0);
     }
   }

@@ -86,6 +86,7 @@ struct KTimer {
   std::vector<cudaEvent_t> ev;   // pairs (start, stop)
   size_t used = 0;
   double ms = 0.0; long long n = 0;
+  double work = 0.0;             // algorithmic work of the timed launches (flops for GEMMs), added by the launcher
   void begin(int c, cudaStream_t st) {
     if (c != cls) return;
     if (used + 2 > ev.size()) {

@@ -56,8 +56,9 @@ int cbx_set_option(cbx_handle* h, const char* key, const char* value);
 long long cbx_launch_count(cbx_handle* h);
 /* cbx_set_option(h, "time_kernel", "paged"|"gemm_tc"|"gemv"|"flash"|"none") brackets every launch of that kernel
  * class with CUDA events on the launching stream; cbx_timer_read waits for them and returns the summed device
- * time and the number of launches since the option was set (bench.py's roofline object) */
-int cbx_timer_read(cbx_handle* h, double* ms, long long* launches);
+ * time and the number of launches since the option was set, plus (GEMM classes) the algorithmic flops 2*M*N*K of
+ * those launches (bench.py's roofline object) */
+int cbx_timer_read(cbx_handle* h, double* ms, long long* launches, double* work);
 /* host fp32 tensor with the reference's state-dict name ("t3." / "flow." / "hift." prefix added by the caller) */
 int cbx_load_tensor(cbx_handle* h, const char* name, const float* host_data, int ndim, const int64_t* shape);
 /* pack loaded tensors of one model ("t3" | "flow" | "hift"): bf16 K-major weights + TMA maps, QKV concat,

@@ -105,8 +105,51 @@ def golden_flow_hift():
     torch.save(out, os.path.join(OUT, "s3gen_golden.pt"))
 
 
+def golden_meanflow_and_mtl():
+    """Variants: meanflow 2-step estimator (Turbo's decoder, s3gen.py:313-317, flow_matching.py:235-246)
+    and the multilingual T3 (text vocab 2454, t3_config.py:28-41)."""
+    R.install()
+    from chatterbox.models.t3.modules.cond_enc import T3Cond
+    fsd = W.make_flow_weights(0, meanflow=True)
+    flow = R.build_flow(meanflow=True)
+    flow.load_state_dict(fsd, strict=True)
+    out = dict(weights_seed=0)
+    np_, n = 30, 21
+    _, cg = W.make_conds(seed=1234, n_gen_prompt=np_)
+    tok = torch.randint(0, 6561, (1, n), generator=torch.Generator().manual_seed(9))
+    torch.manual_seed(77)
+    noise = torch.randn(1, 80, 2 * n)                      # s3gen.py:316
+    z = torch.randn(1, 80, 2 * (np_ + n))                  # flow_matching.py:216
+    z[..., 2 * np_:] = noise                               # flow_matching.py:218-220
+    torch.manual_seed(77)
+    noise2 = torch.randn(1, 80, 2 * n)
+    mel, _ = flow.inference(token=tok, token_len=torch.tensor([n]), prompt_token=cg["prompt_token"],
+                            prompt_token_len=cg["prompt_token_len"], prompt_feat=cg["prompt_feat"], prompt_feat_len=None,
+                            embedding=cg["embedding"], finalize=True, n_timesteps=2, noised_mels=noise2, meanflow=True)
+    out["meanflow"] = dict(n_prompt=np_, n=n, tokens=tok, z=z, mel=mel.clone())
+    print("meanflow", mel.shape, float(mel.std()))
+    # multilingual T3
+    sd = W.make_t3_weights(1, text_vocab=2454)
+    t3 = R.build_t3(multilingual=True)
+    t3.load_state_dict(sd, strict=True)
+    c3, _ = W.make_conds()
+    g = torch.Generator().manual_seed(31)
+    text = torch.randint(1, 2454, (1, 33), generator=g)
+    text[text == 255] = 256
+    text = F.pad(F.pad(torch.cat([text, text], 0), (1, 0), value=255), (0, 1), value=0)
+    torch.manual_seed(5)
+    toks = t3.inference(t3_cond=T3Cond(speaker_emb=c3["speaker_emb"], cond_prompt_speech_tokens=c3["cond_prompt_speech_tokens"],
+                                       emotion_adv=c3["emotion_adv"]),
+                        text_tokens=text, max_new_tokens=10, temperature=0.8, top_p=1.0, min_p=1.0,
+                        repetition_penalty=2.0, cfg_weight=0.5)
+    out["mtl"] = dict(weights_seed=1, text_tokens=text, tokens=toks.clone())
+    print("mtl", toks.tolist())
+    torch.save(out, os.path.join(OUT, "variants_golden.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     golden_t3()
     golden_flow_hift()
+    golden_meanflow_and_mtl()

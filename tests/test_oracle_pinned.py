@@ -61,3 +61,19 @@ def test_weight_norm_fold_is_bf16_representable_to_1ulp_fp32():
     for k, v in folded.items():
         if k.endswith(".weight") and v.dim() == 3 and "source_downs" not in k:
             assert ((v - W.bf16_round(v)).abs() <= 2e-7 * v.abs()).all(), k
+
+
+def test_variants_meanflow_and_multilingual(golden_dir):
+    """meanflow 2-step estimator and the multilingual T3 vocabulary, against the reference's outputs."""
+    g = torch.load(os.path.join(golden_dir, "variants_golden.pt"))
+    mf = g["meanflow"]
+    fo = FlowOracle(W.make_flow_weights(g["weights_seed"], meanflow=True), meanflow=True)
+    _, cg = W.make_conds(seed=1234, n_gen_prompt=mf["n_prompt"])
+    mel = fo.inference(mf["tokens"], cg, 2, z=mf["z"])
+    assert ((mel - mf["mel"]) ** 2).mean().sqrt().item() < 1e-4
+    mt = g["mtl"]
+    sd = W.make_t3_weights(mt["weights_seed"], text_vocab=2454)
+    c3, _ = W.make_conds()
+    toks = T3Oracle(sd).inference(c3, mt["text_tokens"], 10, temperature=0.8, top_p=1.0, min_p=1.0,
+                                  repetition_penalty=2.0, cfg_weight=0.5)
+    assert torch.equal(toks, mt["tokens"])

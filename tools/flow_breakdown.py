@@ -16,5 +16,5 @@ for cls in ["none", "flash", "gemm_tc"]:
     l0 = eng.h.launch_count()
     mels = eng.flow_mel(toks, cg)
     torch.cuda.synchronize(); dt = time.time() - t0
-    ms, n = eng.h.timer_read()
-    print(f"class={cls} wall={dt:.2f}s kernel_ms={ms:.1f} launches={n} total_launches={eng.h.launch_count()-l0} frames={sum(2*(250+t.numel()) for t in toks)}", flush=True)
+    ms, n, work = eng.h.timer_read()
+    print(f"class={cls} wall={dt:.2f}s kernel_ms={ms:.1f} launches={n} total_launches={eng.h.launch_count()-l0} tflops={work/1e9/max(ms,1e-9):.1f} frames={sum(2*(250+t.numel()) for t in toks)}", flush=True)
