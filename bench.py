@@ -241,6 +241,16 @@ def run_engine(args, rank, world, local_rank):
         if world > 1:
             dist.destroy_process_group()
         return
+    # BASELINE config[1]: one utterance (B=1, CFG pair), 150 speech tokens = 6 s of audio: latency / RTF
+    g1 = torch.Generator().manual_seed(1234)
+    text1 = [torch.randint(1, 255, (100,), generator=g1)]
+    tts.generate_batch(text1, max_new_tokens=[150], seed=7, kv_dtype="bf16", to_host=True, timings={})
+    tm1 = {}
+    tts.generate_batch(text1, max_new_tokens=[150], seed=7, kv_dtype="bf16", to_host=True, timings=tm1)
+    b1_ms = tm1["t3_ms"] + tm1["flow_ms"] + tm1["hift_ms"] + tm1["d2h_ms"]
+    b1 = {"audio_s": tm1["audio_s"], "latency_ms": b1_ms, "rtf": b1_ms / 1000.0 / max(tm1["audio_s"], 1e-9),
+          "t3_ms": tm1["t3_ms"], "flow_ms": tm1["flow_ms"], "hift_ms": tm1["hift_ms"]}
+    log("B=1 latency: " + json.dumps(b1))
     hbm_peak, tf_peak, peak_src = load_peaks()
     paged_bytes_per_launch = eng.stats["paged_bytes"] / max(1, eng.stats["paged_launches"])
     achieved = (eng.stats["paged_bytes"] / 1e9) / (paged_ms / 1e3) if paged_ms > 0 else 0.0
@@ -260,7 +270,8 @@ def run_engine(args, rank, world, local_rank):
                    "weights": "seeded random init of the reference architecture (532M T3 + 112M flow + 21M HiFT)",
                    "l2_policy": "working set >> L2 (KV pages ~40 GB, activations GBs); no explicit flush needed",
                    "audio_s_per_step_per_gpu": audio / args.steps, "stage_ms": stage,
-                   "decode_steps_per_step": stats_timed["decode_steps"] / args.steps, "peaks": peak_src},
+                   "decode_steps_per_step": stats_timed["decode_steps"] / args.steps, "peaks": peak_src,
+                   "b1_latency": b1},
         "clocks": clk,
         "gpu_launches": int(launches),
         "e2e": {"value": float(audio_e[0]) / (ms_e / 1000.0), "unit": UNIT,
