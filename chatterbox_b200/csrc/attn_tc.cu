@@ -23,6 +23,7 @@ constexpr int AT_THREADS = 192;
 
 struct AttnTcDev {
   float* O; int ldo;
+  __nv_bfloat16* Ohi; __nv_bfloat16* Olo;   // when set, O is written as bf16 hi/lo planes [rows][ldo] (operand of the out GEMM)
   const int* q_start; const int* q_len; const int* kv_start; const int* kv_len;
   float scale_log2e;      // softmax scale * log2(e)
   int q_col, k_col, v_col;   // column offsets of head 0 inside the packed planes
@@ -263,10 +264,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
     if (q0 + row < qlen) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      float* dst = p.O + (long)(qrow0 + row) * p.ldo + head * 64;
+      if (p.Ohi) {
+        const long off = (long)(qrow0 + row) * p.ldo + head * 64;
+        uint4* dh = reinterpret_cast<uint4*>(p.Ohi + off);
+        uint4* dl = reinterpret_cast<uint4*>(p.Olo + off);
 #pragma unroll
-      for (int i = 0; i < 64; i += 4)
-        *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+        for (int i = 0; i < 64; i += 8) {
+          uint4 h, l;
+          split_pair_at(o[i] * inv, o[i + 1] * inv, h.x, l.x);
+          split_pair_at(o[i + 2] * inv, o[i + 3] * inv, h.y, l.y);
+          split_pair_at(o[i + 4] * inv, o[i + 5] * inv, h.z, l.z);
+          split_pair_at(o[i + 6] * inv, o[i + 7] * inv, h.w, l.w);
+          dh[i / 8] = h; dl[i / 8] = l;
+        }
+      } else {
+        float* dst = p.O + (long)(qrow0 + row) * p.ldo + head * 64;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+      }
+    } else if (p.Ohi) {
+      // Padding rows of the sequence's last 128-row tile (packed layouts start every sequence on a tile boundary): keep
+      // them finite.  They flow through the out GEMM into x, come back as K/V padding rows of the next block, and a NaN
+      // there would poison real rows through 0 * NaN in P.V.
+      const long off = (long)(qrow0 + row) * p.ldo + head * 64;
+      uint4* dh = reinterpret_cast<uint4*>(p.Ohi + off);
+      uint4* dl = reinterpret_cast<uint4*>(p.Olo + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dh[i] = make_uint4(0, 0, 0, 0); dl[i] = make_uint4(0, 0, 0, 0); }
     }
   }
   tcgen05_fence_before();
@@ -502,14 +527,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
 }
 
 // ---- host --------------------------------------------------------------------------------------------
-void make_plane_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long rows, int cols);   // gemm.cu
 
 void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
   if (ctx.dry) return;
   static bool attr = false;
   if (!attr) { CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr = true; }
   AttnTcDev p;
-  p.O = a.O; p.ldo = a.ldo; p.q_start = a.q_start; p.q_len = a.q_len; p.kv_start = a.kv_start; p.kv_len = a.kv_len;
+  p.O = a.O; p.ldo = a.ldo; p.Ohi = a.Ohi; p.Olo = a.Olo; p.q_start = a.q_start; p.q_len = a.q_len; p.kv_start = a.kv_start; p.kv_len = a.kv_len;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.q_col = a.q_col; p.k_col = a.k_col; p.v_col = a.v_col;
   // CBX_ATTN_TC=2 selects the experimental two-query-tile kernel (measured 14% slower than variant 1 in round 1:
@@ -517,7 +541,7 @@ void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
   static const int variant = getenv("CBX_ATTN_TC") ? atoi(getenv("CBX_ATTN_TC")) : 1;
   ctx.launches++;
   if (ctx.timer) ctx.timer->begin(K_FLASH, ctx.stream);
-  if (variant == 2 && a.max_q_len > 128) {
+  if (variant == 2 && a.max_q_len > 128 && !a.Ohi) {
     static bool attr2 = false;
     if (!attr2) { CBX_CHECK(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM)); attr2 = true; }
     dim3 grid((a.max_q_len + 255) / 256, a.n_heads, a.n_seq);

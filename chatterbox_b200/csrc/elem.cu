@@ -60,7 +60,8 @@ void rmsnorm(Ctx& ctx, const float* x, int ldx, const float* w, float* y, int ld
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx, const float* w, const float* b, float* y,
                                                         int ldy, int rows, int dim, float eps, int act, float out_scale,
-                                                        const float* seq_add, int seq_add_ld, int has_seq, SeqMap seq) {
+                                                        const float* seq_add, int seq_add_ld, int has_seq, SeqMap seq,
+                                                        __nv_bfloat16* yhi, __nv_bfloat16* ylo) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -70,7 +71,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx,
     valid = (s >= 0) && (r - seq.out_start[s] < seq.out_len[s]);
   }
   float* yr = y + (long)r * ldy;
-  if (!valid) { for (int i = lane; i < dim; i += 32) yr[i] = 0.f; return; }
+  __nv_bfloat16* hr = yhi ? yhi + (long)r * ldy : nullptr;
+  __nv_bfloat16* lr = yhi ? ylo + (long)r * ldy : nullptr;
+  if (!valid) {
+    for (int i = lane; i < dim; i += 32) {
+      if (yhi) { hr[i] = __float2bfloat16(0.f); lr[i] = __float2bfloat16(0.f); } else yr[i] = 0.f;
+    }
+    return;
+  }
   const float* xr = x + (long)r * ldx;
   float sum = 0.f;
   for (int i = lane; i < dim; i += 32) sum += xr[i];
@@ -82,16 +90,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx,
     float v = (xr[i] - mean) * inv * w[i] + b[i];
     v = act_apply(act, v, 0.f);
     if (seq_add) v += seq_add[(long)s * seq_add_ld + i];
-    yr[i] = v * out_scale;
+    v *= out_scale;
+    if (yhi) { __nv_bfloat16 h, l; split_bf16(v, h, l); hr[i] = h; lr[i] = l; } else yr[i] = v;
   }
 }
 void layernorm(Ctx& ctx, const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int dim,
-               float eps, int act, float out_scale, const float* seq_add, int seq_add_ld, const SeqMap* seq) {
+               float eps, int act, float out_scale, const float* seq_add, int seq_add_ld, const SeqMap* seq,
+               __nv_bfloat16* yhi, __nv_bfloat16* ylo) {
   if (ctx.dry || rows == 0) return;
   ctx.launches++;
   SeqMap sm; if (seq) sm = *seq;
   layernorm_kernel<<<(rows + 7) / 8, 256, 0, ctx.stream>>>(x, ldx, w, b, y, ldy, rows, dim, eps, act, out_scale, seq_add,
-                                                          seq_add_ld, seq ? 1 : 0, sm);
+                                                          seq_add_ld, seq ? 1 : 0, sm, yhi, ylo);
   CBX_CHECK(cudaGetLastError());
 }
 

@@ -262,18 +262,43 @@ static void cfm_resnet(Ctx& ctx, CfmResnet& r, const float* in, int lda, int cin
 }
 static void cfm_tfmr(Ctx& ctx, CfmTfmr& t, float* x, int ldx, const cbx_layout& L, EstBufs& b) {
   const int rows = L.rows;
-  layernorm(ctx, x, ldx, t.ln1_w.p, t.ln1_b.p, b.hn, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
   if (b.tc) {
-    // QKV GEMM writes bf16 hi/lo planes; tcgen05 attention reads them through TMA
-    GemmDev gq = gemm_args_linear(b.hn, 256, rows, t.qkv, nullptr, 0);
+    // Every activation between two GEMMs of the block travels as bf16 hi/lo planes (the producer splits once, in its
+    // epilogue) so that the GEMM loads its A operand by TMA straight into the UMMA layout: LN -> qkv -> tcgen05
+    // attention -> out(+x) ; LN -> ff1(GELU) -> ff2(+x).  Same split as the in-kernel converter: results are unchanged.
+    const size_t R = (size_t)rows;
+    __nv_bfloat16* hn_hi = reinterpret_cast<__nv_bfloat16*>(b.hn);  __nv_bfloat16* hn_lo = hn_hi + R * 256;
+    __nv_bfloat16* at_hi = reinterpret_cast<__nv_bfloat16*>(b.att); __nv_bfloat16* at_lo = at_hi + R * 512;
+    __nv_bfloat16* ff_hi = reinterpret_cast<__nv_bfloat16*>(b.ff);  __nv_bfloat16* ff_lo = ff_hi + R * 1024;
+    layernorm(ctx, x, ldx, t.ln1_w.p, t.ln1_b.p, nullptr, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr, hn_hi, hn_lo);
+    GemmDev gq = gemm_args_linear(nullptr, 256, rows, t.qkv, nullptr, 0);
+    gq.Ahi = hn_hi; gq.Alo = hn_lo; gq.ldab = 256;
     gq.Chi = b.qkv_hi; gq.Clo = b.qkv_lo; gq.ldcb = 1536;
     gemm(ctx, gq, t.qkv);
     AttnTcArgs a;
-    a.tm_hi = &b.tm_hi; a.tm_lo = &b.tm_lo; a.q_col = 0; a.k_col = 512; a.v_col = 1024; a.O = b.att; a.ldo = 512;
+    a.tm_hi = &b.tm_hi; a.tm_lo = &b.tm_lo; a.q_col = 0; a.k_col = 512; a.v_col = 1024; a.O = nullptr; a.ldo = 512;
+    a.Ohi = at_hi; a.Olo = at_lo;
     a.n_seq = L.n_seq; a.n_heads = 8; a.q_start = L.start; a.q_len = L.len; a.kv_start = L.start; a.kv_len = L.len;
     a.max_q_len = L.max_len; a.scale = 0.125f;
     attention_tc(ctx, a);
-  } else {
+    GemmDev go = gemm_args_linear(nullptr, 512, rows, t.out, x, ldx);
+    go.Ahi = at_hi; go.Alo = at_lo; go.ldab = 512;
+    go.res = x; go.ldr = ldx;
+    gemm(ctx, go, t.out);
+    layernorm(ctx, x, ldx, t.ln3_w.p, t.ln3_b.p, nullptr, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr, hn_hi, hn_lo);
+    GemmDev g1 = gemm_args_linear(nullptr, 256, rows, t.ff1, nullptr, 0);
+    g1.Ahi = hn_hi; g1.Alo = hn_lo; g1.ldab = 256;
+    g1.Chi = ff_hi; g1.Clo = ff_lo; g1.ldcb = 1024;
+    g1.act = ACT_GELU;
+    gemm(ctx, g1, t.ff1);
+    GemmDev g2 = gemm_args_linear(nullptr, 1024, rows, t.ff2, x, ldx);
+    g2.Ahi = ff_hi; g2.Alo = ff_lo; g2.ldab = 1024;
+    g2.res = x; g2.ldr = ldx;
+    gemm(ctx, g2, t.ff2);
+    return;
+  }
+  layernorm(ctx, x, ldx, t.ln1_w.p, t.ln1_b.p, b.hn, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
+  {
     gemm(ctx, gemm_args_linear(b.hn, 256, rows, t.qkv, b.qkv, 1536), t.qkv);
     AttnArgs a;
     a.Q = b.qkv; a.K = b.qkv + 512; a.V = b.qkv + 1024; a.ldq = a.ldk = a.ldv = 1536; a.O = b.att; a.ldo = 512;

@@ -127,7 +127,8 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 
 template <int BN, int DUAL>
 __global__ void __launch_bounds__(TC_THREADS, DUAL ? 2 : 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA, const GemmDev g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA,
+               const __grid_constant__ CUtensorMap tmapA2, const GemmDev g) {
   using Cfg = TcCfg<BN, DUAL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -153,7 +154,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == TC_PRODUCER_WARPS + 1) tmem_alloc<BN>(tmem_slot);   // MMA warp owns TMEM
-  if (warp == TC_PRODUCER_WARPS && lane == 0) { tma_prefetch_desc(&tmapW); if (g.a_tma) tma_prefetch_desc(&tmapA); }
+  if (warp == TC_PRODUCER_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmapW);
+    if (g.a_tma) tma_prefetch_desc(&tmapA);
+    if (g.a_tma == 2) tma_prefetch_desc(&tmapA2);
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -164,7 +169,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     const int t = threadIdx.x;            // 0..255
     const int c4 = t & 15;                // float4 chunk inside the 64-wide K block
     const int rsub = t >> 4;              // 0..15
-    if (g.a_tma) {
+    if (g.a_tma == 2) {
+      // A arrives as bf16 planes by TMA: nothing to convert, go wait for the accumulator
+    } else if (g.a_tma) {
       // ===================== converters: smem fp32 tile -> bf16 hi/lo planes, in place ===================
       // software pipelined: the LDS of K block kb+1 are in flight while block kb is converted and stored.
       // (One group of 8 warps on every block: two groups on alternating blocks would skip mbarrier phases, and a
@@ -336,8 +343,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
               if (colok && (r0 + u) < rows_here) cbase[(long)(r0 + u) * g.ldc] = v;
             }
           }
-        } else if (g.Chi && !g.C && !g.C2 && !g.res && g.act == ACT_NONE) {
+        } else if (g.Chi && !g.C && !g.C2 && !g.res) {
           // ---- bf16 hi/lo planes only (QKV projection feeding the tcgen05 attention)
+          const bool pre = g.act != ACT_NONE && colok;
+          if (pre) {       // same in-place activation pass as the fp32 path (GELU of ff1 feeding ff2's plane operand)
+#pragma unroll 1
+            for (int rr = 0; rr < rows_here; ++rr) {
+              float v = st[rr * 33 + lane] * g.alpha + bias;
+              switch (g.act) {
+                case ACT_GELU: v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); break;
+                case ACT_SILU: v = v / (1.0f + expf(-v)); break;
+                default: v = act_apply_slow(g.act, v, ap); break;
+              }
+              st[rr * 33 + lane] = v;
+            }
+          }
+          const float a_mul = pre ? 1.0f : g.alpha, a_add = pre ? 0.0f : bias;
           __nv_bfloat16* hb = g.Chi + grow0 * g.ldcb + n;
           __nv_bfloat16* lb = g.Clo + grow0 * g.ldcb + n;
           for (int r0 = 0; r0 < rows_here; r0 += 8) {
@@ -346,7 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
             for (int u = 0; u < 8; ++u) xv[u] = (colok && (r0 + u) < rows_here) ? st[(r0 + u) * 33 + lane] : 0.f;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              float v = (xv[u] * g.alpha + bias) * g.out_scale;
+              float v = (xv[u] * a_mul + a_add) * g.out_scale;
               if (!((vmask >> (r0 + u)) & 1u)) v = 0.f;
               __nv_bfloat16 h, l;
               split_bf16(v, h, l);
@@ -402,7 +423,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&tma_full[s], g.a_tma ? (Cfg::A_BYTES + Cfg::W_BYTES) : Cfg::W_BYTES);
         tma_load_2d(a_st + Cfg::A_BYTES, &tmapW, &tma_full[s], kb * TC_BK, n0);
-        if (g.a_tma) {
+        if (g.a_tma == 2) {
+          tma_load_2d(a_st, &tmapA, &tma_full[s], kb * TC_BK, m0);             // hi plane, SWIZZLE_128B
+          tma_load_2d(a_st + 16384, &tmapA2, &tma_full[s], kb * TC_BK, m0);    // lo plane
+        } else if (g.a_tma) {
           const int k0 = kb * TC_BK;
           const int tap = k0 / g.ctap, c = k0 - tap * g.ctap;
           tma_load_2d(a_st, &tmapA, &tma_full[s], c, (int)(in_row0 + (long)tap * g.dil));
@@ -416,8 +440,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&tma_full[s], ph);      // W tile landed
-        mbar_wait(&conv_full[s], ph);     // bf16 planes of A written
+        mbar_wait(&tma_full[s], ph);      // W tile landed (and A planes in plane mode)
+        if (g.a_tma != 2) mbar_wait(&conv_full[s], ph);     // bf16 planes of A written by the converters
         tcgen05_fence_after();
         if (dbg && kb < 8) g.dbg[32 + kb] = clock64();
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
@@ -597,11 +621,12 @@ void make_tmaps_for(Weight& W) {
 }
 
 // 2-D map over a [rows][cols] bf16 plane, box 64 x 64, SWIZZLE_128B (tcgen05 attention operands)
-void make_plane_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long rows, int cols) {
+void make_plane_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long rows, int cols, int box_rows, int ld) {
   PFN_encodeTiled enc = get_encode_fn();
+  if (ld == 0) ld = cols;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {64, 64};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -696,12 +721,20 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
   // TMA-fed A operand: plain strided fp32 rows (Linear, stride-1 conv taps)
   g.a_tma = (g.a_mode == A_TAPS && g.stride == 1 && (g.lda % 4) == 0 && (g.c_in % 4) == 0 &&
              (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && g.M_in > 0) ? 1 : 0;
-  CUtensorMap tmA;
-  if (g.a_tma) make_a_tmap(&tmA, g); else tmA = W.tmap[tmap_idx];
+  CUtensorMap tmA, tmA2;
+  if (g.Ahi) {
+    CBX_REQUIRE(g.ntaps == 1 && !g.has_seq && g.Alo && (g.ldab % 8) == 0, "plane operand needs a plain Linear");
+    g.a_tma = 2;
+    make_plane_tmap(&tmA, g.Ahi, g.M, g.k_total, 128, g.ldab);
+    make_plane_tmap(&tmA2, g.Alo, g.M, g.k_total, 128, g.ldab);
+  } else {
+    if (g.a_tma) make_a_tmap(&tmA, g); else tmA = W.tmap[tmap_idx];
+    tmA2 = tmA;
+  }
   dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM);
   if (ctx.timer && ctx.timer->cls == K_GEMM_TC) ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
   if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
-  gemm_tc_kernel<BN, DUAL><<<grid, TC_THREADS, TcCfg<BN, DUAL>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], tmA, g);
+  gemm_tc_kernel<BN, DUAL><<<grid, TC_THREADS, TcCfg<BN, DUAL>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], tmA, tmA2, g);
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
 }
 
@@ -725,7 +758,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     gemm_simt_kernel<<<grid, 256, 0, ctx.stream>>>(g);
   } else {
     const bool plain = !g.has_seq && g.a_mode == A_TAPS && g.ntaps == 1 && g.stride == 1 && g.pad == 0 &&
-                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.Chi &&
+                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.Chi && !g.Ahi &&
                        ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
     if (plain && g.M <= 8) {
       if (g.M <= 2) launch_gemv<2>(ctx, g);

@@ -60,6 +60,9 @@ struct GemmDev {
   float* C2; int ldc2; int act2; float act2_p; const float* act2_vec;  // optional 2nd output act2(v)
   __nv_bfloat16* Chi; __nv_bfloat16* Clo; int ldcb;   // optional bf16 hi/lo planes of v (C may then be null)
   long long* dbg;   // optional [64] clock64 timestamps of CTA (0,0) (kernel anatomy debugging)
+  // A operand already split into bf16 hi/lo planes [M][ldab] by the producing kernel (Linear only): both planes are
+  // fetched by TMA straight into the UMMA layout and the converter warps have nothing to do in the main loop
+  const __nv_bfloat16* Ahi; const __nv_bfloat16* Alo; int ldab;
 };
 
 struct Arena {  // bump allocator over caller-owned workspace; dry=true only counts
@@ -150,12 +153,13 @@ struct AttnTcArgs {
   const CUtensorMap* tm_hi; const CUtensorMap* tm_lo;
   int q_col, k_col, v_col;                    // column of head 0 of Q / K / V inside the planes
   float* O; int ldo;
+  __nv_bfloat16* Ohi = nullptr; __nv_bfloat16* Olo = nullptr;   // optional: write the output as bf16 planes [rows][ldo]
   int n_seq, n_heads;
   const int* q_start; const int* q_len; const int* kv_start; const int* kv_len;
   int max_q_len; float scale;
 };
 void attention_tc(Ctx& ctx, const AttnTcArgs& a);
-void make_plane_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long rows, int cols);
+void make_plane_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long rows, int cols, int box_rows = 64, int ld = 0);
 void attention_generic(Ctx& ctx, const float* Q, const float* K, const float* V, float* O, int n_q, int n_kv,
                        int n_heads, int head_dim, int ldq, int ldk, int ldv, int ldo, float scale);
 
@@ -176,7 +180,8 @@ void rope_and_store_kv(Ctx& ctx, float* qkv, int ldqkv, const PagedKV& kv, int l
 void rmsnorm(Ctx& ctx, const float* x, int ldx, const float* w, float* y, int ldy, int rows, int dim, float eps,
              const int* row_idx);
 void layernorm(Ctx& ctx, const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int dim,
-               float eps, int act, float out_scale, const float* seq_add, int seq_add_ld, const SeqMap* seq);
+               float eps, int act, float out_scale, const float* seq_add, int seq_add_ld, const SeqMap* seq,
+               __nv_bfloat16* yhi = nullptr, __nv_bfloat16* ylo = nullptr);   // yhi/ylo: bf16 planes instead of fp32 y
 void fill(Ctx& ctx, float* p, long n, float v);
 
 }  // namespace cbx
