@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcbx.so")
+LIB_PATH = os.environ.get("CBX_LIB") or os.path.join(_HERE, "libcbx.so")   # CBX_LIB: kernel A/B experiments
 
 
 class CbxError(RuntimeError):
@@ -20,7 +20,7 @@ class Layout(C.Structure):
 class T3State(C.Structure):
     _fields_ = [("n_utts", C.c_int), ("n_rows", C.c_int), ("cfg", C.c_int),
                 ("kv_pages", C.c_void_p), ("kv_dtype", C.c_int), ("page_tokens", C.c_int),
-                ("page_table", C.c_void_p), ("max_pages_per_row", C.c_int),
+                ("page_table", C.c_void_p), ("max_pages_per_row", C.c_int), ("n_pages", C.c_int),
                 ("positions", C.c_void_p), ("base_pos", C.c_void_p),
                 ("tokens", C.c_void_p), ("max_tokens", C.c_int),
                 ("n_gen", C.c_void_p), ("max_new", C.c_void_p), ("done", C.c_void_p), ("seen", C.c_void_p),

@@ -294,31 +294,50 @@ void attention_generic(Ctx& ctx, const float* Q, const float* K, const float* V,
 }
 
 // ================================================================================================
-// paged KV cache: layout [page][layer][k|v][head][token][64]
+// paged KV cache: layout [layer][page][k|v][head][token][64]
 // ================================================================================================
 template <typename T> struct KvTraits;
-template <> struct KvTraits<__nv_bfloat16> { static constexpr int LPT = 8, DPL = 8; };   // lanes per token, dims per lane
+// lanes per token, dims per lane.  PAGED_WIDE: 32 bytes (two 16-byte loads) of K and of V per lane and trip, half the
+// per-byte instruction count of the 16-byte version (softmax bookkeeping, shuffles and address arithmetic amortised).
+#ifndef PAGED_WIDE
+#define PAGED_WIDE 1
+#endif
+#if PAGED_WIDE
+template <> struct KvTraits<__nv_bfloat16> { static constexpr int LPT = 4, DPL = 16; };
+template <> struct KvTraits<float> { static constexpr int LPT = 8, DPL = 8; };
+#else
+template <> struct KvTraits<__nv_bfloat16> { static constexpr int LPT = 8, DPL = 8; };
 template <> struct KvTraits<float> { static constexpr int LPT = 16, DPL = 4; };
+#endif
 
-template <typename T> __device__ __forceinline__ void load_chunk(const T* p, float (&x)[KvTraits<T>::DPL]);
-template <> __device__ __forceinline__ void load_chunk<__nv_bfloat16>(const __nv_bfloat16* p, float (&x)[8]) {
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#ifndef PAGED_PF
+#define PAGED_PF 1
+#endif
+// one 16-byte piece of a K/V row -> fp32
+template <typename T> struct KvPiece;
+template <> struct KvPiece<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void decode(const uint4& u, float* x) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { x[2 * i] = __uint_as_float(w[i] << 16); x[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
-}
-template <> __device__ __forceinline__ void load_chunk<float>(const float* p, float (&x)[4]) {
-  const float4 u = __ldg(reinterpret_cast<const float4*>(p));
-  x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w;
-}
+    for (int i = 0; i < 4; ++i) { x[2 * i] = __uint_as_float(w[i] << 16); x[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+  }
+};
+template <> struct KvPiece<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void decode(const uint4& u, float* x) {
+    x[0] = __uint_as_float(u.x); x[1] = __uint_as_float(u.y); x[2] = __uint_as_float(u.z); x[3] = __uint_as_float(u.w);
+  }
+};
 
 struct PagedDev {
   const float* qkv; int ldqkv;        // [slots][3*H*64] (q rotated in place by rope_store)
-  const void* pages; int n_layers, n_heads, page_tokens, layer;
+  const void* pages; int n_pages, n_layers, n_heads, page_tokens, page_shift, layer;   // page_tokens = 1 << page_shift
   const int* page_table; int max_pages;
   const int* slot_row;                // compact slot -> physical row
   const int* positions;               // [rows] index of the current token (attend to 0..pos)
   float* out; int ldo;                // [slots][H*64]
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;   // when set: the output as bf16 hi/lo planes (operand of the o GEMM)
   float* scratch;                     // [slots][H][nsplit][66] partial (m, l, o[64])
   int nsplit; float scale;
 };
@@ -326,6 +345,7 @@ struct PagedDev {
 template <typename T>
 __global__ void __launch_bounds__(128) paged_decode_kernel(const PagedDev p) {
   constexpr int LPT = KvTraits<T>::LPT, DPL = KvTraits<T>::DPL, TPI = 32 / LPT;   // tokens per warp-iteration
+  constexpr int NP = DPL / KvPiece<T>::N;                                      // 16-byte pieces per lane and row
   const int slot = blockIdx.x, head = blockIdx.y, split = blockIdx.z;
   const int row = p.slot_row[slot];
   const int S = p.positions[row] + 1;
@@ -342,26 +362,41 @@ __global__ void __launch_bounds__(128) paged_decode_kernel(const PagedDev p) {
 #pragma unroll
   for (int i = 0; i < DPL; ++i) o[i] = 0.f;
   const long slab = (long)p.page_tokens * 64;                         // elements per (page,layer,kv,head)
-  const long page_stride = (long)p.n_layers * 2 * H * slab;
-  const T* base = reinterpret_cast<const T*>(p.pages) + ((long)p.layer * 2 * H + head) * slab;
+  const long page_stride = 2L * H * slab;
+  const T* base = reinterpret_cast<const T*>(p.pages) + (long)p.layer * p.n_pages * page_stride + (long)head * slab;
   const int* pt = p.page_table + (long)row * p.max_pages;
   const int n_iter = (S + TPI - 1) / TPI;
   const int stride = 4 * p.nsplit;
-  // one K/V chunk pair in flight per lane and many resident warps: measured 3.25 TB/s (49% of the copy peak) at the
-  // bench shape; requesting 4 token groups per trip (8 loads in flight, 107 registers) cut occupancy and fell to 34%.
-  for (int it = split * 4 + warp; it < n_iter; it += stride) {
+  // Software-pipelined stream: the raw 16-byte K and V chunks of the next PF warp-iterations are already in flight
+  // while the current one is folded into the online softmax (packed bf16 stays packed until use, 8 registers per
+  // stage).  Round-1 history at the bench shape: no prefetch 3.25 TB/s (49% of the copy peak, 9 CTAs/SM x 1 KB per warp
+  // in flight); 4 converted token groups per trip needed 107 registers and fell to 34%.
+  constexpr int PF = PAGED_PF;
+  struct Raw { uint4 k[NP], v[NP]; };
+  const int pmask = p.page_tokens - 1;
+  auto issue = [&](int it, Raw& r) {
     const int tok = it * TPI + grp;
-    const bool ok = tok < S;
-    float kx[DPL], vx[DPL];
-    if (ok) {
-      const int page = pt[tok / p.page_tokens];
-      const T* kp = base + (long)page * page_stride + (long)(tok % p.page_tokens) * 64 + sub * DPL;
-      load_chunk<T>(kp, kx);
-      load_chunk<T>(kp + (long)H * slab, vx);
+    if (it < n_iter && tok < S) {
+      const int page = pt[tok >> p.page_shift];
+      const uint4* kp = reinterpret_cast<const uint4*>(base + (long)page * page_stride + (long)(tok & pmask) * 64 + sub * DPL);
+      const uint4* vp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(kp) + (long)H * slab);
+#pragma unroll
+      for (int j = 0; j < NP; ++j) { r.k[j] = __ldg(kp + j); r.v[j] = __ldg(vp + j); }
     } else {
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) { kx[i] = 0.f; vx[i] = 0.f; }
+      for (int j = 0; j < NP; ++j) { r.k[j] = make_uint4(0, 0, 0, 0); r.v[j] = r.k[j]; }
     }
+  };
+  Raw rq[PF + 1];
+  const int it0 = split * 4 + warp;
+#pragma unroll
+  for (int f = 0; f < PF; ++f) issue(it0 + f * stride, rq[f]);
+  for (int it = it0; it < n_iter; it += stride) {
+    issue(it + PF * stride, rq[PF]);
+    const bool ok = it * TPI + grp < S;
+    float kx[DPL], vx[DPL];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) KvPiece<T>::decode(rq[0].k[j], kx + j * KvPiece<T>::N);
     float sc = 0.f;
 #pragma unroll
     for (int i = 0; i < DPL; ++i) sc = fmaf(q[i], kx[i], sc);
@@ -372,15 +407,19 @@ __global__ void __launch_bounds__(128) paged_decode_kernel(const PagedDev p) {
       const float c = (m == -INFINITY) ? 0.f : expf(m - mn);
       const float e = expf(sc - mn);
 #pragma unroll
+      for (int j = 0; j < NP; ++j) KvPiece<T>::decode(rq[0].v[j], vx + j * KvPiece<T>::N);
+#pragma unroll
       for (int i = 0; i < DPL; ++i) o[i] = o[i] * c + e * vx[i];
       l = l * c + e; m = mn;
     }
+#pragma unroll
+    for (int f = 0; f < PF; ++f) rq[f] = rq[f + 1];
   }
   // ---- merge the 4*TPI independent streams of this CTA
-  __shared__ float sm_m[4 * 32], sm_l[4 * 32], sm_o[4 * 32 * 8];
+  __shared__ float sm_m[4 * 32], sm_l[4 * 32], sm_o[4 * 32 * DPL];
   sm_m[threadIdx.x] = m; sm_l[threadIdx.x] = l;
 #pragma unroll
-  for (int i = 0; i < DPL; ++i) sm_o[threadIdx.x * 8 + i] = o[i];
+  for (int i = 0; i < DPL; ++i) sm_o[threadIdx.x * DPL + i] = o[i];
   __syncthreads();
   if (threadIdx.x < 64) {
     const int d = threadIdx.x;
@@ -396,10 +435,13 @@ __global__ void __launch_bounds__(128) paged_decode_kernel(const PagedDev p) {
         if (ms == -INFINITY) continue;
         const float c = expf(ms - mt);
         lt += sm_l[th] * c;
-        ot += sm_o[th * 8 + oi] * c;
+        ot += sm_o[th * DPL + oi] * c;
       }
     if (p.nsplit == 1) {
-      p.out[(long)slot * p.ldo + head * 64 + d] = lt > 0.f ? ot / lt : 0.f;
+      const float ov = lt > 0.f ? ot / lt : 0.f;
+      const long oidx = (long)slot * p.ldo + head * 64 + d;
+      if (p.out_hi) { __nv_bfloat16 hh, ll; split_bf16(ov, hh, ll); p.out_hi[oidx] = hh; p.out_lo[oidx] = ll; }
+      else p.out[oidx] = ov;
     } else {
       float* sp = p.scratch + (((long)slot * H + head) * p.nsplit + split) * 66;
       sp[2 + d] = ot;
@@ -408,7 +450,8 @@ __global__ void __launch_bounds__(128) paged_decode_kernel(const PagedDev p) {
   }
 }
 
-__global__ void paged_combine_kernel(const float* scratch, float* out, int ldo, int H, int nsplit) {
+__global__ void paged_combine_kernel(const float* scratch, float* out, int ldo, int H, int nsplit,
+                                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
   const int slot = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
   const float* sp = scratch + ((long)slot * H + head) * nsplit * 66;
   float mt = -INFINITY;
@@ -421,15 +464,23 @@ __global__ void paged_combine_kernel(const float* scratch, float* out, int ldo, 
     lt += sp[s * 66 + 1] * c;
     ot += sp[s * 66 + 2 + d] * c;
   }
-  out[(long)slot * ldo + head * 64 + d] = lt > 0.f ? ot / lt : 0.f;
+  const float ov = lt > 0.f ? ot / lt : 0.f;
+  const long oi = (long)slot * ldo + head * 64 + d;
+  if (out_hi) { __nv_bfloat16 hh, ll; split_bf16(ov, hh, ll); out_hi[oi] = hh; out_lo[oi] = ll; }
+  else out[oi] = ov;
 }
 
 void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* slot_row,
-                            int n_slots, const int* positions, float* out, int ldo, float* scratch, int nsplit) {
+                            int n_slots, const int* positions, float* out, int ldo, float* scratch, int nsplit,
+                            __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
   if (ctx.dry) return;
   PagedDev p;
-  p.qkv = qkv; p.ldqkv = ldqkv; p.pages = kv.pages; p.n_layers = kv.n_layers; p.n_heads = kv.n_heads;
-  p.page_tokens = kv.page_tokens; p.layer = layer; p.page_table = kv.page_table; p.max_pages = kv.max_pages_per_row;
+  p.out_hi = out_hi; p.out_lo = out_lo;
+  p.qkv = qkv; p.ldqkv = ldqkv; p.pages = kv.pages; p.n_pages = kv.n_pages; p.n_layers = kv.n_layers; p.n_heads = kv.n_heads;
+  p.page_tokens = kv.page_tokens; p.layer = layer;
+  p.page_shift = 0;
+  while ((1 << p.page_shift) < kv.page_tokens) ++p.page_shift;
+  CBX_REQUIRE((1 << p.page_shift) == kv.page_tokens, "page_tokens must be a power of two"); p.page_table = kv.page_table; p.max_pages = kv.max_pages_per_row;
   p.slot_row = slot_row; p.positions = positions; p.out = out; p.ldo = ldo; p.scratch = scratch; p.nsplit = nsplit;
   p.scale = 0.125f;
   dim3 grid(n_slots, kv.n_heads, nsplit);
@@ -440,7 +491,7 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
   if (ctx.timer) ctx.timer->end(K_PAGED, ctx.stream);
   if (nsplit > 1) {
     ctx.launches++;
-    paged_combine_kernel<<<dim3(n_slots, kv.n_heads), 64, 0, ctx.stream>>>(scratch, out, ldo, kv.n_heads, nsplit);
+    paged_combine_kernel<<<dim3(n_slots, kv.n_heads), 64, 0, ctx.stream>>>(scratch, out, ldo, kv.n_heads, nsplit, out_hi, out_lo);
   }
   CBX_CHECK(cudaGetLastError());
 }
@@ -448,7 +499,7 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
 // ---- RoPE (rotate_half convention) on q,k in place + append k,v to the paged cache -------------------
 // token i of the launch: qkv row i, physical cache row tok_row[i], position tok_pos[i]
 template <typename T>
-__global__ void __launch_bounds__(256) rope_store_kernel(float* qkv, int ldqkv, void* pages, int n_layers, int H,
+__global__ void __launch_bounds__(256) rope_store_kernel(float* qkv, int ldqkv, void* pages, int n_pages, int H,
                                                          int page_tokens, int layer, const int* page_table,
                                                          int max_pages, const int* tok_row, const int* tok_pos,
                                                          int pos_is_per_row, const float* cos_t, const float* sin_t) {
@@ -457,10 +508,9 @@ __global__ void __launch_bounds__(256) rope_store_kernel(float* qkv, int ldqkv, 
   const int pos = pos_is_per_row ? tok_pos[row] : tok_pos[i];
   float* base = qkv + (long)i * ldqkv;
   const long slab = (long)page_tokens * 64;
-  const long page_stride = (long)n_layers * 2 * H * slab;
+  const long page_stride = 2L * H * slab;
   const int page = page_table[(long)row * max_pages + pos / page_tokens];
-  T* kbase = reinterpret_cast<T*>(pages) + (long)page * page_stride + ((long)layer * 2 * H) * slab +
-             (long)(pos % page_tokens) * 64;
+  T* kbase = reinterpret_cast<T*>(pages) + ((long)layer * n_pages + page) * page_stride + (long)(pos % page_tokens) * 64;
   for (int idx = threadIdx.x; idx < H * 32; idx += blockDim.x) {
     const int head = idx >> 5, j = idx & 31;
     const float c = cos_t[(long)pos * 32 + j], s = sin_t[(long)pos * 32 + j];
@@ -484,11 +534,11 @@ void rope_and_store_kv(Ctx& ctx, float* qkv, int ldqkv, const PagedKV& kv, int l
   if (ctx.dry || n_tok == 0) return;
   ctx.launches++;
   if (kv.kv_fp32)
-    rope_store_kernel<float><<<n_tok, 256, 0, ctx.stream>>>(qkv, ldqkv, kv.pages, kv.n_layers, kv.n_heads, kv.page_tokens,
+    rope_store_kernel<float><<<n_tok, 256, 0, ctx.stream>>>(qkv, ldqkv, kv.pages, kv.n_pages, kv.n_heads, kv.page_tokens,
                                                            layer, kv.page_table, kv.max_pages_per_row, tok_row, tok_pos,
                                                            pos_is_per_row, cos_t, sin_t);
   else
-    rope_store_kernel<__nv_bfloat16><<<n_tok, 256, 0, ctx.stream>>>(qkv, ldqkv, kv.pages, kv.n_layers, kv.n_heads,
+    rope_store_kernel<__nv_bfloat16><<<n_tok, 256, 0, ctx.stream>>>(qkv, ldqkv, kv.pages, kv.n_pages, kv.n_heads,
                                                                    kv.page_tokens, layer, kv.page_table,
                                                                    kv.max_pages_per_row, tok_row, tok_pos,
                                                                    pos_is_per_row, cos_t, sin_t);

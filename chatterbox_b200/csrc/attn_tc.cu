@@ -6,8 +6,8 @@
 //   softmax        4 warps, one query row per thread (tcgen05.ld 64 columns), online max / sum in fp32,
 //                  P split into bf16 hi/lo and written to swizzled smem as the next A operand
 //   PV = P V       tcgen05.mma M128 N64 K64, V consumed in its natural [key][d] layout as an MN-major B operand
-//   O accumulate   in registers (O = O * exp(m_old - m_new) + PV), normalised and stored as fp32
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = softmax / correction / epilogue.
+//   O accumulate   in registers (O = O * exp(m_old - m_new) + PV), normalised and stored as fp32 or as bf16 planes
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 (2..9 with SPLIT 2) = softmax / correction / epilogue.
 #include "ops.h"
 #include <cstdlib>
 
@@ -18,8 +18,7 @@ constexpr int AT_TILE = AT_BN * 128;                 // 64 rows x 128 B = 8 KB (
 constexpr int AT_Q_BYTES = 2 * 2 * AT_TILE;          // 128 rows x 2 planes = 32 KB
 constexpr int AT_KV_STAGE = 4 * AT_TILE;             // K hi, K lo, V hi, V lo = 32 KB
 constexpr int AT_P_BYTES = 2 * 2 * AT_TILE;          // P hi, P lo (128 rows each) = 32 KB
-constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * AT_KV_STAGE + AT_P_BYTES + 1024 + 256;
-constexpr int AT_THREADS = 192;
+constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * AT_KV_STAGE + AT_P_BYTES + 1024 + 256 + 2048;   // + barriers + row exchange
 
 struct AttnTcDev {
   float* O; int ldo;
@@ -55,8 +54,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+// SPLIT = softmax threads per query row.  SPLIT 1 (default): 4 softmax warps, one row per thread.  SPLIT 2: 8 softmax warps, the two warps that share a TMEM lane
+// quarter each own 32 of the 64 key columns of a block (and 32 of the 64 output columns); the row maximum and the
+// final row sum are exchanged through shared memory behind a 64-thread named barrier.  Two warps per scheduler hide
+// the MUFU / tcgen05.ld latencies that a single in-order warp exposes (round-1 profile: IPC 0.2 with SPLIT 1).
+template <int SPLIT>
+__global__ void __launch_bounds__(64 + 128 * SPLIT, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const AttnTcDev p) {
+  constexpr int NSW = 4 * SPLIT;            // softmax warps
+  constexpr int NC = 64 / SPLIT;            // key columns (and output columns) per softmax thread
   const int seq = blockIdx.z, head = blockIdx.y;
   const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
   const int q0 = blockIdx.x * AT_BM;
@@ -80,13 +86,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   uint64_t* pv_full = p_full + 1;           // 1
   uint64_t* pv_empty = pv_full + 1;         // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_empty + 1);
+  float* xch = reinterpret_cast<float*>(bars + 32);     // [2 buffers][2 halves][128 rows] row-max / row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
-    mbar_init(p_full, 4); mbar_init(pv_full, 1); mbar_init(pv_empty, 4);
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NSW); }
+    mbar_init(p_full, NSW); mbar_init(pv_full, 1); mbar_init(pv_empty, NSW);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -165,81 +172,89 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue (128 threads, one query row each) ============
-    const int quarter = warp & 3;                     // TMEM lane quarter of this warp
+    // ===================== softmax / correction / epilogue (SPLIT threads per query row) =================
+    const int quarter = warp & 3;                     // TMEM lane quarter of this warp (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;                 // which NC-column slice of the row (always 0 when SPLIT == 1)
     const int row = quarter * 32 + lane;              // query row inside the tile
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float o[64];
+    const int col0 = half * NC;
+    float o[NC];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    for (int i = 0; i < NC; ++i) o[i] = 0.f;
     float m = -INFINITY, l = 0.f, c_prev = 1.f;
     uint8_t* prow_hi = sP + row * 128;
     uint8_t* prow_lo = sP + 2 * AT_TILE + row * 128;
+    auto fold_pv = [&](bool release) {                // O = O * c_prev + PV (this thread's NC output columns)
+      uint32_t v0[32];
+#pragma unroll
+      for (int cc = 0; cc < NC; cc += 32) {
+        tmem_ld_32x32(tPV + lane_off + col0 + cc, v0);
+        tmem_ld_wait();
+        if (release && cc + 32 >= NC) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pv_empty);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[cc + i] = o[cc + i] * c_prev + __uint_as_float(v0[i]);
+      }
+    };
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tcgen05_fence_after();
-      uint32_t r0[32], r1[32];
-      const uint32_t ts = ((j & 1) ? tS1 : tS0) + lane_off;
-      tmem_ld_32x32(ts, r0);
-      tmem_ld_32x32(ts + 32, r1);
+      uint32_t r[NC];
+      const uint32_t ts = ((j & 1) ? tS1 : tS0) + lane_off + col0;
+#pragma unroll
+      for (int cc = 0; cc < NC; cc += 32) tmem_ld_32x32(ts + cc, *reinterpret_cast<uint32_t(*)[32]>(r + cc));
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[j & 1]);
       // scores in the log2 domain; keys beyond the sequence are masked
-      const int kbase = j * AT_BN;
-      float mx = m;
-      if (kbase + AT_BN > kvlen) {                 // only the last key block needs the length mask
+      const int kbase = j * AT_BN + col0;
+      if (j * AT_BN + AT_BN > kvlen) {             // only the last key block needs the length mask
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (kbase + i >= kvlen) r0[i] = 0xff800000u;        // -inf
-          if (kbase + 32 + i >= kvlen) r1[i] = 0xff800000u;
-        }
+        for (int i = 0; i < NC; ++i)
+          if (kbase + i >= kvlen) r[i] = 0xff800000u;        // -inf
       }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+      for (int i = 0; i < NC; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if (SPLIT == 2) {                            // row maximum over both halves (double-buffered slot, one barrier)
+        float* slot = xch + (j & 1) * 256;
+        slot[half * 128 + row] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        mx = fmaxf(mx, slot[(half ^ 1) * 128 + row]);
+      }
+      mx = fmaxf(mx, m);
       // raw scores are unscaled; the (positive) scale commutes with max, so scale once here
       const float mxs = mx * p.scale_log2e;
       const float c = (m == -INFINITY) ? 1.f : fast_exp2(m * p.scale_log2e - mxs);
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float a = fast_exp2(fmaf(__uint_as_float(r0[i]), p.scale_log2e, -mxs));
-        const float b = fast_exp2(fmaf(__uint_as_float(r1[i]), p.scale_log2e, -mxs));
-        sum += a + b;
-        r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(b);
+      for (int i = 0; i < NC; ++i) {
+        const float a = fast_exp2(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mxs));
+        sum4[i & 3] += a;
+        r[i] = __float_as_uint(a);
       }
-      l = l * c + sum;
+      l = l * c + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       m = mx;
       // fold the previous block's PV into O (it was computed relative to the previous max)
       if (j > 0) {
         mbar_wait(pv_full, (j - 1) & 1);
         tcgen05_fence_after();
-        uint32_t v0[32];
-        tmem_ld_32x32(tPV + lane_off, v0);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = o[i] * c_prev + __uint_as_float(v0[i]);
-        tmem_ld_32x32(tPV + lane_off + 32, v0);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pv_empty);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[32 + i] = o[32 + i] * c_prev + __uint_as_float(v0[i]);
+        fold_pv(true);
       }
       c_prev = c;
       // P_j -> bf16 hi/lo planes in swizzled smem (row-major 128 B rows, 16-byte chunk XOR row%8)
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int cq = 0; cq < NC / 8; ++cq) {
         uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = ch * 8 + e * 2;
-          const float a = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
-          const float b = __uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]);
-          split_pair_at(a, b, hi[e], lo[e]);
-        }
+        for (int e = 0; e < 4; ++e)
+          split_pair_at(__uint_as_float(r[cq * 8 + e * 2]), __uint_as_float(r[cq * 8 + e * 2 + 1]), hi[e], lo[e]);
+        const int ch = half * (NC / 8) + cq;
         const uint32_t off = ((uint32_t)(ch ^ (row & 7))) << 4;
         *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(prow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -249,49 +264,45 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       if (lane == 0) mbar_arrive(p_full);
     }
     // last block's PV
-    {
-      mbar_wait(pv_full, (nblk - 1) & 1);
-      tcgen05_fence_after();
-      uint32_t v0[32];
-      tmem_ld_32x32(tPV + lane_off, v0);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = o[i] * c_prev + __uint_as_float(v0[i]);
-      tmem_ld_32x32(tPV + lane_off + 32, v0);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[32 + i] = o[32 + i] * c_prev + __uint_as_float(v0[i]);
+    mbar_wait(pv_full, (nblk - 1) & 1);
+    tcgen05_fence_after();
+    fold_pv(false);
+    if (SPLIT == 2) {                              // row sum over both halves
+      float* slot = xch + (nblk & 1) * 256;
+      slot[half * 128 + row] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      l += slot[(half ^ 1) * 128 + row];
     }
     if (q0 + row < qlen) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
+      const long off = (long)(qrow0 + row) * p.ldo + head * 64 + col0;
       if (p.Ohi) {
-        const long off = (long)(qrow0 + row) * p.ldo + head * 64;
         uint4* dh = reinterpret_cast<uint4*>(p.Ohi + off);
         uint4* dl = reinterpret_cast<uint4*>(p.Olo + off);
 #pragma unroll
-        for (int i = 0; i < 64; i += 8) {
-          uint4 h, l;
-          split_pair_at(o[i] * inv, o[i + 1] * inv, h.x, l.x);
-          split_pair_at(o[i + 2] * inv, o[i + 3] * inv, h.y, l.y);
-          split_pair_at(o[i + 4] * inv, o[i + 5] * inv, h.z, l.z);
-          split_pair_at(o[i + 6] * inv, o[i + 7] * inv, h.w, l.w);
-          dh[i / 8] = h; dl[i / 8] = l;
+        for (int i = 0; i < NC; i += 8) {
+          uint4 h, lw;
+          split_pair_at(o[i] * inv, o[i + 1] * inv, h.x, lw.x);
+          split_pair_at(o[i + 2] * inv, o[i + 3] * inv, h.y, lw.y);
+          split_pair_at(o[i + 4] * inv, o[i + 5] * inv, h.z, lw.z);
+          split_pair_at(o[i + 6] * inv, o[i + 7] * inv, h.w, lw.w);
+          dh[i / 8] = h; dl[i / 8] = lw;
         }
       } else {
-        float* dst = p.O + (long)(qrow0 + row) * p.ldo + head * 64;
+        float* dst = p.O + off;
 #pragma unroll
-        for (int i = 0; i < 64; i += 4)
+        for (int i = 0; i < NC; i += 4)
           *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
       }
     } else if (p.Ohi) {
       // Padding rows of the sequence's last 128-row tile (packed layouts start every sequence on a tile boundary): keep
       // them finite.  They flow through the out GEMM into x, come back as K/V padding rows of the next block, and a NaN
       // there would poison real rows through 0 * NaN in P.V.
-      const long off = (long)(qrow0 + row) * p.ldo + head * 64;
+      const long off = (long)(qrow0 + row) * p.ldo + head * 64 + col0;
       uint4* dh = reinterpret_cast<uint4*>(p.Ohi + off);
       uint4* dl = reinterpret_cast<uint4*>(p.Olo + off);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { dh[i] = make_uint4(0, 0, 0, 0); dl[i] = make_uint4(0, 0, 0, 0); }
+      for (int i = 0; i < NC / 8; ++i) { dh[i] = make_uint4(0, 0, 0, 0); dl[i] = make_uint4(0, 0, 0, 0); }
     }
   }
   tcgen05_fence_before();
@@ -299,257 +310,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
-// ================================================================================================
-// Two query tiles per CTA (256 queries): the K/V blocks are loaded once for both tiles (half the L2->SM traffic) and
-// the softmax of one tile runs while the tensor pipe works on the other.  Warps: 0 TMA, 1 MMA, 2-5 softmax of tile A,
-// 6-9 softmax of tile B.  TMEM: per tile S[2] (2 x 64 columns) + PV (64 columns) = 384 of 512 columns.
-// ================================================================================================
-constexpr int A2_STAGES = 2;
-constexpr int A2_Q_BYTES = 2 * AT_Q_BYTES;            // two tiles x (hi, lo) x 128 rows = 64 KB
-constexpr int A2_P_BYTES = 2 * AT_P_BYTES;            // 64 KB
-constexpr int A2_SMEM = A2_Q_BYTES + A2_STAGES * AT_KV_STAGE + A2_P_BYTES + 1024 + 512;
-constexpr int A2_THREADS = 320;
-
-__global__ void __launch_bounds__(A2_THREADS, 1)
-attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const AttnTcDev p) {
-  const int seq = blockIdx.z, head = blockIdx.y;
-  const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
-  const int q0 = blockIdx.x * 256;
-  if (q0 >= qlen) return;
-  const int qrow0 = p.q_start[seq] + q0, krow0 = p.kv_start[seq];
-  const int nblk = (kvlen + AT_BN - 1) / AT_BN;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                                   // tile t at t*32 KB: [hi: 128 rows][lo: 128 rows]
-  uint8_t* sKV = sQ + A2_Q_BYTES;                       // stages of [Khi][Klo][Vhi][Vlo]
-  uint8_t* sP = sKV + A2_STAGES * AT_KV_STAGE;          // tile t at t*32 KB: [hi][lo]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + A2_P_BYTES);
-  uint64_t* q_full = bars;                    // 1
-  uint64_t* kv_full = bars + 1;               // [2]
-  uint64_t* kv_empty = kv_full + 2;           // [2]
-  uint64_t* s_full = kv_empty + 2;            // [tile][2]
-  uint64_t* s_empty = s_full + 4;             // [tile][2]
-  uint64_t* p_full = s_empty + 4;             // [tile]
-  uint64_t* pv_full = p_full + 2;             // [tile]
-  uint64_t* pv_empty = pv_full + 2;           // [tile]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 4); mbar_init(&pv_full[t], 1); mbar_init(&pv_empty[t], 4); }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_hi); tma_prefetch_desc(&tm_lo); }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  // tile t: S buffers at t*192 + {0, 64}, PV at t*192 + 128
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, A2_Q_BYTES);
-      const int qc = p.q_col + head * 64;
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        uint8_t* d = sQ + t * AT_Q_BYTES;
-        tma_load_2d(d, &tm_hi, q_full, qc, qrow0 + t * 128);
-        tma_load_2d(d + AT_TILE, &tm_hi, q_full, qc, qrow0 + t * 128 + 64);
-        tma_load_2d(d + 2 * AT_TILE, &tm_lo, q_full, qc, qrow0 + t * 128);
-        tma_load_2d(d + 3 * AT_TILE, &tm_lo, q_full, qc, qrow0 + t * 128 + 64);
-      }
-      const int kc = p.k_col + head * 64, vc = p.v_col + head * 64;
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        uint8_t* st = sKV + s * AT_KV_STAGE;
-        mbar_arrive_expect_tx(&kv_full[s], AT_KV_STAGE);
-        const int r = krow0 + j * AT_BN;
-        tma_load_2d(st, &tm_hi, &kv_full[s], kc, r);
-        tma_load_2d(st + AT_TILE, &tm_lo, &kv_full[s], kc, r);
-        tma_load_2d(st + 2 * AT_TILE, &tm_hi, &kv_full[s], vc, r);
-        tma_load_2d(st + 3 * AT_TILE, &tm_lo, &kv_full[s], vc, r);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BM, 64) | (1u << 16);
-      mbar_wait(q_full, 0);
-      auto issue_s = [&](int j, int t) {
-        const int s = j & 1;
-        mbar_wait(&s_empty[t * 2 + (j & 1)], ((j >> 1) & 1) ^ 1);
-        tcgen05_fence_after();
-        const uint32_t q_hi = smem_u32(sQ + t * AT_Q_BYTES), q_lo = q_hi + 2 * AT_TILE;
-        const uint32_t k_hi = smem_u32(sKV + s * AT_KV_STAGE), k_lo = k_hi + AT_TILE;
-        const uint32_t d = tmem_base + t * 192 + (j & 1) * 64;
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint64_t dkh = umma_desc_sw128(k_hi + k4 * 32), dkl = umma_desc_sw128(k_lo + k4 * 32);
-          const uint64_t dqh = umma_desc_sw128(q_hi + k4 * 32), dql = umma_desc_sw128(q_lo + k4 * 32);
-          umma_bf16(d, dql, dkh, idesc_s, k4 != 0 ? 1u : 0u);
-          umma_bf16(d, dqh, dkl, idesc_s, 1u);
-          umma_bf16(d, dqh, dkh, idesc_s, 1u);
-        }
-        umma_commit(&s_full[t * 2 + (j & 1)]);
-      };
-      auto issue_pv = [&](int j, int t) {
-        const int s = j & 1;
-        mbar_wait(&p_full[t], j & 1);
-        mbar_wait(&pv_empty[t], (j & 1) ^ 1);
-        tcgen05_fence_after();
-        const uint32_t p_hi = smem_u32(sP + t * AT_P_BYTES), p_lo = p_hi + 2 * AT_TILE;
-        const uint32_t v_hi = smem_u32(sKV + s * AT_KV_STAGE + 2 * AT_TILE), v_lo = v_hi + AT_TILE;
-        const uint32_t d = tmem_base + t * 192 + 128;
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint64_t dvh = umma_desc_sw128_mn(v_hi + k4 * 2048), dvl = umma_desc_sw128_mn(v_lo + k4 * 2048);
-          const uint64_t dph = umma_desc_sw128(p_hi + k4 * 32), dpl = umma_desc_sw128(p_lo + k4 * 32);
-          umma_bf16(d, dpl, dvh, idesc_pv, k4 != 0 ? 1u : 0u);
-          umma_bf16(d, dph, dvl, idesc_pv, 1u);
-          umma_bf16(d, dph, dvh, idesc_pv, 1u);
-        }
-        umma_commit(&pv_full[t]);
-      };
-      mbar_wait(&kv_full[0], 0);
-      issue_s(0, 0); issue_s(0, 1);
-      for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) {
-          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-          issue_s(j + 1, 0); issue_s(j + 1, 1);
-        }
-        issue_pv(j, 0);
-        issue_pv(j, 1);
-        umma_commit(&kv_empty[j & 1]);               // both tiles are done with this K/V stage
-      }
-    }
-  } else {
-    // ===================== softmax / correction / epilogue: warps 2-5 tile 0, warps 6-9 tile 1 ==========
-    const int t = (warp - 2) >> 2;
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tS = tmem_base + t * 192 + lane_off, tPV = tmem_base + t * 192 + 128 + lane_off;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f, c_prev = 1.f;
-    uint8_t* prow_hi = sP + t * AT_P_BYTES + row * 128;
-    uint8_t* prow_lo = prow_hi + 2 * AT_TILE;
-    for (int j = 0; j <= nblk; ++j) {
-      // fold the previous block's PV into O first (keeps S and PV registers from being live together)
-      if (j > 0) {
-        mbar_wait(&pv_full[t], (j - 1) & 1);
-        tcgen05_fence_after();
-        uint32_t v0[32];
-        tmem_ld_32x32(tPV, v0);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = o[i] * c_prev + __uint_as_float(v0[i]);
-        tmem_ld_32x32(tPV + 32, v0);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&pv_empty[t]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[32 + i] = o[32 + i] * c_prev + __uint_as_float(v0[i]);
-      }
-      if (j == nblk) break;
-      mbar_wait(&s_full[t * 2 + (j & 1)], (j >> 1) & 1);
-      tcgen05_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(tS + (j & 1) * 64, r0);
-      tmem_ld_32x32(tS + (j & 1) * 64 + 32, r1);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[t * 2 + (j & 1)]);
-      const int kbase = j * AT_BN;
-      float mx = m;
-      if (kbase + AT_BN > kvlen) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (kbase + i >= kvlen) r0[i] = 0xff800000u;
-          if (kbase + 32 + i >= kvlen) r1[i] = 0xff800000u;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-      const float mxs = mx * p.scale_log2e;
-      const float c = (m == -INFINITY) ? 1.f : fast_exp2(m * p.scale_log2e - mxs);
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float a = fast_exp2(fmaf(__uint_as_float(r0[i]), p.scale_log2e, -mxs));
-        const float b = fast_exp2(fmaf(__uint_as_float(r1[i]), p.scale_log2e, -mxs));
-        sum += a + b;
-        r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(b);
-      }
-      l = l * c + sum;
-      m = mx;
-      c_prev = c;
-      // P smem is free: PV_{j-1} completed (pv_full waited above)
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = ch * 8 + e * 2;
-          const float a = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
-          const float b = __uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]);
-          split_pair_at(a, b, hi[e], lo[e]);
-        }
-        const uint32_t off = ((uint32_t)(ch ^ (row & 7))) << 4;
-        *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(prow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
-    }
-    const int qi = q0 + t * 128 + row;
-    if (qi < qlen) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      float* dst = p.O + (long)(qrow0 + t * 128 + row) * p.ldo + head * 64;
-#pragma unroll
-      for (int i = 0; i < 64; i += 4)
-        *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
 // ---- host --------------------------------------------------------------------------------------------
 
 void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
   if (ctx.dry) return;
   static bool attr = false;
-  if (!attr) { CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr = true; }
+  if (!attr) {
+    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    attr = true;
+  }
   AttnTcDev p;
   p.O = a.O; p.ldo = a.ldo; p.Ohi = a.Ohi; p.Olo = a.Olo; p.q_start = a.q_start; p.q_len = a.q_len; p.kv_start = a.kv_start; p.kv_len = a.kv_len;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.q_col = a.q_col; p.k_col = a.k_col; p.v_col = a.v_col;
-  // CBX_ATTN_TC=2 selects the experimental two-query-tile kernel (measured 14% slower than variant 1 in round 1:
-  // the single MMA-issuing thread serialises the two tiles; kept for the next round's tuning)
+  // CBX_ATTN_TC=2 selects two softmax threads per query row.  Measured on B200 (B=32 flow stage): 1170 ms vs 1123 ms
+  // for one thread per row -- the kernel is bound by shared-memory operand traffic of the N=64 SS-mode MMAs
+  // (~208 KB per key block), not by softmax latency, so the default stays 1.
   static const int variant = getenv("CBX_ATTN_TC") ? atoi(getenv("CBX_ATTN_TC")) : 1;
   ctx.launches++;
   if (ctx.timer) ctx.timer->begin(K_FLASH, ctx.stream);
-  if (variant == 2 && a.max_q_len > 128 && !a.Ohi) {
-    static bool attr2 = false;
-    if (!attr2) { CBX_CHECK(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM)); attr2 = true; }
-    dim3 grid((a.max_q_len + 255) / 256, a.n_heads, a.n_seq);
-    attn_tc2_kernel<<<grid, A2_THREADS, A2_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
-  } else {
-    dim3 grid((a.max_q_len + AT_BM - 1) / AT_BM, a.n_heads, a.n_seq);
-    attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
-  }
+  dim3 grid((a.max_q_len + AT_BM - 1) / AT_BM, a.n_heads, a.n_seq);
+  if (variant == 1) attn_tc_kernel<1><<<grid, 192, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
+  else attn_tc_kernel<2><<<grid, 320, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
   if (ctx.timer) ctx.timer->end(K_FLASH, ctx.stream);
   CBX_CHECK(cudaGetLastError());
 }

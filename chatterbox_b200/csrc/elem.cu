@@ -36,7 +36,7 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
 // RMSNorm (modeling_llama.py LlamaRMSNorm: x * rsqrt(mean(x^2)+eps) * w), one CTA per row
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* x, int ldx, const float* w, float* y, int ldy, int dim,
-                                                      float eps, const int* row_idx) {
+                                                      float eps, const int* row_idx, __nv_bfloat16* yhi, __nv_bfloat16* ylo) {
   __shared__ float sh[32];
   const int r = blockIdx.x;
   const float* xr = x + (long)(row_idx ? row_idx[r] : r) * ldx;
@@ -44,13 +44,17 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* x, int ldx, c
   for (int i = threadIdx.x; i < dim; i += blockDim.x) { float v = xr[i]; ss += v * v; }
   ss = block_sum(ss, sh);
   const float inv = rsqrtf(ss / dim + eps);
-  for (int i = threadIdx.x; i < dim; i += blockDim.x) y[(long)r * ldy + i] = w[i] * (xr[i] * inv);
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    const float v = w[i] * (xr[i] * inv);
+    if (yhi) { __nv_bfloat16 h, l; split_bf16(v, h, l); yhi[(long)r * ldy + i] = h; ylo[(long)r * ldy + i] = l; }
+    else y[(long)r * ldy + i] = v;
+  }
 }
 void rmsnorm(Ctx& ctx, const float* x, int ldx, const float* w, float* y, int ldy, int rows, int dim, float eps,
-             const int* row_idx) {
+             const int* row_idx, __nv_bfloat16* yhi, __nv_bfloat16* ylo) {
   if (ctx.dry || rows == 0) return;
   ctx.launches++;
-  rmsnorm_kernel<<<rows, 256, 0, ctx.stream>>>(x, ldx, w, y, ldy, dim, eps, row_idx);
+  rmsnorm_kernel<<<rows, 256, 0, ctx.stream>>>(x, ldx, w, y, ldy, dim, eps, row_idx, yhi, ylo);
   CBX_CHECK(cudaGetLastError());
 }
 

@@ -273,6 +273,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
       if (n0 + col >= g.n_out) break;
       uint32_t r[32];
       if (dbg && threadIdx.x == 0 && cc == 0) g.dbg[40] = clock64();
+      // residual rows of this chunk: all 32 loads in flight before the TMEM read and the transpose (C may alias res, so
+      // the compiler cannot hoist them over the stores itself; each element is read and written by the same thread)
+      float rres[32];
+      const bool hot_res = g.res && !g.swiglu && !g.C2 && !g.Chi && !g.accumulate;
+      if (hot_res) {
+        const int nh = n0 + col + lane;
+        const float* rb = g.res + (long)(m0 + q * 32) * g.ldr + nh;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) rres[u] = (nh < g.n_out && u < rows_here) ? rb[(long)u * g.ldr] : 0.f;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) rres[u] = 0.f;
+      }
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
       tmem_ld_wait();
       if (dbg && threadIdx.x == 0 && cc == 0) g.dbg[41] = clock64();
@@ -294,7 +307,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
             const float v0 = st[rr * 33 + 2 * lane] * g.alpha + b0, v1 = st[rr * 33 + 2 * lane + 1] * g.alpha + b1;
             float v = act_apply_slow(ACT_SILU, v0, 0.f) * v1;
             if (!rv) v = 0.f;
-            g.C[(long)(m0 + q * 32 + rr) * g.ldc + nout] = v;
+            if (g.Chi) {
+              __nv_bfloat16 hh, ll;
+              split_bf16(v, hh, ll);
+              g.Chi[(long)(m0 + q * 32 + rr) * g.ldcb + nout] = hh;
+              g.Clo[(long)(m0 + q * 32 + rr) * g.ldcb + nout] = ll;
+            } else {
+              g.C[(long)(m0 + q * 32 + rr) * g.ldc + nout] = v;
+            }
           }
         }
       } else {
@@ -327,18 +347,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
           }
           const float a_mul = pre ? 1.0f : g.alpha, a_add = pre ? 0.0f : bias;
           float* cbase = g.C + grow0 * g.ldc + n;
-          const float* rbase = g.res ? g.res + grow0 * g.ldr + n : nullptr;
-          for (int r0 = 0; r0 < rows_here; r0 += 8) {
-            float xv[8], rres[8];
+#pragma unroll
+          for (int r0 = 0; r0 < 32; r0 += 8) {
+            if (r0 >= rows_here) break;
+            float xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = (colok && (r0 + u) < rows_here) ? st[(r0 + u) * 33 + lane] : 0.f;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const bool ok = colok && (r0 + u) < rows_here;
-              xv[u] = ok ? st[(r0 + u) * 33 + lane] : 0.f;
-              rres[u] = (ok && rbase) ? rbase[(long)(r0 + u) * g.ldr] : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              float v = (xv[u] * a_mul + a_add + rres[u]) * g.out_scale;
+              float v = (xv[u] * a_mul + a_add + rres[r0 + u]) * g.out_scale;
               if (!((vmask >> (r0 + u)) & 1u)) v = 0.f;
               if (colok && (r0 + u) < rows_here) cbase[(long)(r0 + u) * g.ldc] = v;
             }

@@ -165,20 +165,23 @@ void attention_generic(Ctx& ctx, const float* Q, const float* K, const float* V,
 
 // ---- T3 paged KV cache ------------------------------------------------------------------------------
 struct PagedKV {
-  void* pages;            // [n_pages][n_layers][2][n_heads][page_tokens][64] of kv dtype
+  void* pages;            // [n_layers][n_pages][2][n_heads][page_tokens][64] of kv dtype (layer-major)
+  int n_pages;
   int kv_fp32;            // 0 = bf16, 1 = fp32
   int n_layers, n_heads, page_tokens;
   const int* page_table;  // [rows][max_pages_per_row]
   int max_pages_per_row;
 };
 void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* slot_row,
-                            int n_slots, const int* positions, float* out, int ldo, float* scratch, int nsplit);
+                            int n_slots, const int* positions, float* out, int ldo, float* scratch, int nsplit,
+                            __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);   // planes instead of out
 void rope_and_store_kv(Ctx& ctx, float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* tok_row,
                        const int* tok_pos, int pos_is_per_row, int n_tok, const float* cos_t, const float* sin_t);
 
 // ---- norms / fill -------------------------------------------------------------------------------------
 void rmsnorm(Ctx& ctx, const float* x, int ldx, const float* w, float* y, int ldy, int rows, int dim, float eps,
-             const int* row_idx);
+             const int* row_idx,
+             __nv_bfloat16* yhi = nullptr, __nv_bfloat16* ylo = nullptr);   // yhi/ylo: bf16 planes [rows][ldy] instead of y
 void layernorm(Ctx& ctx, const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int dim,
                float eps, int act, float out_scale, const float* seq_add, int seq_add_ld, const SeqMap* seq,
                __nv_bfloat16* yhi = nullptr, __nv_bfloat16* ylo = nullptr);   // yhi/ylo: bf16 planes instead of fp32 y

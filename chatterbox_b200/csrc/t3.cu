@@ -123,7 +123,7 @@ void t3_cond_encode(cbx_handle* h, Ctx& ctx, const float* spk, const int* prompt
 
 static PagedKV paged_of(const cbx_t3_state& st, int n_layers) {
   PagedKV kv;
-  kv.pages = st.kv_pages; kv.kv_fp32 = st.kv_dtype; kv.n_layers = n_layers; kv.n_heads = 16;
+  kv.pages = st.kv_pages; kv.n_pages = st.n_pages; kv.kv_fp32 = st.kv_dtype; kv.n_layers = n_layers; kv.n_heads = 16;
   kv.page_tokens = st.page_tokens; kv.page_table = st.page_table; kv.max_pages_per_row = st.max_pages_per_row;
   return kv;
 }
@@ -144,10 +144,21 @@ void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, cons
   t3_embed(ctx, x, n_tok, tok_row, tok_pos, cond, row_voice, len_cond, text_flat, text_start, n_text, row_uncond,
            m.text_emb.p, m.text_vocab, m.text_pos.p, m.speech_emb.p, m.speech_pos.p, 6561);
   PagedKV kv = paged_of(st, m.n_layers);
+  // tensor-core batches: GEMM operands that a norm / SwiGLU epilogue produces travel as bf16 hi/lo planes (see t3_decode)
+  const bool planes = (n_tok > 8 && ctx.gemm_impl == 0);
+  __nv_bfloat16* xn_hi = reinterpret_cast<__nv_bfloat16*>(xn);   __nv_bfloat16* xn_lo = xn_hi + (size_t)n_tok * 1024;
+  __nv_bfloat16* ac_hi = reinterpret_cast<__nv_bfloat16*>(act);  __nv_bfloat16* ac_lo = ac_hi + (size_t)n_tok * 4096;
   for (int l = 0; l < m.n_layers; ++l) {
     T3Layer& ly = m.layers[l];
-    rmsnorm(ctx, x, 1024, ly.ln1.p, xn, 1024, n_tok, 1024, 1e-5f, nullptr);
-    gemm(ctx, gemm_args_linear(xn, 1024, n_tok, ly.qkv, qkv, 3072), ly.qkv);
+    if (planes) {
+      rmsnorm(ctx, x, 1024, ly.ln1.p, nullptr, 1024, n_tok, 1024, 1e-5f, nullptr, xn_hi, xn_lo);
+      GemmDev gq = gemm_args_linear(nullptr, 1024, n_tok, ly.qkv, qkv, 3072);
+      gq.Ahi = xn_hi; gq.Alo = xn_lo; gq.ldab = 1024;
+      gemm(ctx, gq, ly.qkv);
+    } else {
+      rmsnorm(ctx, x, 1024, ly.ln1.p, xn, 1024, n_tok, 1024, 1e-5f, nullptr);
+      gemm(ctx, gemm_args_linear(xn, 1024, n_tok, ly.qkv, qkv, 3072), ly.qkv);
+    }
     rope_and_store_kv(ctx, qkv, 3072, kv, l, tok_row, tok_pos, 0, n_tok, m.rope_cos.p, m.rope_sin.p);
     AttnArgs a;
     a.Q = qkv; a.K = qkv + 1024; a.V = qkv + 2048; a.ldq = a.ldk = a.ldv = 3072; a.O = att; a.ldo = 1024;
@@ -157,6 +168,18 @@ void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, cons
     GemmDev go = gemm_args_linear(att, 1024, n_tok, ly.o, x, 1024);
     go.res = x; go.ldr = 1024;
     gemm(ctx, go, ly.o);
+    if (planes) {
+      rmsnorm(ctx, x, 1024, ly.ln2.p, nullptr, 1024, n_tok, 1024, 1e-5f, nullptr, xn_hi, xn_lo);
+      GemmDev gg = gemm_args_linear(nullptr, 1024, n_tok, ly.gu, nullptr, 0);
+      gg.Ahi = xn_hi; gg.Alo = xn_lo; gg.ldab = 1024;
+      gg.swiglu = 1; gg.Chi = ac_hi; gg.Clo = ac_lo; gg.ldcb = 4096;
+      gemm(ctx, gg, ly.gu);
+      GemmDev gd = gemm_args_linear(nullptr, 4096, n_tok, ly.down, x, 1024);
+      gd.Ahi = ac_hi; gd.Alo = ac_lo; gd.ldab = 4096;
+      gd.res = x; gd.ldr = 1024;
+      gemm(ctx, gd, ly.down);
+      continue;
+    }
     rmsnorm(ctx, x, 1024, ly.ln2.p, xn, 1024, n_tok, 1024, 1e-5f, nullptr);
     GemmDev gg = gemm_args_linear(xn, 1024, n_tok, ly.gu, act, 4096);
     gg.swiglu = 1;
@@ -195,10 +218,39 @@ void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, const int* act_u
   sp.seen = st.seen; sp.positions = st.positions; sp.base_pos = st.base_pos; sp.x = st.x;
   sp.speech_emb = m.speech_emb.p; sp.speech_pos = m.speech_pos.p; sp.q_noise = st.q_noise; sp.seed = st.seed;
   float* x = st.x;
+  // Tensor-core batches (S > 8): every GEMM operand travels as bf16 hi/lo planes written by its producer (RMSNorm,
+  // paged attention, SwiGLU epilogue) and is loaded by TMA -- no fp32->bf16 converter pass in the GEMM main loop.
+  // Small batches keep fp32 activations for the GEMV kernels.
+  const bool planes = (S > 8 && ctx.gemm_impl == 0);
+  __nv_bfloat16* xn_hi = reinterpret_cast<__nv_bfloat16*>(xn);   __nv_bfloat16* xn_lo = xn_hi + (size_t)S * 1024;
+  __nv_bfloat16* at_hi = reinterpret_cast<__nv_bfloat16*>(att);  __nv_bfloat16* at_lo = at_hi + (size_t)S * 1024;
+  __nv_bfloat16* ac_hi = reinterpret_cast<__nv_bfloat16*>(act);  __nv_bfloat16* ac_lo = ac_hi + (size_t)S * 4096;
   for (int step = 0; step < n_steps; ++step) {
     t3_sample(ctx, sp, n_act);
     for (int l = 0; l < m.n_layers; ++l) {
       T3Layer& ly = m.layers[l];
+      if (planes) {
+        rmsnorm(ctx, x, 1024, ly.ln1.p, nullptr, 1024, S, 1024, 1e-5f, nullptr, xn_hi, xn_lo);
+        GemmDev gq = gemm_args_linear(nullptr, 1024, S, ly.qkv, qkv, 3072);
+        gq.Ahi = xn_hi; gq.Alo = xn_lo; gq.ldab = 1024;
+        gemm(ctx, gq, ly.qkv);
+        rope_and_store_kv(ctx, qkv, 3072, kv, l, slot_row, st.positions, 1, S, m.rope_cos.p, m.rope_sin.p);
+        paged_decode_attention(ctx, qkv, 3072, kv, l, slot_row, S, st.positions, nullptr, 1024, scratch, nsplit, at_hi, at_lo);
+        GemmDev go = gemm_args_linear(nullptr, 1024, S, ly.o, x, 1024);
+        go.Ahi = at_hi; go.Alo = at_lo; go.ldab = 1024;
+        go.res = x; go.ldr = 1024;
+        gemm(ctx, go, ly.o);
+        rmsnorm(ctx, x, 1024, ly.ln2.p, nullptr, 1024, S, 1024, 1e-5f, nullptr, xn_hi, xn_lo);
+        GemmDev gg = gemm_args_linear(nullptr, 1024, S, ly.gu, nullptr, 0);
+        gg.Ahi = xn_hi; gg.Alo = xn_lo; gg.ldab = 1024;
+        gg.swiglu = 1; gg.Chi = ac_hi; gg.Clo = ac_lo; gg.ldcb = 4096;
+        gemm(ctx, gg, ly.gu);
+        GemmDev gd = gemm_args_linear(nullptr, 4096, S, ly.down, x, 1024);
+        gd.Ahi = ac_hi; gd.Alo = ac_lo; gd.ldab = 4096;
+        gd.res = x; gd.ldr = 1024;
+        gemm(ctx, gd, ly.down);
+        continue;
+      }
       rmsnorm(ctx, x, 1024, ly.ln1.p, xn, 1024, S, 1024, 1e-5f, nullptr);
       gemm(ctx, gemm_args_linear(xn, 1024, S, ly.qkv, qkv, 3072), ly.qkv);
       rope_and_store_kv(ctx, qkv, 3072, kv, l, slot_row, st.positions, 1, S, m.rope_cos.p, m.rope_sin.p);

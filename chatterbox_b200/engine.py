@@ -193,7 +193,7 @@ class Engine:
         n_pages = nxt
         kvt = torch.float32 if kv_dtype in ("fp32", "f32", torch.float32) else torch.bfloat16
         L = self.t3_layers
-        kv = torch.empty(n_pages, L, 2, 16, PAGE_TOKENS, 64, dtype=kvt, device=dev)
+        kv = torch.empty(L, n_pages, 2, 16, PAGE_TOKENS, 64, dtype=kvt, device=dev)     # layer-major (include/cbx.h)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         d = dict(tok_row=t(tok_row), tok_pos=t(tok_pos), row_start=t(row_start), row_len=t(row_len),
                  text_flat=t(text_flat), row_text_start=t(row_text_start), row_ntext=t(row_ntext),
@@ -209,7 +209,7 @@ class Engine:
             logits=torch.zeros(R, LDL, dtype=torch.float32, device=dev))
         st_t["seen"][:, START_SPEECH] = 1          # repetition penalty history starts with BOS (t3.py:316,347)
         qn = q_noise.to(dev, torch.float32).contiguous() if q_noise is not None else None
-        st = T3State(B, R, cfg, _ptr(kv), 1 if kvt == torch.float32 else 0, PAGE_TOKENS, _ptr(d["page_table"]), max_pages,
+        st = T3State(B, R, cfg, _ptr(kv), 1 if kvt == torch.float32 else 0, PAGE_TOKENS, _ptr(d["page_table"]), max_pages, n_pages,
                      _ptr(st_t["positions"]), _ptr(st_t["base_pos"]), _ptr(st_t["tokens"]), max_tokens,
                      _ptr(st_t["n_gen"]), _ptr(st_t["max_new"]), _ptr(st_t["done"]), _ptr(st_t["seen"]),
                      _ptr(st_t["x"]), _ptr(st_t["logits"]), LDL, float(cfg_weight), float(repetition_penalty),

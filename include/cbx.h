@@ -68,9 +68,11 @@ int cbx_finalize_weights(cbx_handle* h, const char* model);
 /* ---- T3 (reference src/chatterbox/models/t3/) ----------------------------------------------------- */
 typedef struct {
   int n_utts, n_rows, cfg;    /* n_rows = n_utts * (cfg ? 2 : 1); rows (2b, 2b+1) = (cond, uncond) */
-  /* paged KV cache: pages[page][layer][k|v][head][token][64] */
+  /* paged KV cache, layer-major: pages[layer][page][k|v][head][token][64] (one layer's pages are contiguous so that
+   * a decode step of that layer stays inside ~1/n_layers of the pool: TLB reach) */
   void* kv_pages; int kv_dtype; /* 0 = bf16, 1 = fp32 */ int page_tokens;
   const int* page_table; int max_pages_per_row; /* device [n_rows][max_pages_per_row] */
+  int n_pages;             /* pages in the pool (stride between layers) */
   int* positions;          /* device [n_rows] rope position of the token being fed */
   const int* base_pos;     /* device [n_rows] prefill length S0 */
   int* tokens; int max_tokens; /* device [n_utts][max_tokens] generated ids */
