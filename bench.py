@@ -34,6 +34,7 @@ def log(*a):
         print(f"[bench {time.time() - _T0:7.1f}s]", *a, file=sys.stderr, flush=True)
 
 METRIC = "audio_seconds_per_second"
+WORKLOAD = "Chatterbox 0.5B en, batch=256 mixed-length utterances per GPU, CFG, 10-step CFM, paged bf16 KV"
 UNIT = "audio-s/s"
 
 
@@ -152,7 +153,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "rtf": wall / audio,
-            "config": {"workload": "chatterbox-0.5B-en, CPU oracle port of the reference algorithm, bounded sample",
+            "config": {"workload": WORKLOAD, "arm": "CPU oracle port of the reference algorithm (fp32, torch CPU ops in the "
+                       "reference's order), bounded sample of the workload: one utterance per step",
                        "sample": sample, "split_s": split},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -266,7 +268,7 @@ def run_engine(args, rank, world, local_rank):
         "dtype": "bf16 weights/KV, fp32 activations+accumulate (activations split hi+lo bf16 on the tensor cores)",
         "data": "synthetic",
         "rtf": (ms / 1000.0) / audio_total * world,
-        "config": {"workload": "Chatterbox 0.5B en, batch=256 mixed-length utterances per GPU, CFG, 10-step CFM, paged bf16 KV",
+        "config": {"workload": WORKLOAD,
                    "utterances_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": f"utterance-sharded dp{world}",
                    "weights": "seeded random init of the reference architecture (532M T3 + 112M flow + 21M HiFT)",
                    "l2_policy": "working set >> L2 (KV pages ~40 GB, activations GBs); no explicit flush needed",
