@@ -1,6 +1,6 @@
 """Generate tests/golden/*.pt by running the UNMODIFIED reference modules (authoring container only).
 
-    python -m oracle.make_golden
+    python -m oracle.make_golden [t3] [s3gen] [variants] [turbo]
 
 The reference ships no golden vectors, known-answer tests or fixtures for this path (SURVEY.md 4,
 8c), so the fixtures are outputs of the reference itself: its own `T3.inference`,
@@ -147,9 +147,52 @@ def golden_meanflow_and_mtl():
     torch.save(out, os.path.join(OUT, "variants_golden.pt"))
 
 
+TURBO_TEXT_VOCAB = 2048      # fixture-sized gather table (shipped: 50276); see ref_harness.build_t3_turbo
+
+
+def golden_turbo():
+    """Turbo T3: the reference's own `T3(hp).inference_turbo` (t3.py:392-468) on the GPT2_medium
+    backbone (24 layers), seeded weights, 375-token voice prompt (tts_turbo.py:157)."""
+    R.install()
+    from chatterbox.models.t3.modules.cond_enc import T3Cond
+    sd = W.make_t3_turbo_weights(0, text_vocab=TURBO_TEXT_VOCAB)
+    t3 = R.build_t3_turbo(text_vocab=TURBO_TEXT_VOCAB)
+    res = t3.load_state_dict(sd, strict=False)
+    assert res.missing_keys == ["tfmr.wte.weight"] and not res.unexpected_keys, res   # wte is deleted by the reference
+    c3, _ = W.make_conds(seed=1234, n_t3_prompt=375)
+    mk = lambda: T3Cond(speaker_emb=c3["speaker_emb"], cond_prompt_speech_tokens=c3["cond_prompt_speech_tokens"],
+                        emotion_adv=c3["emotion_adv"])
+    out = dict(weights_seed=0, conds_seed=1234, text_vocab=TURBO_TEXT_VOCAB, n_prompt=375)
+    cases = []
+    for (tseed, ntext, steps, rng_seed, top_k, top_p, rep) in [(21, 19, 16, 11, 1000, 0.95, 1.2), (21, 19, 16, 3, 1, 0.95, 1.2),
+                                                               (22, 47, 10, 5, 1, 1.0, 2.0), (23, 30, 12, 9, 50, 0.8, 1.2)]:
+        g = torch.Generator().manual_seed(tseed)
+        text = torch.randint(0, TURBO_TEXT_VOCAB, (1, ntext), generator=g)
+        torch.manual_seed(rng_seed)
+        toks = t3.inference_turbo(mk(), text, temperature=0.8, top_k=top_k, top_p=top_p, repetition_penalty=rep,
+                                  max_gen_len=steps)
+        embeds, len_cond = t3.prepare_input_embeds(t3_cond=mk(), text_tokens=text,
+                                                   speech_tokens=6561 * torch.ones_like(text[:, :1]), cfg_weight=0.0)
+        with torch.inference_mode():
+            hs = t3.tfmr(inputs_embeds=embeds, use_cache=True)[0]
+            pl = t3.speech_head(hs[:, -1:])[:, -1, :]
+        cases.append(dict(text_seed=tseed, n_text=ntext, steps=steps, rng_seed=rng_seed, top_k=top_k, top_p=top_p,
+                          rep=rep, text_tokens=text, tokens=toks.clone(), prefill_logits=pl.clone(), len_cond=len_cond,
+                          cond_emb_head=t3.prepare_conditioning(mk())[:, :4].clone()))   # [spkr | first prompt rows]
+        print("turbo case", tseed, ntext, steps, top_k, top_p, toks[0, :8].tolist(), toks.shape)
+    out["cases"] = cases
+    torch.save(out, os.path.join(OUT, "turbo_golden.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    torch.set_num_threads(os.cpu_count())
-    golden_t3()
-    golden_flow_hift()
-    golden_meanflow_and_mtl()
+    torch.set_num_threads(min(16, len(os.sched_getaffinity(0))))
+    which = sys.argv[1:] or ["t3", "s3gen", "variants", "turbo"]
+    if "t3" in which:
+        golden_t3()
+    if "s3gen" in which:
+        golden_flow_hift()
+    if "variants" in which:
+        golden_meanflow_and_mtl()
+    if "turbo" in which:
+        golden_turbo()

@@ -125,6 +125,31 @@ def build_t3(multilingual=False):
     return T3(hp).eval()
 
 
+def build_t3_turbo(text_vocab=50276, n_layers=24):
+    """Turbo T3 exactly as tts_turbo.py:151-166 constructs it (GPT2_medium backbone).  `n_layers` / `text_vocab`
+    only shrink the *config values* handed to the unmodified reference constructors (fewer identical blocks, a
+    smaller gather table) so that fixtures stay small; 24 / 50276 are the shipped values."""
+    install()
+    from chatterbox.models.t3 import llama_configs
+    from chatterbox.models.t3.t3 import T3
+    from chatterbox.models.t3.modules.t3_config import T3Config
+    hp = T3Config(text_tokens_dict_size=text_vocab)
+    hp.llama_config_name = "GPT2_medium"
+    hp.speech_tokens_dict_size = 6563
+    hp.input_pos_emb = None
+    hp.speech_cond_prompt_len = 375
+    hp.use_perceiver_resampler = False
+    hp.emotion_adv = False
+    saved = llama_configs.LLAMA_CONFIGS["GPT2_medium"]
+    try:
+        llama_configs.LLAMA_CONFIGS["GPT2_medium"] = dict(saved, n_layer=n_layers, attn_pdrop=0.0, embd_pdrop=0.0,
+                                                          resid_pdrop=0.0)
+        t3 = T3(hp)
+    finally:
+        llama_configs.LLAMA_CONFIGS["GPT2_medium"] = saved
+    return t3.eval()
+
+
 def build_flow(meanflow=False):
     """CausalMaskedDiffWithXvec exactly as constructed in s3gen.py:64-104."""
     install()

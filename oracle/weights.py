@@ -111,6 +111,62 @@ def make_t3_weights(seed=0, text_vocab=704, n_layers=T3_LAYERS, head_std=0.06):
     return sd
 
 
+# ----------------------------------------------------------------------------- T3 Turbo (GPT-2 backbone)
+TURBO_SPEECH_VOCAB = 6563
+TURBO_LAYERS = 24
+
+
+def t3_turbo_spec(text_vocab=50276, n_layers=TURBO_LAYERS):
+    """Turbo T3 (reference tts_turbo.py:151-159: T3Config(text_tokens_dict_size=50276), GPT2_medium backbone
+    llama_configs.py:35-68, speech vocab 6563, no learned input position tables, no perceiver, no emotion).
+    GPT-2 `Conv1D` weights are stored [in, out] (transformers pytorch_utils.Conv1D)."""
+    D = T3_DIM
+    s = [("tfmr.wpe.weight", (8196, D), "p")]
+    for i in range(n_layers):
+        p = f"tfmr.h.{i}."
+        s.append((p + "ln_1.weight", (D,), "n")); s.append((p + "ln_1.bias", (D,), "b"))
+        s.append((p + "attn.c_attn.weight", (D, 3 * D), "wt")); s.append((p + "attn.c_attn.bias", (3 * D,), "b"))
+        s.append((p + "attn.c_proj.weight", (D, D), "wt")); s.append((p + "attn.c_proj.bias", (D,), "b"))
+        s.append((p + "ln_2.weight", (D,), "n")); s.append((p + "ln_2.bias", (D,), "b"))
+        s.append((p + "mlp.c_fc.weight", (D, 4 * D), "wt")); s.append((p + "mlp.c_fc.bias", (4 * D,), "b"))
+        s.append((p + "mlp.c_proj.weight", (4 * D, D), "wt")); s.append((p + "mlp.c_proj.bias", (D,), "b"))
+    s.append(("tfmr.ln_f.weight", (D,), "n")); s.append(("tfmr.ln_f.bias", (D,), "b"))
+    s.append(("cond_enc.spkr_enc.weight", (D, 256), "w"))
+    s.append(("cond_enc.spkr_enc.bias", (D,), "b"))
+    s.append(("text_emb.weight", (text_vocab, D), "e"))
+    s.append(("speech_emb.weight", (TURBO_SPEECH_VOCAB, D), "e"))
+    s.append(("text_head.weight", (text_vocab, D), "w"))
+    s.append(("speech_head.weight", (TURBO_SPEECH_VOCAB, D), "h"))
+    s.append(("speech_head.bias", (TURBO_SPEECH_VOCAB,), "b"))
+    return s
+
+
+def make_t3_turbo_weights(seed=0, text_vocab=50276, n_layers=TURBO_LAYERS, head_std=0.06):
+    """Seeded Turbo checkpoint with the reference key names (`tfmr.wte.weight` is left out: the reference deletes it
+    right after loading, tts_turbo.py:166, and it is never read on the inputs_embeds path)."""
+    sd = OrderedDict()
+    for key, shape, kind in t3_turbo_spec(text_vocab, n_layers):
+        if kind == "w":
+            sd[key] = _randn(seed, "turbo." + key, shape, std=0.7 / math.sqrt(shape[-1]), bf16=True)
+        elif kind == "wt":      # Conv1D [in, out]: fan-in is shape[0]
+            sd[key] = _randn(seed, "turbo." + key, shape, std=0.7 / math.sqrt(shape[0]), bf16=True)
+        elif kind == "h":
+            w = _randn(seed, "turbo." + key, shape, std=head_std, bf16=True)
+            w[6561:] = w[6561:] * (2.0 ** -6)      # BOS/EOS logits near zero (see make_t3_weights)
+            sd[key] = w
+        elif kind == "n":
+            sd[key] = _randn(seed, "turbo." + key, shape, std=0.1, mean=1.0)
+        elif kind == "b":
+            sd[key] = _randn(seed, "turbo." + key, shape, std=0.02)
+        elif kind == "e":
+            sd[key] = _randn(seed, "turbo." + key, shape, std=0.5)
+        elif kind == "p":
+            sd[key] = _randn(seed, "turbo." + key, shape, std=0.1)
+        else:
+            raise ValueError(kind)
+    return sd
+
+
 # ----------------------------------------------------------------------------- flow (encoder + CFM estimator)
 def flow_spec(meanflow=False):
     s = []

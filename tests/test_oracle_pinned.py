@@ -12,6 +12,7 @@ from oracle import weights as W
 from oracle.t3_ref import T3Oracle
 from oracle.flow_ref import FlowOracle
 from oracle.hift_ref import HiFTOracle
+from oracle.t3_turbo_ref import TurboOracle
 
 
 
@@ -27,6 +28,26 @@ def test_t3_oracle_matches_reference_tokens_and_logits(golden_dir):
         toks, logits = orc.inference(c3, case["text_tokens"], case["steps"], temperature=0.8, top_p=1.0,
                                      min_p=case["min_p"], repetition_penalty=1.2, cfg_weight=0.5,
                                      return_logits=True)
+        assert torch.equal(toks, case["tokens"]), (toks, case["tokens"])       # bit-exact ids
+        err = (logits[0] - case["prefill_logits"]).abs().max().item()
+        assert err < 2e-4, err
+
+
+def test_turbo_oracle_matches_reference_tokens_and_logits(golden_dir):
+    """Turbo T3 (GPT-2 backbone, reference t3.py:392-468): the restatement reproduces the reference's sampled and
+    greedy ids bit for bit (same torch CPU RNG stream) and its prefill logits."""
+    g = torch.load(os.path.join(golden_dir, "turbo_golden.pt"))
+    sd = W.make_t3_turbo_weights(g["weights_seed"], text_vocab=g["text_vocab"])
+    c3, _ = W.make_conds(g["conds_seed"], n_t3_prompt=g["n_prompt"])
+    orc = TurboOracle(sd)
+    for case in g["cases"]:
+        cond = orc.prepare_conditioning(c3["speaker_emb"], c3["cond_prompt_speech_tokens"])
+        assert cond.shape[1] == case["len_cond"] == 1 + g["n_prompt"]
+        assert torch.allclose(cond[:, :4], case["cond_emb_head"], atol=2e-5, rtol=1e-5)
+        torch.manual_seed(case["rng_seed"])
+        toks, logits = orc.inference_turbo(c3, case["text_tokens"], temperature=0.8, top_k=case["top_k"],
+                                           top_p=case["top_p"], repetition_penalty=case["rep"],
+                                           max_gen_len=case["steps"], return_logits=True)
         assert torch.equal(toks, case["tokens"]), (toks, case["tokens"])       # bit-exact ids
         err = (logits[0] - case["prefill_logits"]).abs().max().item()
         assert err < 2e-4, err
