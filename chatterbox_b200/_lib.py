@@ -27,7 +27,7 @@ class T3State(C.Structure):
                 ("x", C.c_void_p), ("logits", C.c_void_p), ("ldl", C.c_int),
                 ("cfg_weight", C.c_float), ("rep_penalty", C.c_float), ("temperature", C.c_float),
                 ("min_p", C.c_float), ("top_p", C.c_float),
-                ("q_noise", C.c_void_p), ("seed", C.c_ulonglong)]
+                ("q_noise", C.c_void_p), ("seed", C.c_ulonglong), ("sampler", C.c_int), ("top_k", C.c_int)]
 
 
 class HiftGeom(C.Structure):

@@ -188,7 +188,9 @@ size_t cbx_t3_workspace_bytes(cbx_handle* h, int n_tok_prefill, int n_rows) {
   if (!h) return 0;
   try {
     cbx_t3_state st; memset(&st, 0, sizeof(st));
-    st.n_rows = n_rows; st.cfg = 1; st.n_utts = (n_rows + 1) / 2; st.ldl = 8256;
+    const bool gpt = h->t3.gpt;     // Turbo: one row per utterance, inference_turbo sampler
+    st.n_rows = n_rows; st.cfg = gpt ? 0 : 1; st.n_utts = gpt ? n_rows : (n_rows + 1) / 2; st.ldl = 8256;
+    st.sampler = gpt ? 1 : 0;
     Ctx c = make_ctx(h, nullptr, 0, nullptr, true);
     t3_prefill(h, c, st, n_tok_prefill, nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr, 34, nullptr, nullptr,
                nullptr, nullptr);

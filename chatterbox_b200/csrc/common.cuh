@@ -190,7 +190,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 // activations used by epilogues / elementwise kernels
 // ---------------------------------------------------------------------------------------------
 enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_MISH = 3, ACT_ELU = 4, ACT_LRELU = 5, ACT_SNAKE = 6,
-                 ACT_TANH = 7 };
+                 ACT_TANH = 7, ACT_GELU_TANH = 8 };
 
 // transcendental activations stay out of line: inlining them into unrolled epilogues blows the kernels up to
 // hundreds of KB and the SM then stalls on instruction fetch (ncu: stalled_no_instructions ~40%)
@@ -208,6 +208,8 @@ static __device__ __noinline__ float act_apply_slow(int act, float v, float p) {
       return v + (1.0f / (p + 1e-9f)) * (s * s);
     }
     case ACT_TANH: return tanhf(v);
+    case ACT_GELU_TANH:   // transformers NewGELUActivation (GPT-2 'gelu_new')
+      return 0.5f * v * (1.0f + tanhf(0.79788456080286535588f * (v + 0.044715f * (v * v * v))));
     default: return v;
   }
 }

@@ -208,7 +208,8 @@ void pack_hilo(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat16* 
 __global__ void t3_embed_kernel(float* out, int n_tok, const int* tok_row, const int* tok_pos, const float* cond,
                                 const int* row_voice, int len_cond, const int* text_flat, const int* text_start,
                                 const int* n_text, const int* row_uncond, const float* text_emb, int text_vocab,
-                                const float* text_pos, const float* speech_emb, const float* speech_pos, int bos_id) {
+                                const float* text_pos, const float* speech_emb, const float* speech_pos, int bos_id,
+                                const float* wpe) {
   const int i = blockIdx.x;
   const int row = tok_row[i], pos = tok_pos[i];
   float* o = out + (long)i * 1024;
@@ -221,23 +222,28 @@ __global__ void t3_embed_kernel(float* out, int n_tok, const int* tok_row, const
     int id = text_flat[text_start[row] + j];
     if (id < 0 || id >= text_vocab) id = 0;
     const float* e = text_emb + (long)id * 1024;
-    const float* pe = text_pos + (long)j * 1024;
+    const float* pe = text_pos ? text_pos + (long)j * 1024 : nullptr;       // Turbo has no learned input tables
     const bool unc = row_uncond[row] != 0;
-    for (int d = threadIdx.x; d < 1024; d += blockDim.x) o[d] = (unc ? 0.f : e[d]) + pe[d];
+    for (int d = threadIdx.x; d < 1024; d += blockDim.x) o[d] = (unc ? 0.f : e[d]) + (pe ? pe[d] : 0.f);
   } else {
     const float* e = speech_emb + (long)bos_id * 1024;
-    for (int d = threadIdx.x; d < 1024; d += blockDim.x) o[d] = e[d] + speech_pos[d];
+    for (int d = threadIdx.x; d < 1024; d += blockDim.x) o[d] = e[d] + (speech_pos ? speech_pos[d] : 0.f);
+  }
+  if (wpe) {   // GPT2Model adds wpe[position] to inputs_embeds (modeling_gpt2.py GPT2Model.forward)
+    __syncthreads();
+    const float* w = wpe + (long)pos * 1024;
+    for (int d = threadIdx.x; d < 1024; d += blockDim.x) o[d] += w[d];
   }
 }
 void t3_embed(Ctx& ctx, float* out, int n_tok, const int* tok_row, const int* tok_pos, const float* cond,
               const int* row_voice, int len_cond, const int* text_flat, const int* text_start, const int* n_text,
               const int* row_uncond, const float* text_emb, int text_vocab, const float* text_pos,
-              const float* speech_emb, const float* speech_pos, int bos_id) {
+              const float* speech_emb, const float* speech_pos, int bos_id, const float* wpe) {
   if (ctx.dry || n_tok == 0) return;
   ctx.launches++;
   t3_embed_kernel<<<n_tok, 256, 0, ctx.stream>>>(out, n_tok, tok_row, tok_pos, cond, row_voice, len_cond, text_flat,
                                                 text_start, n_text, row_uncond, text_emb, text_vocab, text_pos,
-                                                speech_emb, speech_pos, bos_id);
+                                                speech_emb, speech_pos, bos_id, wpe);
   CBX_CHECK(cudaGetLastError());
 }
 
@@ -263,45 +269,52 @@ __global__ void __launch_bounds__(1024) t3_sample_kernel(T3SampleDev p) {
   extern __shared__ float smf[];
   float* lg = smf;                              // [SV] logits -> probabilities
   float* sh = smf + SV;                         // [64] reduction scratch
-  float* skey = sh + 64;                        // [SV_PAD] sort keys (top-p only)
+  float* skey = sh + 64;                        // [SV_PAD] sort keys (top-k / top-p only)
   int* sidx = reinterpret_cast<int*>(skey + SV_PAD);   // [SV_PAD]
   const int j = blockIdx.x;
   const int utt = p.act_utt[j];
   if (p.done[utt]) return;
+  const int V = p.vocab;                        // 8194, Turbo 6563 (tables keep the SV stride)
+  const bool turbo = p.turbo != 0;
   const int rows_per = p.cfg ? 2 : 1;
   const float* lc = p.logits + (long)(j * rows_per) * p.ldl;
   const float* lu = p.cfg ? lc + p.ldl : nullptr;
   const int step = p.n_gen[utt];
   unsigned char* seen = p.seen + (long)utt * SV;
-  const float w = p.cfg_weight, rp = p.rep_penalty, invT = 1.0f / p.temperature;
-  // 1-3: CFG combine, repetition penalty (history incl. BOS), temperature
+  const float w = p.cfg_weight, rp = p.rep_penalty;
+  // T3.inference (t3.py:339-356): CFG combine, repetition penalty (history incl. BOS), temperature, min-p, top-p.
+  // T3.inference_turbo (t3.py:396-404): temperature, top-k, top-p, repetition penalty (history: BOS for the first
+  // token, then the generated ids only).
   float mx = -INFINITY;
-  for (int v = threadIdx.x; v < SV; v += blockDim.x) {
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
     float l = lc[v];
-    if (lu) l = l + w * (l - lu[v]);
-    if (seen[v]) l = (l < 0.f) ? l * rp : l / rp;
-    if (p.temperature != 1.0f) l = l / p.temperature;
+    if (!turbo) {
+      if (lu) l = l + w * (l - lu[v]);
+      if (seen[v]) l = (l < 0.f) ? l * rp : l / rp;
+      if (p.temperature != 1.0f) l = l / p.temperature;
+    } else if (p.temperature > 0.f && p.temperature != 1.0f) {
+      l = l / p.temperature;
+    }
     lg[v] = l;
     mx = fmaxf(mx, l);
   }
-  (void)invT;
   mx = block_max(mx, sh);
-  // 4: min-p: drop softmax(l) < min_p * max prob (max prob = 1/Z); keep >= 1 token (the max itself)
-  float z = 0.f;
-  for (int v = threadIdx.x; v < SV; v += blockDim.x) z += expf(lg[v] - mx);
-  z = block_sum(z, sh);
-  const float pmax = 1.0f / z;
-  for (int v = threadIdx.x; v < SV; v += blockDim.x) {
-    const float pr = expf(lg[v] - mx) / z;
-    if (pr < p.min_p * pmax && lg[v] < mx) lg[v] = -INFINITY;
+  if (!turbo) {
+    // min-p: drop softmax(l) < min_p * max prob (max prob = 1/Z); keep >= 1 token (the max itself)
+    float z = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) z += expf(lg[v] - mx);
+    z = block_sum(z, sh);
+    const float pmax = 1.0f / z;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float pr = expf(lg[v] - mx) / z;
+      if (pr < p.min_p * pmax && lg[v] < mx) lg[v] = -INFINITY;
+    }
   }
   __syncthreads();
-  // 5: top-p (ascending sort; remove while cumulative prob <= 1 - top_p; keep the last one)
-  if (p.top_p < 1.0f) {
-    float z2 = 0.f;
-    for (int v = threadIdx.x; v < SV; v += blockDim.x) z2 += (lg[v] == -INFINITY) ? 0.f : expf(lg[v] - mx);
-    z2 = block_sum(z2, sh);
-    for (int v = threadIdx.x; v < SV_PAD; v += blockDim.x) { skey[v] = (v < SV) ? lg[v] : INFINITY; sidx[v] = v; }
+  const bool use_topk = turbo && p.top_k > 0 && p.top_k < V;
+  if (p.top_p < 1.0f || use_topk) {
+    // ascending bitonic sort of (logit, id); ids >= V are +inf padding and end up behind the vocabulary
+    for (int v = threadIdx.x; v < SV_PAD; v += blockDim.x) { skey[v] = (v < V) ? lg[v] : INFINITY; sidx[v] = v; }
     __syncthreads();
     for (int k = 2; k <= SV_PAD; k <<= 1)
       for (int jj = k >> 1; jj > 0; jj >>= 1) {
@@ -316,24 +329,51 @@ __global__ void __launch_bounds__(1024) t3_sample_kernel(T3SampleDev p) {
         }
         __syncthreads();
       }
-    // sequential fp64 cumulative sum over the ascending order (torch CPU cumsum accumulates float in fp64)
-    if (threadIdx.x == 0) {
-      double cum = 0.0;
-      const float thr = 1.0f - p.top_p;
-      for (int i = 0; i < SV - 1; ++i) {          // never remove the last (largest) one
-        const float pr = (skey[i] == -INFINITY) ? 0.f : expf(skey[i] - mx) / z2;
-        cum += (double)pr;
-        if ((float)cum <= thr) lg[sidx[i]] = -INFINITY; else break;
+    if (use_topk) {
+      // TopKLogitsWarper: remove scores < k-th largest (ties with the threshold stay)
+      const float kth = skey[V - p.top_k];
+      __syncthreads();
+      for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        if (lg[v] < kth) lg[v] = -INFINITY;
+        if (skey[v] < kth) skey[v] = -INFINITY;
       }
+      __syncthreads();
     }
+    if (p.top_p < 1.0f) {
+      // TopPLogitsWarper: ascending order; remove while cumulative prob <= 1 - top_p; never the last (largest) one
+      float z2 = 0.f;
+      for (int v = threadIdx.x; v < V; v += blockDim.x) z2 += (lg[v] == -INFINITY) ? 0.f : expf(lg[v] - mx);
+      z2 = block_sum(z2, sh);
+      // sequential fp64 cumulative sum over the ascending order (torch CPU cumsum accumulates float in fp64)
+      if (threadIdx.x == 0) {
+        double cum = 0.0;
+        const float thr = 1.0f - p.top_p;
+        for (int i = 0; i < V - 1; ++i) {
+          const float pr = (skey[i] == -INFINITY) ? 0.f : expf(skey[i] - mx) / z2;
+          cum += (double)pr;
+          if ((float)cum <= thr) lg[sidx[i]] = -INFINITY; else break;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (turbo) {
+    // RepetitionPenaltyLogitsProcessor comes last in inference_turbo; the softmax below needs the new maximum
+    float m2 = -INFINITY;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      float l = lg[v];
+      if (seen[v] && rp != 1.0f) { l = (l < 0.f) ? l * rp : l / rp; lg[v] = l; }
+      m2 = fmaxf(m2, l);
+    }
+    mx = block_max(m2, sh);
     __syncthreads();
   }
   // 6: softmax + sample
   float z3 = 0.f;
-  for (int v = threadIdx.x; v < SV; v += blockDim.x) z3 += (lg[v] == -INFINITY) ? 0.f : expf(lg[v] - mx);
+  for (int v = threadIdx.x; v < V; v += blockDim.x) z3 += (lg[v] == -INFINITY) ? 0.f : expf(lg[v] - mx);
   z3 = block_sum(z3, sh);
   float best = -1.f; int besti = SV;
-  for (int v = threadIdx.x; v < SV; v += blockDim.x) {
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
     const float pr = (lg[v] == -INFINITY) ? 0.f : expf(lg[v] - mx) / z3;
     float q;
     if (p.q_noise) q = p.q_noise[((long)step * p.n_utts + utt) * SV + v];
@@ -363,10 +403,12 @@ __global__ void __launch_bounds__(1024) t3_sample_kernel(T3SampleDev p) {
   __syncthreads();
   const int tok = bi[0];
   // 7: bookkeeping + next embedding (speech_emb[tok] + speech_pos[step+1], both CFG rows)
-  const bool finished = (tok == p.eos_id) || (step + 1 >= p.max_new[utt]);
+  // inference_turbo samples its first token from the prefill without an EOS check (t3.py:428-433)
+  const bool finished = (tok == p.eos_id && !(turbo && step == 0)) || (step + 1 >= p.max_new[utt]);
   if (threadIdx.x == 0) {
     p.tokens[(long)utt * p.max_tokens + step] = tok;
     p.n_gen[utt] = step + 1;
+    if (turbo && step == 0) seen[p.bos_id] = 0;     // from the second token on the history is the generated ids only
     seen[tok] = 1;
     if (finished) p.done[utt] = 1;
     for (int r = 0; r < rows_per; ++r) {
@@ -375,7 +417,8 @@ __global__ void __launch_bounds__(1024) t3_sample_kernel(T3SampleDev p) {
     }
   }
   const float* e = p.speech_emb + (long)tok * 1024;
-  const float* pe = p.speech_pos + (long)(step + 1) * 1024;
+  // next input: speech_emb[tok] + speech_pos_emb[step+1] (t3.py:371-372); Turbo: + wpe[absolute position] (GPT2Model)
+  const float* pe = turbo ? p.wpe + (long)(p.base_pos[utt * rows_per] + step) * 1024 : p.speech_pos + (long)(step + 1) * 1024;
   for (int d = threadIdx.x; d < 1024; d += blockDim.x) {
     const float v = e[d] + pe[d];
     for (int r = 0; r < rows_per; ++r) p.x[((long)(j * rows_per + r)) * 1024 + d] = v;

@@ -14,12 +14,17 @@ struct DevVec {   // small fp32 parameter vector on the device
 };
 
 // ---- T3 ------------------------------------------------------------------------------------------
-struct T3Layer { Weight qkv, o, gu, down; DevVec ln1, ln2; };
+// Llama backbone: qkv, o, gu (gate/up interleaved), down, RMSNorm weights ln1/ln2.
+// GPT-2 backbone (Turbo): qkv = c_attn, o = attn.c_proj, gu = mlp.c_fc, down = mlp.c_proj (all with bias), LayerNorm
+// weights ln1/ln2 + biases ln1_b/ln2_b.
+struct T3Layer { Weight qkv, o, gu, down; DevVec ln1, ln2, ln1_b, ln2_b; };
 struct T3Model {
   bool ready = false;
+  bool gpt = false;          // Turbo: GPT-2 blocks, learned absolute positions (wpe), no CFG, speech vocab 6563
   int n_layers = 0, text_vocab = 0, max_pos = 0;
+  int vocab = 8194;          // rows of speech_head / speech_emb
   std::vector<T3Layer> layers;
-  DevVec final_norm, text_emb, speech_emb, text_pos, speech_pos, rope_cos, rope_sin;
+  DevVec final_norm, final_norm_b, text_emb, speech_emb, text_pos, speech_pos, rope_cos, rope_sin, wpe;
   Weight head;
   // conditioning encoder
   Weight spkr, pq, pk, pv, pproj;

@@ -18,6 +18,10 @@ struct T3SampleDev {
   const float* speech_emb; const float* speech_pos;
   const float* q_noise;                  // optional [steps][B][8194] Exp(1) noise (parity mode), else counter RNG
   unsigned long long seed;
+  int vocab;                             // speech ids scored (8194; Turbo 6563)
+  int turbo;                             // 1: T3.inference_turbo processor order (temperature, top-k, top-p, repetition penalty)
+  int top_k; int bos_id;
+  const float* wpe;                      // Turbo: learned absolute positions, added to the next input embedding
 };
 
 void ew_act(Ctx& ctx, const float* x, int ldx, float* y, int ldy, long rows, int cols, int act, float p, const float* vec);
@@ -29,7 +33,7 @@ void pack_hilo_cat(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat
 void t3_embed(Ctx& ctx, float* out, int n_tok, const int* tok_row, const int* tok_pos, const float* cond,
               const int* row_voice, int len_cond, const int* text_flat, const int* text_start, const int* n_text,
               const int* row_uncond, const float* text_emb, int text_vocab, const float* text_pos,
-              const float* speech_emb, const float* speech_pos, int bos_id);
+              const float* speech_emb, const float* speech_pos, int bos_id, const float* wpe = nullptr);
 void t3_sample(Ctx& ctx, const T3SampleDev& p, int n_act);
 void add_pos_bias(Ctx& ctx, const float* qkv, int ld, const float* u, const float* v, float* qu, float* qv, long rows);
 void relpos_table(Ctx& ctx, float* pe, int T, int d_model);

@@ -2,6 +2,9 @@
 //   prefill  : packed tokens -> 30 x [RMSNorm, QKV GEMM, RoPE + KV append, causal flash attention, O GEMM(+res),
 //              RMSNorm, gate/up GEMM with fused SiLU*mul, down GEMM(+res)] -> final norm -> speech head
 //   decode   : per step  sampler kernel -> same layer stack with paged decode attention (one token per row)
+// Turbo (reference t3.py:392-468, tts_turbo.py:151-166) swaps the backbone for transformers GPT2Model: LayerNorm,
+// fused c_attn with bias, learned absolute positions (wpe) added to the input embeddings, gelu_new MLP, no RoPE, no CFG,
+// speech head with bias over 6563 ids.  Same kernels, same paged KV cache; the RoPE tables are the identity.
 #include "engine.h"
 
 namespace cbx {
@@ -12,8 +15,56 @@ static std::vector<float> concat_rows(const std::vector<const HostTensor*>& ts) 
   return out;
 }
 
+// GPT-2 `Conv1D` keeps its weight as [in, out]; the GEMM packs K-major [out, in]
+static std::vector<float> transposed(const HostTensor& t) {
+  const int K = (int)t.shape[0], N = (int)t.shape[1];
+  std::vector<float> out((size_t)N * K);
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < N; ++n) out[(size_t)n * K + k] = t.data[(size_t)k * N + n];
+  return out;
+}
+
+static void t3_finalize_gpt(cbx_handle* h) {
+  T3Model& m = h->t3;
+  m.gpt = true;
+  int L = 0;
+  while (has_tensor(h, "t3.tfmr.h." + std::to_string(L) + ".attn.c_attn.weight")) ++L;
+  m.n_layers = L;
+  m.layers.resize(L);
+  CBX_REQUIRE(host_tensor(h, "t3.tfmr.h.0.attn.c_attn.weight").shape[0] == 1024, "only the 1024-wide GPT2_medium Turbo backbone is supported");
+  for (int i = 0; i < L; ++i) {
+    const std::string p = "t3.tfmr.h." + std::to_string(i) + ".";
+    T3Layer& ly = m.layers[i];
+    pack_linear(ly.qkv, transposed(host_tensor(h, p + "attn.c_attn.weight")).data(), host_tensor(h, p + "attn.c_attn.bias").data.data(), 3072, 1024);
+    pack_linear(ly.o, transposed(host_tensor(h, p + "attn.c_proj.weight")).data(), host_tensor(h, p + "attn.c_proj.bias").data.data(), 1024, 1024);
+    pack_linear(ly.gu, transposed(host_tensor(h, p + "mlp.c_fc.weight")).data(), host_tensor(h, p + "mlp.c_fc.bias").data.data(), 4096, 1024);
+    pack_linear(ly.down, transposed(host_tensor(h, p + "mlp.c_proj.weight")).data(), host_tensor(h, p + "mlp.c_proj.bias").data.data(), 1024, 4096);
+    ly.ln1 = upload_tensor(h, p + "ln_1.weight"); ly.ln1_b = upload_tensor(h, p + "ln_1.bias");
+    ly.ln2 = upload_tensor(h, p + "ln_2.weight"); ly.ln2_b = upload_tensor(h, p + "ln_2.bias");
+  }
+  m.final_norm = upload_tensor(h, "t3.tfmr.ln_f.weight");
+  m.final_norm_b = upload_tensor(h, "t3.tfmr.ln_f.bias");
+  m.wpe = upload_tensor(h, "t3.tfmr.wpe.weight");
+  m.text_emb = upload_tensor(h, "t3.text_emb.weight");
+  m.text_vocab = (int)host_tensor(h, "t3.text_emb.weight").shape[0];
+  m.speech_emb = upload_tensor(h, "t3.speech_emb.weight");
+  m.vocab = (int)host_tensor(h, "t3.speech_head.weight").shape[0];
+  CBX_REQUIRE(m.vocab <= 8194 && (int)host_tensor(h, "t3.speech_emb.weight").shape[0] == m.vocab, "speech vocab");
+  m.rope_cos = upload_tensor(h, "t3.rope_cos");      // identity tables supplied by the host shim: cos = 1, sin = 0
+  m.rope_sin = upload_tensor(h, "t3.rope_sin");
+  m.max_pos = (int)host_tensor(h, "t3.tfmr.wpe.weight").shape[0];
+  CBX_REQUIRE((int)host_tensor(h, "t3.rope_cos").shape[0] >= m.max_pos, "rope identity table shorter than wpe");
+  pack_linear(m.head, host_tensor(h, "t3.speech_head.weight").data.data(), host_tensor(h, "t3.speech_head.bias").data.data(),
+              m.vocab, 1024);
+  pack_linear(m.spkr, host_tensor(h, "t3.cond_enc.spkr_enc.weight").data.data(),
+              host_tensor(h, "t3.cond_enc.spkr_enc.bias").data.data(), 1024, 256);
+  m.ready = true;
+}
+
 void t3_finalize(cbx_handle* h) {
   T3Model& m = h->t3;
+  if (has_tensor(h, "t3.tfmr.h.0.attn.c_attn.weight")) { t3_finalize_gpt(h); return; }
+  m.gpt = false; m.vocab = 8194;
   int L = 0;
   while (has_tensor(h, "t3.tfmr.layers." + std::to_string(L) + ".self_attn.q_proj.weight")) ++L;
   CBX_REQUIRE(L > 0, "no T3 layers loaded");
@@ -103,6 +154,18 @@ void t3_cond_encode(cbx_handle* h, Ctx& ctx, const float* spk, const int* prompt
                     int n_voices, float* cond_out) {
   T3Model& m = h->t3;
   CBX_REQUIRE(m.ready, "t3 weights not finalized");
+  if (m.gpt) {
+    // Turbo: [spkr_enc(speaker_emb) | speech_emb(prompt tokens)], no position table, no perceiver, no emotion row
+    // (t3.py:96-100 with is_gpt; cond_enc.py:64-97 with use_perceiver_resampler / emotion_adv off)
+    const int lc = 1 + n_prompt;
+    for (int v = 0; v < n_voices; ++v) {
+      float* out = cond_out + (size_t)v * lc * 1024;
+      gemm(ctx, gemm_args_linear(spk + (size_t)v * 256, 256, 1, m.spkr, out, 1024), m.spkr);
+      gather_rows(ctx, m.speech_emb.p, 1024, prompt + (size_t)v * n_prompt, out + 1024, 1024, n_prompt, 1024, nullptr, 0,
+                  nullptr, m.vocab);
+    }
+    return;
+  }
   const int len_cond = 34;
   float* emb = ctx.ws.get<float>((size_t)n_prompt * 1024);
   float* pre = ctx.ws.get<float>((size_t)32 * 1024);
@@ -128,6 +191,46 @@ static PagedKV paged_of(const cbx_t3_state& st, int n_layers) {
   return kv;
 }
 
+// ---- Turbo: one transformers GPT2Block on n rows (modeling_gpt2.py GPT2Block.forward) -----------------
+//   x += c_proj(attn(c_attn(ln_1(x)))) ; x += mlp.c_proj(gelu_new(mlp.c_fc(ln_2(x))))
+// `attend(att_hi, att_lo)` appends K/V to the paged cache and writes the attention output either as fp32 `att`
+// (att_hi == nullptr) or as bf16 planes.
+template <class Attend>
+static void gpt_block(Ctx& ctx, T3Layer& ly, float* x, int n, float* xn, float* qkv, float* att, float* act, bool planes,
+                      bool att_planes, Attend&& attend) {
+  __nv_bfloat16* xn_hi = reinterpret_cast<__nv_bfloat16*>(xn);   __nv_bfloat16* xn_lo = xn_hi + (size_t)n * 1024;
+  __nv_bfloat16* at_hi = reinterpret_cast<__nv_bfloat16*>(att);  __nv_bfloat16* at_lo = at_hi + (size_t)n * 1024;
+  __nv_bfloat16* ac_hi = reinterpret_cast<__nv_bfloat16*>(act);  __nv_bfloat16* ac_lo = ac_hi + (size_t)n * 4096;
+  GemmDev gq = gemm_args_linear(xn, 1024, n, ly.qkv, qkv, 3072);
+  if (planes) {
+    layernorm(ctx, x, 1024, ly.ln1.p, ly.ln1_b.p, nullptr, 1024, n, 1024, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr, xn_hi, xn_lo);
+    gq.A = nullptr; gq.Ahi = xn_hi; gq.Alo = xn_lo; gq.ldab = 1024;
+  } else {
+    layernorm(ctx, x, 1024, ly.ln1.p, ly.ln1_b.p, xn, 1024, n, 1024, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
+  }
+  gemm(ctx, gq, ly.qkv);
+  const bool ap = planes && att_planes;
+  attend(ap ? at_hi : nullptr, ap ? at_lo : nullptr);
+  GemmDev go = gemm_args_linear(att, 1024, n, ly.o, x, 1024);
+  if (ap) { go.A = nullptr; go.Ahi = at_hi; go.Alo = at_lo; go.ldab = 1024; }
+  go.res = x; go.ldr = 1024;
+  gemm(ctx, go, ly.o);
+  GemmDev gf = gemm_args_linear(xn, 1024, n, ly.gu, act, 4096);
+  GemmDev gd = gemm_args_linear(act, 4096, n, ly.down, x, 1024);
+  gf.act = ACT_GELU_TANH;
+  if (planes) {
+    layernorm(ctx, x, 1024, ly.ln2.p, ly.ln2_b.p, nullptr, 1024, n, 1024, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr, xn_hi, xn_lo);
+    gf.A = nullptr; gf.Ahi = xn_hi; gf.Alo = xn_lo; gf.ldab = 1024;
+    gf.C = nullptr; gf.Chi = ac_hi; gf.Clo = ac_lo; gf.ldcb = 4096;
+    gd.A = nullptr; gd.Ahi = ac_hi; gd.Alo = ac_lo; gd.ldab = 4096;
+  } else {
+    layernorm(ctx, x, 1024, ly.ln2.p, ly.ln2_b.p, xn, 1024, n, 1024, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
+  }
+  gemm(ctx, gf, ly.gu);
+  gd.res = x; gd.ldr = 1024;
+  gemm(ctx, gd, ly.down);
+}
+
 void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, const int* tok_row, const int* tok_pos,
                 const int* row_start, const int* row_len, int max_row_len, const float* cond, const int* row_voice,
                 int len_cond, const int* text_flat, const int* text_start, const int* n_text, const int* row_uncond) {
@@ -142,7 +245,7 @@ void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, cons
   float* hn = ctx.ws.get<float>((size_t)R * 1024);
   int* last = ctx.ws.get<int>(R);
   t3_embed(ctx, x, n_tok, tok_row, tok_pos, cond, row_voice, len_cond, text_flat, text_start, n_text, row_uncond,
-           m.text_emb.p, m.text_vocab, m.text_pos.p, m.speech_emb.p, m.speech_pos.p, 6561);
+           m.text_emb.p, m.text_vocab, m.text_pos.p, m.speech_emb.p, m.speech_pos.p, 6561, m.gpt ? m.wpe.p : nullptr);
   PagedKV kv = paged_of(st, m.n_layers);
   // tensor-core batches: GEMM operands that a norm / SwiGLU epilogue produces travel as bf16 hi/lo planes (see t3_decode)
   const bool planes = (n_tok > 8 && ctx.gemm_impl == 0);
@@ -150,6 +253,17 @@ void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, cons
   __nv_bfloat16* ac_hi = reinterpret_cast<__nv_bfloat16*>(act);  __nv_bfloat16* ac_lo = ac_hi + (size_t)n_tok * 4096;
   for (int l = 0; l < m.n_layers; ++l) {
     T3Layer& ly = m.layers[l];
+    if (m.gpt) {
+      gpt_block(ctx, ly, x, n_tok, xn, qkv, att, act, planes, false, [&](__nv_bfloat16*, __nv_bfloat16*) {
+        rope_and_store_kv(ctx, qkv, 3072, kv, l, tok_row, tok_pos, 0, n_tok, m.rope_cos.p, m.rope_sin.p);   // identity rotation
+        AttnArgs a;
+        a.Q = qkv; a.K = qkv + 1024; a.V = qkv + 2048; a.ldq = a.ldk = a.ldv = 3072; a.O = att; a.ldo = 1024;
+        a.n_seq = R; a.n_heads = 16; a.q_start = row_start; a.q_len = row_len; a.kv_start = row_start; a.kv_len = row_len;
+        a.max_q_len = max_row_len; a.scale = 0.125f; a.causal = 1;
+        attention(ctx, a);
+      });
+      continue;
+    }
     if (planes) {
       rmsnorm(ctx, x, 1024, ly.ln1.p, nullptr, 1024, n_tok, 1024, 1e-5f, nullptr, xn_hi, xn_lo);
       GemmDev gq = gemm_args_linear(nullptr, 1024, n_tok, ly.qkv, qkv, 3072);
@@ -192,7 +306,13 @@ void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, cons
     ctx.launches++;
     last_index_kernel<<<(R + 127) / 128, 128, 0, ctx.stream>>>(row_start, row_len, last, R);
   }
-  rmsnorm(ctx, x, 1024, m.final_norm.p, hn, 1024, R, 1024, 1e-5f, last);
+  if (m.gpt) {        // ln_f on the last position of every row, then the speech head (with bias)
+    float* hl = ctx.ws.get<float>((size_t)R * 1024);
+    gather_rows(ctx, x, 1024, last, hl, 1024, R, 1024, nullptr, 0, nullptr, n_tok);
+    layernorm(ctx, hl, 1024, m.final_norm.p, m.final_norm_b.p, hn, 1024, R, 1024, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
+  } else {
+    rmsnorm(ctx, x, 1024, m.final_norm.p, hn, 1024, R, 1024, 1e-5f, last);
+  }
   gemm(ctx, gemm_args_linear(hn, 1024, R, m.head, st.logits, st.ldl), m.head);
 }
 
@@ -217,6 +337,9 @@ void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, const int* act_u
   sp.tokens = st.tokens; sp.max_tokens = st.max_tokens; sp.n_gen = st.n_gen; sp.max_new = st.max_new; sp.done = st.done;
   sp.seen = st.seen; sp.positions = st.positions; sp.base_pos = st.base_pos; sp.x = st.x;
   sp.speech_emb = m.speech_emb.p; sp.speech_pos = m.speech_pos.p; sp.q_noise = st.q_noise; sp.seed = st.seed;
+  sp.vocab = m.vocab; sp.turbo = m.gpt ? 1 : 0; sp.top_k = st.top_k; sp.bos_id = 6561; sp.wpe = m.gpt ? m.wpe.p : nullptr;
+  CBX_REQUIRE((st.sampler != 0) == m.gpt, "cbx_t3_state.sampler does not match the loaded backbone (1 = Turbo)");
+  CBX_REQUIRE(!(m.gpt && st.cfg), "the Turbo backbone runs without CFG rows");
   float* x = st.x;
   // Tensor-core batches (S > 8): every GEMM operand travels as bf16 hi/lo planes written by its producer (RMSNorm,
   // paged attention, SwiGLU epilogue) and is loaded by TMA -- no fp32->bf16 converter pass in the GEMM main loop.
@@ -229,6 +352,13 @@ void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, const int* act_u
     t3_sample(ctx, sp, n_act);
     for (int l = 0; l < m.n_layers; ++l) {
       T3Layer& ly = m.layers[l];
+      if (m.gpt) {
+        gpt_block(ctx, ly, x, S, xn, qkv, att, act, planes, true, [&](__nv_bfloat16* ah, __nv_bfloat16* al) {
+          rope_and_store_kv(ctx, qkv, 3072, kv, l, slot_row, st.positions, 1, S, m.rope_cos.p, m.rope_sin.p);
+          paged_decode_attention(ctx, qkv, 3072, kv, l, slot_row, S, st.positions, ah ? nullptr : att, 1024, scratch, nsplit, ah, al);
+        });
+        continue;
+      }
       if (planes) {
         rmsnorm(ctx, x, 1024, ly.ln1.p, nullptr, 1024, S, 1024, 1e-5f, nullptr, xn_hi, xn_lo);
         GemmDev gq = gemm_args_linear(nullptr, 1024, S, ly.qkv, qkv, 3072);
@@ -266,7 +396,8 @@ void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, const int* act_u
       gd.res = x; gd.ldr = 1024;
       gemm(ctx, gd, ly.down);
     }
-    rmsnorm(ctx, x, 1024, m.final_norm.p, xn, 1024, S, 1024, 1e-5f, nullptr);
+    if (m.gpt) layernorm(ctx, x, 1024, m.final_norm.p, m.final_norm_b.p, xn, 1024, S, 1024, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
+    else rmsnorm(ctx, x, 1024, m.final_norm.p, xn, 1024, S, 1024, 1e-5f, nullptr);
     gemm(ctx, gemm_args_linear(xn, 1024, S, m.head, st.logits, st.ldl), m.head);
   }
 }

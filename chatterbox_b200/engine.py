@@ -101,6 +101,7 @@ class Engine:
         self.h = Handle(device)
         self._ws = None
         self.t3_layers = 0
+        self.t3_turbo = False       # GPT-2 backbone (reference tts_turbo.py): no CFG, learned absolute positions
         self.meanflow = False
         # algorithmic-traffic bookkeeping for bench.py's roofline (bytes the paged decode attention must read)
         self.stats = dict(paged_bytes=0.0, paged_launches=0, decode_steps=0, decode_row_steps=0)
@@ -113,12 +114,21 @@ class Engine:
             self.h.call("cbx_load_tensor", (prefix + k).encode(), C.c_void_p(t.data_ptr()), t.dim(), shape)
 
     def load_t3(self, sd, max_pos=4608):
-        sd = {k: v for k, v in sd.items() if not k.startswith("text_head") and not k.startswith("tfmr.embed_tokens")}
+        """State dict with the reference key names: Llama backbone (`tfmr.layers.*`, t3.py:49-85) or the Turbo GPT-2
+        backbone (`tfmr.h.*`, `tfmr.wpe`, tts_turbo.py:151-166; `tfmr.wte` is ignored like the reference deletes it)."""
+        sd = {k: v for k, v in sd.items() if not k.startswith("text_head") and not k.startswith("tfmr.embed_tokens")
+              and not k.startswith("tfmr.wte")}
+        self.t3_turbo = any(k.startswith("tfmr.h.") for k in sd)
         self._load("t3.", sd)
-        cos, sin = llama3_rope_tables(max_pos)
+        if self.t3_turbo:
+            n_pos = int(sd["tfmr.wpe.weight"].shape[0])
+            cos, sin = torch.ones(n_pos, 32), torch.zeros(n_pos, 32)      # GPT-2 has no rotary embedding: identity
+            self.t3_layers = len({k.split(".")[2] for k in sd if k.startswith("tfmr.h.")})
+        else:
+            cos, sin = llama3_rope_tables(max_pos)
+            self.t3_layers = len({k.split(".")[2] for k in sd if k.startswith("tfmr.layers.")})
         self._load("t3.", {"rope_cos": cos, "rope_sin": sin})
         self.h.call("cbx_finalize_weights", b"t3")
-        self.t3_layers = len({k.split(".")[2] for k in sd if k.startswith("tfmr.layers.")})
 
     def load_flow(self, sd, max_len=5000):
         self._load("flow.", sd)
@@ -150,7 +160,8 @@ class Engine:
         nv = spk.shape[0]
         ptok = prompt_tokens.to(dev, torch.int32).reshape(nv, -1).contiguous()
         emo = emotion_adv.to(dev, torch.float32).reshape(nv).contiguous()
-        out = torch.empty(nv, LEN_COND, 1024, device=dev, dtype=torch.float32)
+        len_cond = 1 + ptok.shape[1] if self.t3_turbo else LEN_COND      # Turbo: [spkr | prompt embeddings]
+        out = torch.empty(nv, len_cond, 1024, device=dev, dtype=torch.float32)
         ws = self.workspace(self.h.lib.cbx_t3_workspace_bytes(self.h.h, 256, 2))
         self.h.call("cbx_t3_cond_encode", _ptr(spk), _ptr(ptok), ptok.shape[1], _ptr(emo), nv, _ptr(out), _ptr(ws),
                     ws.numel(), self._stream())
@@ -158,19 +169,24 @@ class Engine:
 
     def t3_generate(self, text_tokens, cond, voice_ids=None, max_new_tokens=1000, cfg_weight=0.5, temperature=0.8,
                     top_p=1.0, min_p=0.05, repetition_penalty=1.2, q_noise=None, seed=0, kv_dtype="bf16",
-                    max_sync_steps=32, return_state=False):
-        """Batched equivalent of T3.inference (t3.py:225-390).
-        text_tokens: list of 1-D int tensors incl. SOT/EOT (one per utterance).  cond: [n_voices,34,1024].
-        max_new_tokens: int or per-utterance list.  Returns a list of 1-D int64 CPU tensors (EOS included if hit)."""
+                    max_sync_steps=32, return_state=False, top_k=0):
+        """Batched equivalent of T3.inference (t3.py:225-390) or, with a Turbo checkpoint loaded, of
+        T3.inference_turbo (t3.py:392-468: no CFG, processors temperature -> top_k -> top_p -> repetition penalty,
+        min_p unused; max_new_tokens counts the token sampled from the prefill, i.e. max_gen_len + 1).
+        text_tokens: list of 1-D int tensors incl. SOT/EOT (Turbo: raw tokenizer ids), one per utterance.
+        cond: [n_voices, len_cond, 1024] from t3_cond.  max_new_tokens: int or per-utterance list.
+        Returns a list of 1-D int64 CPU tensors (EOS included if hit)."""
         dev = self.device
         B = len(text_tokens)
-        cfg = 1 if cfg_weight > 0.0 else 0
+        turbo = self.t3_turbo
+        len_cond = int(cond.shape[1])
+        cfg = 1 if (cfg_weight > 0.0 and not turbo) else 0
         rp = 2 if cfg else 1
         R = B * rp
         voice_ids = [0] * B if voice_ids is None else list(voice_ids)
         max_new = [int(max_new_tokens)] * B if np.isscalar(max_new_tokens) else [int(m) for m in max_new_tokens]
         n_text = np.array([len(t) for t in text_tokens], dtype=np.int32)
-        s0 = LEN_COND + n_text + 2
+        s0 = len_cond + n_text + (1 if turbo else 2)       # [cond | text | BOS (| BOS)]  (t3.py:126-129, 305-313, 407-413)
         row_len = np.repeat(s0, rp).astype(np.int32)
         row_start = np.concatenate([[0], np.cumsum(row_len)[:-1]]).astype(np.int32)
         n_tok = int(row_len.sum())
@@ -213,11 +229,11 @@ class Engine:
                      _ptr(st_t["positions"]), _ptr(st_t["base_pos"]), _ptr(st_t["tokens"]), max_tokens,
                      _ptr(st_t["n_gen"]), _ptr(st_t["max_new"]), _ptr(st_t["done"]), _ptr(st_t["seen"]),
                      _ptr(st_t["x"]), _ptr(st_t["logits"]), LDL, float(cfg_weight), float(repetition_penalty),
-                     float(temperature), float(min_p), float(top_p), _ptr(qn), int(seed))
+                     float(temperature), float(min_p), float(top_p), _ptr(qn), int(seed), 1 if turbo else 0, int(top_k))
         ws = self.workspace(self.h.lib.cbx_t3_workspace_bytes(self.h.h, n_tok, R))
         cond = cond.to(dev, torch.float32).contiguous()
         self.h.call("cbx_t3_prefill", C.byref(st), n_tok, _ptr(d["tok_row"]), _ptr(d["tok_pos"]), _ptr(d["row_start"]),
-                    _ptr(d["row_len"]), int(row_len.max()), _ptr(cond), _ptr(d["row_voice"]), LEN_COND,
+                    _ptr(d["row_len"]), int(row_len.max()), _ptr(cond), _ptr(d["row_voice"]), len_cond,
                     _ptr(d["text_flat"]), _ptr(d["row_text_start"]), _ptr(d["row_ntext"]), _ptr(d["row_uncond"]),
                     _ptr(ws), ws.numel(), self._stream())
         if return_state == "prefill":

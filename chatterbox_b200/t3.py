@@ -36,8 +36,8 @@ class T3:
             engine.load_t3(state_dict)
 
     def prepare_conditioning(self, t3_cond: T3Cond):
-        """reference t3.py:92-100 -> (1, 34, 1024) on the device."""
-        emo = t3_cond.emotion_adv
+        """reference t3.py:92-100 -> (1, 34, 1024) on the device (Turbo: (1, 1 + n_prompt, 1024))."""
+        emo = t3_cond.emotion_adv if t3_cond.emotion_adv is not None else 0.0
         emo = emo if torch.is_tensor(emo) else torch.tensor(float(emo))
         return self.engine.t3_cond(t3_cond.speaker_emb, t3_cond.cond_prompt_speech_tokens, emo.reshape(-1)[:1])
 
@@ -61,3 +61,26 @@ class T3:
                                        temperature=temperature, top_p=top_p, min_p=min_p,
                                        repetition_penalty=repetition_penalty, q_noise=qn, seed=seed, kv_dtype=kv_dtype)
         return toks[0][None]
+
+    @torch.inference_mode()
+    def inference_turbo(self, t3_cond: T3Cond, text_tokens, temperature=0.8, top_k=1000, top_p=0.95,
+                        repetition_penalty=1.2, max_gen_len=1000, q_noise=None, seed=0, kv_dtype="bf16"):
+        """reference t3.py:392-468 (Turbo checkpoint: GPT-2 backbone, no CFG).  text_tokens (1, n) tokenizer ids;
+        returns LongTensor (1, n_generated) with a trailing EOS stripped, like the reference (t3.py:465-466).
+        Extra kwargs as in inference(): q_noise [steps, V] Exp(1) draws for torch.multinomial parity."""
+        assert self.engine.t3_turbo, "inference_turbo needs a Turbo (GPT-2 backbone) checkpoint"
+        text_tokens = torch.atleast_2d(text_tokens).to(torch.long)
+        cond = self.prepare_conditioning(t3_cond)
+        qn = None
+        if q_noise is not None:          # the engine's noise rows keep the 8194 stride of the speech vocabulary
+            qn = torch.ones(q_noise.shape[0], 1, 8194, dtype=torch.float32)
+            qn[:, 0, :q_noise.shape[1]] = q_noise
+        toks = self.engine.t3_generate([text_tokens[0].cpu()], cond, max_new_tokens=max_gen_len + 1, cfg_weight=0.0,
+                                       temperature=temperature, top_p=top_p, min_p=0.0,
+                                       repetition_penalty=repetition_penalty, q_noise=qn, seed=seed, kv_dtype=kv_dtype,
+                                       top_k=top_k)
+        t = toks[0]
+        self._last_turbo_draws = int(t.numel())      # tokens sampled incl. a trailing EOS (one multinomial draw each)
+        if t.numel() > 0 and int(t[-1]) == self.stop_speech_token:
+            t = t[:-1]
+        return t[None]

@@ -85,21 +85,31 @@ typedef struct {
   float cfg_weight, rep_penalty, temperature, min_p, top_p;
   const float* q_noise;    /* optional device [steps][n_utts][8194] Exp(1) draws (torch.multinomial parity) */
   unsigned long long seed; /* counter-RNG seed when q_noise == NULL */
+  int sampler;             /* 0 = T3.inference order (CFG, repetition penalty, temperature, min-p, top-p; t3.py:339-356),
+                              1 = T3.inference_turbo order (temperature, top-k, top-p, repetition penalty; t3.py:396-404);
+                              must match the loaded backbone (Llama / GPT-2) */
+  int top_k;               /* sampler 1 only; <= 0 disables */
 } cbx_t3_state;
 
 /* replaces T3.prepare_conditioning + T3CondEnc.forward + Perceiver.forward
- * (t3.py:92-100, modules/cond_enc.py:64-97, modules/perceiver.py:200-212).  cond_out [n_voices][34][1024] */
+ * (t3.py:92-100, modules/cond_enc.py:64-97, modules/perceiver.py:200-212).  cond_out [n_voices][34][1024].
+ * Turbo checkpoint (GPT-2 backbone, tts_turbo.py:151-159: no perceiver, no emotion row, no position table):
+ * cond_out [n_voices][1 + n_prompt][1024] = [spkr_enc(speaker_emb) | speech_emb(prompt_tokens)]; emotion_adv unused */
 int cbx_t3_cond_encode(cbx_handle* h, const float* speaker_emb, const int* prompt_tokens, int n_prompt,
                        const float* emotion_adv, int n_voices, float* cond_out, void* ws, size_t ws_bytes,
                        cbx_stream stream);
 /* replaces T3.prepare_input_embeds + the prefill forward of T3.inference (t3.py:102-130, 303-335 ->
- * transformers LlamaModel.forward) for a packed batch of n_tok tokens; fills the KV pages and st->logits */
+ * transformers LlamaModel.forward) for a packed batch of n_tok tokens; fills the KV pages and st->logits.
+ * Row layout [cond(len_cond) | text | BOS | BOS]; Turbo (T3.inference_turbo prefill, t3.py:407-424 -> transformers
+ * GPT2Model.forward with inputs_embeds, wpe added inside): [cond | text | BOS], one row per utterance */
 int cbx_t3_prefill(cbx_handle* h, const cbx_t3_state* st, int n_tok, const int* tok_row, const int* tok_pos,
                    const int* row_start, const int* row_len, int max_row_len, const float* cond,
                    const int* row_voice, int len_cond, const int* text_flat, const int* text_start,
                    const int* n_text, const int* row_uncond, void* ws, size_t ws_bytes, cbx_stream stream);
 /* replaces n_steps iterations of the sampling loop of T3.inference (t3.py:338-386): sample (CFG, repetition
- * penalty, temperature, min-p, top-p, multinomial) then one cached forward, for the n_act active utterances */
+ * penalty, temperature, min-p, top-p, multinomial) then one cached forward, for the n_act active utterances.
+ * With st->sampler == 1 it is the loop of T3.inference_turbo (t3.py:426-461): the first token comes from the prefill
+ * logits without an EOS check, history for the repetition penalty is BOS for that token and the generated ids after */
 int cbx_t3_decode(cbx_handle* h, const cbx_t3_state* st, const int* act_utt, const int* slot_row, int n_act,
                   int n_steps, void* ws, size_t ws_bytes, cbx_stream stream);
 /* keep only slots whose utterance is listed in new_act (gathers x / logits rows; keep_slot = old slot index) */

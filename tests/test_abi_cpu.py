@@ -77,3 +77,37 @@ def test_punc_norm_and_token_cleanup():
     assert punc_norm("") == "You need to add some text for me to talk."
     x = torch.tensor([6561, 5, 7, 6562, 9])
     assert drop_invalid_tokens(x).tolist() == [5, 7]
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """include/cbx.h is plain C: compile a probe with gcc and compare sizes / field offsets with the ctypes mirrors."""
+    import ctypes as C
+    import subprocess
+    from chatterbox_b200._lib import T3State, Layout, HiftGeom
+    fields = ["n_utts", "kv_pages", "page_table", "n_pages", "positions", "tokens", "max_new", "seen", "logits", "ldl",
+              "cfg_weight", "top_p", "q_noise", "seed", "sampler", "top_k"]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "cbx.h"', 'int main(void) {',
+           'printf("%zu %zu %zu\\n", sizeof(cbx_t3_state), sizeof(cbx_layout), sizeof(cbx_hift_geom));']
+    src += [f'printf("%zu\\n", offsetof(cbx_t3_state, {f}));' for f in fields]
+    src += ['return 0; }']
+    c = tmp_path / "probe.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert [int(x) for x in out[:3]] == [C.sizeof(T3State), C.sizeof(Layout), C.sizeof(HiftGeom)]
+    assert [int(x) for x in out[3:]] == [getattr(T3State, f).offset for f in fields]
+
+
+def test_turbo_shim_surface():
+    """Turbo boundary mirrors the reference's (tts_turbo.py:104-321, t3.py:392-394) without needing a GPU."""
+    import inspect
+    from chatterbox_b200 import ChatterboxTurboTTS, T3
+    sig = inspect.signature(T3.inference_turbo)
+    for name, default in [("temperature", 0.8), ("top_k", 1000), ("top_p", 0.95), ("repetition_penalty", 1.2),
+                          ("max_gen_len", 1000)]:
+        assert sig.parameters[name].default == default
+    gsig = inspect.signature(ChatterboxTurboTTS.generate)
+    for name, default in [("repetition_penalty", 1.2), ("min_p", 0.0), ("top_p", 0.95), ("exaggeration", 0.0),
+                          ("cfg_weight", 0.0), ("temperature", 0.8), ("top_k", 1000), ("norm_loudness", True)]:
+        assert gsig.parameters[name].default == default
