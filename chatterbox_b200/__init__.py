@@ -12,7 +12,7 @@ from ._lib import CbxError, LIB_PATH  # noqa: F401
 from .engine import Engine, PackedLayout  # noqa: F401
 from .t3 import T3, T3Cond  # noqa: F401
 from .s3gen import S3Gen  # noqa: F401
-from .tts import ChatterboxTTS, Conditionals, punc_norm  # noqa: F401
+from .tts import ChatterboxTTS, ChatterboxMultilingualTTS, Conditionals, punc_norm  # noqa: F401
 from .tts_turbo import ChatterboxTurboTTS  # noqa: F401
 
-__all__ = ["Engine", "T3", "T3Cond", "S3Gen", "ChatterboxTTS", "ChatterboxTurboTTS", "Conditionals", "punc_norm", "CbxError"]
+__all__ = ["Engine", "T3", "T3Cond", "S3Gen", "ChatterboxTTS", "ChatterboxMultilingualTTS", "ChatterboxTurboTTS", "Conditionals", "punc_norm", "CbxError"]

@@ -261,3 +261,51 @@ class ChatterboxTTS:
         if return_intermediates:
             return out, dict(tokens=toks, speech_tokens=st, mel=mel, source=src)
         return out
+
+
+# reference mtl_tts.py:31-55
+SUPPORTED_LANGUAGES = {
+    "ar": "Arabic", "da": "Danish", "de": "German", "el": "Greek", "en": "English", "es": "Spanish", "fi": "Finnish",
+    "fr": "French", "he": "Hebrew", "hi": "Hindi", "it": "Italian", "ja": "Japanese", "ko": "Korean", "ms": "Malay",
+    "nl": "Dutch", "no": "Norwegian", "pl": "Polish", "pt": "Portuguese", "ru": "Russian", "sv": "Swedish",
+    "sw": "Swahili", "tr": "Turkish", "zh": "Chinese",
+}
+
+
+def mtl_tail_trim(wav, n_speech_tokens):
+    """reference mtl_tts.py:346-351: drop the audio of the final speech token (960 samples per token, keep >= 1)."""
+    keep = max(1, int(n_speech_tokens) - 1) * (S3GEN_SR // 25)
+    return wav[..., :keep]
+
+
+class ChatterboxMultilingualTTS(ChatterboxTTS):
+    """Drop-in for reference ChatterboxMultilingualTTS (mtl_tts.py:137-355): the same hot path with the multilingual
+    T3 checkpoint (text vocabulary 2454, t3_config.py:28-41); language only changes the token ids
+    (`[lang]` prefix token, models/tokenizers/tokenizer.py:301-302), plus the tail-trim rule of mtl_tts.py:346-351."""
+
+    @classmethod
+    def get_supported_languages(cls):
+        return SUPPORTED_LANGUAGES.copy()
+
+    def text_to_tokens(self, text, language_id=None):
+        assert self.tokenizer is not None, "no multilingual tokenizer loaded; pass token ids to generate_tokens()"
+        return self.tokenizer.text_to_tokens(text, language_id=language_id)
+
+    @torch.inference_mode()
+    def generate(self, text, language_id, audio_prompt_path=None, exaggeration=0.5, cfg_weight=0.5, temperature=0.8,
+                 repetition_penalty=1.2, min_p=0.05, top_p=1.0, max_new_tokens=1000, rng="torch_cpu", kv_dtype="bf16"):
+        """reference mtl_tts.py:280-355 (same keyword defaults)."""
+        if language_id and language_id.lower() not in SUPPORTED_LANGUAGES:
+            raise ValueError(f"Unsupported language_id '{language_id}'. Supported languages: "
+                             + ", ".join(SUPPORTED_LANGUAGES.keys()))
+        assert audio_prompt_path is None, "prepare_conditionals is outside the hot path; set .conds"
+        ids = self.text_to_tokens(punc_norm(text), language_id=language_id.lower() if language_id else None)
+        return self.generate_tokens(ids, repetition_penalty=repetition_penalty, min_p=min_p, top_p=top_p,
+                                    exaggeration=exaggeration, cfg_weight=cfg_weight, temperature=temperature,
+                                    max_new_tokens=max_new_tokens, rng=rng, kv_dtype=kv_dtype)
+
+    @torch.inference_mode()
+    def generate_tokens(self, text_tokens, *args, return_intermediates=False, **kw):
+        wav, mid = super().generate_tokens(text_tokens, *args, return_intermediates=True, **kw)
+        wav = mtl_tail_trim(wav, mid["speech_tokens"].numel())
+        return (wav, mid) if return_intermediates else wav

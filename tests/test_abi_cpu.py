@@ -111,3 +111,15 @@ def test_turbo_shim_surface():
     for name, default in [("repetition_penalty", 1.2), ("min_p", 0.0), ("top_p", 0.95), ("exaggeration", 0.0),
                           ("cfg_weight", 0.0), ("temperature", 0.8), ("top_k", 1000), ("norm_loudness", True)]:
         assert gsig.parameters[name].default == default
+
+
+def test_multilingual_shim_rules():
+    """mtl_tts.py:293-298 (language validation) and :346-351 (tail trim) without a GPU."""
+    from chatterbox_b200.tts import ChatterboxMultilingualTTS, mtl_tail_trim, SUPPORTED_LANGUAGES
+    assert len(SUPPORTED_LANGUAGES) == 23 and "sw" in ChatterboxMultilingualTTS.get_supported_languages()
+    wav = torch.arange(5 * 960, dtype=torch.float32)[None]
+    assert mtl_tail_trim(wav, 5).shape == (1, 4 * 960)
+    assert mtl_tail_trim(wav[:, :960], 1).shape == (1, 960)          # keeps at least one token of audio
+    tts = ChatterboxMultilingualTTS.__new__(ChatterboxMultilingualTTS)
+    with pytest.raises(ValueError):
+        tts.generate("hola", language_id="xx")
