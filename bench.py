@@ -167,6 +167,7 @@ def run_engine(args, rank, world, local_rank):
     from oracle import weights as W            # only the seeded synthetic checkpoint generator + cpu_baseline leg
     from chatterbox_b200 import ChatterboxTTS, Conditionals, T3, T3Cond, S3Gen, Engine
     torch.cuda.set_device(local_rank)
+    torch.set_num_threads(max(1, host_threads() // max(1, world)))     # host-side weight synthesis: do not oversubscribe
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = Engine(local_rank)
