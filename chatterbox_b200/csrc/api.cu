@@ -71,6 +71,7 @@ void cbx_destroy(cbx_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (void* p : h->owned) cudaFree(p);
+  if (h->decode_exec) cudaGraphExecDestroy(h->decode_exec);
   auto fw = [](Weight& w) { free_weight(w); };
   for (auto& l : h->t3.layers) { fw(l.qkv); fw(l.o); fw(l.gu); fw(l.down); }
   fw(h->t3.head); fw(h->t3.spkr); fw(h->t3.pq); fw(h->t3.pk); fw(h->t3.pv); fw(h->t3.pproj);
@@ -84,6 +85,7 @@ int cbx_set_option(cbx_handle* h, const char* key, const char* value) {
   const std::string k = key, v = value;
   if (k == "gemm") h->gemm_impl = (v == "simt") ? 1 : 0;
   else if (k == "attn") h->attn_impl = (v == "simt") ? 1 : 0;
+  else if (k == "decode_graph") h->decode_graph = (v == "1" || v == "on") ? 1 : 0;
   else if (k == "time_kernel") {
     h->timer.drain(); h->timer.ms = 0.0; h->timer.n = 0; h->timer.work = 0.0;
     h->timer.cls = v == "gemm_tc" ? K_GEMM_TC : v == "gemv" ? K_GEMV : v == "flash" ? K_FLASH : v == "paged" ? K_PAGED : K_NONE;

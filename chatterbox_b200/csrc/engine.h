@@ -73,6 +73,10 @@ struct cbx_handle {
   int gemm_impl = 0, attn_impl = 0;
   long long launches = 0;
   cbx::KTimer timer;
+  // "decode_graph" option: steps 2..n of a cbx_t3_decode call replay a CUDA graph captured from step 1 (launch-bound
+  // small batches).  The executable of the previous call is released at the next call / destroy.
+  int decode_graph = 0;
+  cudaGraphExec_t decode_exec = nullptr;
   std::vector<void*> owned;                      // device allocations to free
 };
 

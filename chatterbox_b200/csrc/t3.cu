@@ -348,7 +348,7 @@ void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, const int* act_u
   __nv_bfloat16* xn_hi = reinterpret_cast<__nv_bfloat16*>(xn);   __nv_bfloat16* xn_lo = xn_hi + (size_t)S * 1024;
   __nv_bfloat16* at_hi = reinterpret_cast<__nv_bfloat16*>(att);  __nv_bfloat16* at_lo = at_hi + (size_t)S * 1024;
   __nv_bfloat16* ac_hi = reinterpret_cast<__nv_bfloat16*>(act);  __nv_bfloat16* ac_lo = ac_hi + (size_t)S * 4096;
-  for (int step = 0; step < n_steps; ++step) {
+  auto one_step = [&]() {
     t3_sample(ctx, sp, n_act);
     for (int l = 0; l < m.n_layers; ++l) {
       T3Layer& ly = m.layers[l];
@@ -399,7 +399,37 @@ void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, const int* act_u
     if (m.gpt) layernorm(ctx, x, 1024, m.final_norm.p, m.final_norm_b.p, xn, 1024, S, 1024, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
     else rmsnorm(ctx, x, 1024, m.final_norm.p, xn, 1024, S, 1024, 1e-5f, nullptr);
     gemm(ctx, gemm_args_linear(xn, 1024, S, m.head, st.logits, st.ldl), m.head);
+  
+  };
+  // Launch-bound small batches (B=1: ~250 launches per step): capture one step into a CUDA graph and replay it.
+  // Every launch parameter of a step is constant within one call (positions / tokens / done flags live on the device),
+  // so the graph of step 1 is valid for steps 2..n-1.  Step 0 runs directly so that lazy one-time setup
+  // (cudaFuncSetAttribute) happens outside the capture.  Needs a capturable (non-legacy) stream and no event timer.
+  const bool use_graph = h->decode_graph && !ctx.dry && !ctx.timer && n_steps >= 3 && ctx.stream != nullptr &&
+                         ctx.stream != cudaStreamLegacy;
+  if (!use_graph) {
+    for (int step = 0; step < n_steps; ++step) one_step();
+    return;
   }
+  if (h->decode_exec) { cudaGraphExecDestroy(h->decode_exec); h->decode_exec = nullptr; }   // previous call has drained
+  one_step();
+  const long before = ctx.launches;
+  cudaGraph_t graph = nullptr;
+  CBX_CHECK(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    one_step();
+  } catch (...) {
+    cudaStreamEndCapture(ctx.stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  CBX_CHECK(cudaStreamEndCapture(ctx.stream, &graph));
+  const long per_step = ctx.launches - before;
+  cudaError_t ge = cudaGraphInstantiate(&h->decode_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  CBX_CHECK(ge);
+  for (int step = 1; step < n_steps; ++step) CBX_CHECK(cudaGraphLaunch(h->decode_exec, ctx.stream));
+  ctx.launches += per_step * (long)(n_steps - 2);     // the captured step was counted once, it ran n_steps - 1 times
 }
 
 }  // namespace cbx

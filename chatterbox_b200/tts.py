@@ -62,6 +62,53 @@ def drop_invalid_tokens(x):
     return x[s:e]
 
 
+def synthesize_batch(eng, speech, refs, seed=0, flow_frames_per_chunk=120000, hift_frames_per_chunk=24000,
+                     n_cfm_timesteps=None, marks=None):
+    """speech tokens (list of 1-D id tensors) -> list of device waveforms: flow (encoder + CFM) and HiFT over packed
+    chunks, longest utterances first (stage part of generate_batch; shared with the Turbo front-end)."""
+    B = len(speech)
+    order = sorted(range(B), key=lambda b: -speech[b].numel())
+    mels = [None] * B
+    i = 0
+    while i < B:                                          # chunk the packed batch by total mel frames
+        j, frames = i, 0
+        while j < B:
+            f = 2 * (int(refs[order[j]]["prompt_token"].shape[-1]) + speech[order[j]].numel())
+            if j > i and frames + f > flow_frames_per_chunk:
+                break
+            frames += f
+            j += 1
+        idx = order[i:j]
+        out = eng.flow_mel([speech[b] for b in idx], [refs[b] for b in idx], n_timesteps=n_cfm_timesteps)
+        for b, m in zip(idx, out):
+            mels[b] = m
+        i = j
+    if marks is not None:
+        marks[0].record()
+    wavs = [None] * B
+    i = 0
+    while i < B:
+        j, frames = i, 0
+        while j < B:
+            f = int(mels[order[j]].shape[-1])
+            if j > i and frames + f > hift_frames_per_chunk:
+                break
+            frames += f
+            j += 1
+        idx = [b for b in order[i:j] if mels[b].shape[-1] > 0]
+        if idx:
+            w, _ = eng.hift([mels[b] for b in idx], seed=seed + i, trim_fade=True)
+            for b, x in zip(idx, w):
+                wavs[b] = x.clone()
+        for b in order[i:j]:
+            if wavs[b] is None:
+                wavs[b] = torch.zeros(0, device=eng.device)
+        i = j
+    if marks is not None:
+        marks[1].record()
+    return wavs
+
+
 class ChatterboxTTS:
     """Drop-in for reference ChatterboxTTS (tts.py:106-272); every FLOP of generate() runs in libcbx."""
 

@@ -7,7 +7,7 @@ import torch
 from .engine import Engine
 from .t3 import T3
 from .s3gen import S3Gen, S3GEN_SR, SPEECH_VOCAB_SIZE
-from .tts import Conditionals, punc_norm
+from .tts import Conditionals, punc_norm, synthesize_batch
 
 S3GEN_SIL = 4299            # reference models/s3gen/const.py:2
 TURBO_SPEECH_VOCAB = 6563   # tts_turbo.py:155
@@ -64,6 +64,42 @@ class ChatterboxTurboTTS:
         ids = self.tokenizer(punc_norm(text), return_tensors="pt", padding=True, truncation=True).input_ids
         return self.generate_tokens(ids, repetition_penalty=repetition_penalty, top_p=top_p, temperature=temperature,
                                     top_k=top_k, rng=rng, kv_dtype=kv_dtype)
+
+    @torch.inference_mode()
+    def generate_batch(self, text_tokens, max_gen_len=1000, repetition_penalty=1.2, top_p=0.95, temperature=0.8,
+                       top_k=1000, seed=0, kv_dtype="bf16", to_host=True, timings=None):
+        """Batched generate(): equal to calling the reference's Turbo generate() once per utterance (each with its own
+        device RNG stream, seed + utterance index).  text_tokens: list of 1-D tokenizer-id tensors; max_gen_len: int or
+        per-utterance list.  One T3 row per utterance (no CFG), 2-step meanflow CFM, HiFT.  Returns float32 waveforms."""
+        assert self.conds is not None, "Please set .conds (Conditionals)"
+        eng = self.engine
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        marks = [ev() for _ in range(4)]
+        marks[0].record()
+        B = len(text_tokens)
+        tts = [torch.as_tensor(t).reshape(-1).to(torch.long).cpu() for t in text_tokens]
+        c = self.conds.t3
+        cond = eng.t3_cond(c.speaker_emb.reshape(1, 256), c.cond_prompt_speech_tokens.reshape(1, -1), torch.zeros(1))
+        budgets = [int(max_gen_len) + 1] * B if np.isscalar(max_gen_len) else [int(m) + 1 for m in max_gen_len]
+        toks = eng.t3_generate(tts, cond, max_new_tokens=budgets, cfg_weight=0.0, temperature=temperature, top_p=top_p,
+                               min_p=0.0, repetition_penalty=repetition_penalty, seed=seed, kv_dtype=kv_dtype, top_k=top_k)
+        marks[1].record()
+        sil = torch.tensor([S3GEN_SIL] * 3, dtype=torch.long)
+        speech = []
+        for t in toks:                                        # tts_turbo.py:307-311 per utterance
+            if t.numel() > 0 and int(t[-1]) == 6562:
+                t = t[:-1]                                    # t3.py:465-466
+            speech.append(torch.cat([t[t < SPEECH_VOCAB_SIZE], sil]))
+        refs = [self.conds.gen] * B
+        wavs = synthesize_batch(eng, speech, refs, seed=seed, n_cfm_timesteps=2, marks=marks[2:4])
+        if to_host:
+            wavs = [w.cpu() for w in wavs]
+        torch.cuda.synchronize()
+        if timings is not None:
+            timings.update(t3_ms=marks[0].elapsed_time(marks[1]), flow_ms=marks[1].elapsed_time(marks[2]),
+                           hift_ms=marks[2].elapsed_time(marks[3]),
+                           audio_s=sum(int(x.numel()) for x in speech) / 25.0)
+        return wavs
 
     @torch.inference_mode()
     def generate_tokens(self, text_tokens, repetition_penalty=1.2, top_p=0.95, temperature=0.8, top_k=1000,

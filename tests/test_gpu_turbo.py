@@ -121,3 +121,9 @@ def test_turbo_generate_matches_oracle_pipeline(golden_dir):
     ref_wav2, _ = ho.inference(mid["mel"].cpu(), s=mid["source"].cpu())
     err2 = (wav - ref_wav2).abs().max().item()
     assert wav.shape == ref_wav2.shape and err2 < 2e-4, f"vocoder max|dwav|={err2}"
+    # batched front-end: one T3 row per utterance, 2-step meanflow, HiFT; 960 samples per speech token (+3 silence tokens)
+    tm = {}
+    wavs = tts.generate_batch([text[0], text[0][:10]], max_gen_len=[6, 9], top_k=1, timings=tm)
+    assert len(wavs) == 2 and all(torch.isfinite(w).all() for w in wavs)
+    assert sum(int(w.numel()) for w in wavs) == int(round(tm["audio_s"] * 25)) * 960
+    assert all(int(w.numel()) >= 4 * 960 for w in wavs)
