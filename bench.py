@@ -224,6 +224,7 @@ def run_engine(args, rank, world, local_rank):
     clk = clocks.stop() if rank == 0 else None
     log(f"timed: {ms:.1f} ms for {args.steps} steps")
     gemm_ms, gemm_n, gemm_flops = eng.h.timer_read()
+    gemm_bytes = eng.h.timer_read_bytes()
     stats_timed = dict(eng.stats)
     eng.h.set_option("time_kernel", "paged")          # second family, measured during the e2e pass below
     launches = eng.h.launch_count() - launches0
@@ -286,7 +287,12 @@ def run_engine(args, rank, world, local_rank):
                      "peak": tf_peak, "unit": "TFLOP/s", "frac": (gemm_flops / 1e12 / (gemm_ms / 1e3)) / tf_peak if gemm_ms > 0 else 0.0,
                      "traffic": None, "algorithmic_flops_per_launch": gemm_flops / max(1, gemm_n), "launches": gemm_n,
                      "avg_launch_ms": gemm_ms / max(1, gemm_n), "share_of_step": gemm_ms / ms,
-                     "note": "algorithmic flops = 2*M*N*K per launch (the bf16 hi/lo activation split issues 2x that on the tensor pipe)"},
+                     "note": "algorithmic flops = 2*M*N*K per launch (the bf16 hi/lo activation split issues 2x that on the tensor pipe)",
+                     # the same launches against the other roof: weights, activations and results once each (DESIGN.md 7:
+                     # the K=256 CFM block GEMMs sit below the ridge at fp32-precision activations)
+                     "hbm_view": {"algorithmic_bytes_per_launch": gemm_bytes / max(1, gemm_n),
+                                  "achieved": gemm_bytes / 1e9 / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0, "peak": hbm_peak,
+                                  "unit": "GB/s", "frac": (gemm_bytes / 1e9 / (gemm_ms / 1e3)) / hbm_peak if gemm_ms > 0 else 0.0}},
         "roofline_secondary": {"kernel": "paged_decode_kernel<bf16> (T3 decode attention over the paged KV cache)", "bound": "hbm",
                                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                                "algorithmic_bytes_per_launch": paged_bytes_per_launch, "launches": paged_n,

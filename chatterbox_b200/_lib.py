@@ -45,6 +45,7 @@ SYMBOLS = {
     "cbx_set_option": (_I, [_P, C.c_char_p, C.c_char_p]),
     "cbx_launch_count": (C.c_longlong, [_P]),
     "cbx_timer_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
+    "cbx_timer_read_bytes": (_I, [_P, C.POINTER(C.c_double)]),
     "cbx_load_tensor": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(C.c_int64)]),
     "cbx_finalize_weights": (_I, [_P, C.c_char_p]),
     "cbx_t3_cond_encode": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _S, _P]),
@@ -111,6 +112,11 @@ class Handle:
         ms, n, w = C.c_double(0), C.c_longlong(0), C.c_double(0)
         self.call("cbx_timer_read", C.byref(ms), C.byref(n), C.byref(w))
         return float(ms.value), int(n.value), float(w.value)
+
+    def timer_read_bytes(self):
+        b = C.c_double(0)
+        self.call("cbx_timer_read_bytes", C.byref(b))
+        return float(b.value)
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:

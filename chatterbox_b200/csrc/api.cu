@@ -87,7 +87,7 @@ int cbx_set_option(cbx_handle* h, const char* key, const char* value) {
   else if (k == "attn") h->attn_impl = (v == "simt") ? 1 : 0;
   else if (k == "decode_graph") h->decode_graph = (v == "1" || v == "on") ? 1 : 0;
   else if (k == "time_kernel") {
-    h->timer.drain(); h->timer.ms = 0.0; h->timer.n = 0; h->timer.work = 0.0;
+    h->timer.drain(); h->timer.ms = 0.0; h->timer.n = 0; h->timer.work = 0.0; h->timer.bytes = 0.0;
     h->timer.cls = v == "gemm_tc" ? K_GEMM_TC : v == "gemv" ? K_GEMV : v == "flash" ? K_FLASH : v == "paged" ? K_PAGED : K_NONE;
   }
   else { h->err = "unknown option " + k; return CBX_ERR_INVALID; }
@@ -101,6 +101,13 @@ int cbx_timer_read(cbx_handle* h, double* ms, long long* launches, double* work)
   h->timer.drain();
   *ms = h->timer.ms; *launches = h->timer.n;
   if (work) *work = h->timer.work;
+  return CBX_OK;
+}
+
+int cbx_timer_read_bytes(cbx_handle* h, double* bytes) {
+  if (!h || !bytes) return CBX_ERR_INVALID;
+  h->timer.drain();
+  *bytes = h->timer.bytes;
   return CBX_OK;
 }
 

@@ -749,7 +749,20 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
     tmA2 = tmA;
   }
   dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM);
-  if (ctx.timer && ctx.timer->cls == K_GEMM_TC) ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
+  if (ctx.timer && ctx.timer->cls == K_GEMM_TC) {
+    ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
+    // algorithmic HBM bytes: weights once (bf16), the activation matrix once (fp32 or hi+lo planes = 4 B per element),
+    // every output element once per destination, the residual once
+    const double a_rows = (g.a_mode == A_TAPS && g.ntaps > 1) ? (double)g.M_in : (double)g.M * g.stride;
+    double b = (double)g.Npad * g.Kpad * 2.0 + a_rows * (double)g.c_in * 4.0;
+    const double out_elems = (double)g.M * (double)(g.swiglu ? g.n_out / 2 : g.n_out);
+    if (g.C) b += out_elems * 4.0;
+    if (g.Chi) b += out_elems * 4.0;
+    if (g.C2) b += out_elems * 4.0;
+    if (g.res) b += out_elems * 4.0;
+    if (g.accumulate) b += out_elems * 4.0;
+    ctx.timer->bytes += b;
+  }
   if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
   gemm_tc_kernel<BN, DUAL><<<grid, TC_THREADS, TcCfg<BN, DUAL>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], tmA, tmA2, g);
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);

@@ -90,6 +90,7 @@ struct KTimer {
   size_t used = 0;
   double ms = 0.0; long long n = 0;
   double work = 0.0;             // algorithmic work of the timed launches (flops for GEMMs), added by the launcher
+  double bytes = 0.0;            // algorithmic HBM bytes of the timed launches (operands once in, results once out)
   void begin(int c, cudaStream_t st) {
     if (c != cls) return;
     if (used + 2 > ev.size()) {

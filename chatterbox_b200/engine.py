@@ -102,6 +102,7 @@ class Engine:
         self._ws = None
         self.t3_layers = 0
         self.t3_turbo = False       # GPT-2 backbone (reference tts_turbo.py): no CFG, learned absolute positions
+        self._decode_stream = None  # set_decode_graph(True): decode steps replay a CUDA graph on a side stream
         self.meanflow = False
         # algorithmic-traffic bookkeeping for bench.py's roofline (bytes the paged decode attention must read)
         self.stats = dict(paged_bytes=0.0, paged_launches=0, decode_steps=0, decode_row_steps=0)
@@ -150,6 +151,12 @@ class Engine:
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_decode_graph(self, on=True):
+        """Launch-bound small batches: steps 2..n of every cbx_t3_decode call replay a CUDA graph captured from step 1
+        (stream capture needs a non-default stream, so decode then runs on a side stream)."""
+        self.h.set_option("decode_graph", "1" if on else "0")
+        self._decode_stream = torch.cuda.Stream(self.device) if on else None
 
     # ------------------------------------------------------------------ T3
     def t3_cond(self, speaker_emb, prompt_tokens, emotion_adv):
@@ -239,6 +246,23 @@ class Engine:
         if return_state == "prefill":
             return st_t
         # decode with host-driven retirement of finished utterances
+        if self._decode_stream is not None:
+            self._decode_stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._decode_stream):
+                self._decode_loop(st, st_t, B, rp, max_new, max_sync_steps, s0, kvt, L, ws)
+            torch.cuda.current_stream(self.device).wait_stream(self._decode_stream)
+        else:
+            self._decode_loop(st, st_t, B, rp, max_new, max_sync_steps, s0, kvt, L, ws)
+        toks = st_t["tokens"].cpu()
+        n_gen = st_t["n_gen"].cpu()
+        out = [toks[b, :int(n_gen[b])].to(torch.int64) for b in range(B)]
+        if return_state:
+            return out, st_t
+        return out
+
+    def _decode_loop(self, st, st_t, B, rp, max_new, max_sync_steps, s0, kvt, L, ws):
+        dev = self.device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         act = np.arange(B, dtype=np.int32)
         n_gen_h = np.zeros(B, dtype=np.int64)
         budget = np.asarray(max_new, dtype=np.int64)
@@ -271,12 +295,6 @@ class Engine:
             if len(act):
                 d_keep = t(keep_slots.astype(np.int32))
                 self.h.call("cbx_t3_compact", C.byref(st), _ptr(d_keep), len(keep_slots), _ptr(ws), ws.numel(), self._stream())
-        toks = st_t["tokens"].cpu()
-        n_gen = st_t["n_gen"].cpu()
-        out = [toks[b, :int(n_gen[b])].to(torch.int64) for b in range(B)]
-        if return_state:
-            return out, st_t
-        return out
 
     # ------------------------------------------------------------------ flow
     def flow_mel(self, tokens, ref_dicts, z=None, n_timesteps=None, cfg_rate=0.7, return_mu=False):

@@ -59,6 +59,8 @@ long long cbx_launch_count(cbx_handle* h);
  * time and the number of launches since the option was set, plus (GEMM classes) the algorithmic flops 2*M*N*K of
  * those launches (bench.py's roofline object) */
 int cbx_timer_read(cbx_handle* h, double* ms, long long* launches, double* work);
+/* algorithmic HBM bytes of the same launches (GEMM family: weights, activations and results once each) */
+int cbx_timer_read_bytes(cbx_handle* h, double* bytes);
 /* host fp32 tensor with the reference's state-dict name ("t3." / "flow." / "hift." prefix added by the caller) */
 int cbx_load_tensor(cbx_handle* h, const char* name, const float* host_data, int ndim, const int64_t* shape);
 /* pack loaded tensors of one model ("t3" | "flow" | "hift"): bf16 K-major weights + TMA maps, QKV concat,
