@@ -19,6 +19,9 @@ constexpr int AT_Q_BYTES = 2 * 2 * AT_TILE;          // 128 rows x 2 planes = 32
 constexpr int AT_KV_STAGE = 4 * AT_TILE;             // K hi, K lo, V hi, V lo = 32 KB
 constexpr int AT_P_BYTES = 2 * 2 * AT_TILE;          // P hi, P lo (128 rows each) = 32 KB
 constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * AT_KV_STAGE + AT_P_BYTES + 1024 + 256 + 2048;   // + barriers + row exchange
+// F16 variant (one fp16 plane per operand, one MMA term): half the tile bytes, twice the K/V stages
+constexpr int AT_STAGES_F16 = 6;
+constexpr int AT_SMEM_F16 = AT_Q_BYTES / 2 + AT_STAGES_F16 * (AT_KV_STAGE / 2) + AT_P_BYTES / 2 + 1024 + 256 + 2048;
 
 struct AttnTcDev {
   float* O; int ldo;
@@ -42,6 +45,16 @@ __device__ __forceinline__ void split_pair_at(float a, float b, uint32_t& hi, ui
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// fp32 pair -> packed fp16x2 (round to nearest)
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// instruction descriptor for fp16 x fp16 -> f32 (a_format = b_format = 0), K-major A and B
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // MN-major SWIZZLE_128B descriptor (B operand stored [k][n], n contiguous, 64 n = one 128-byte row):
 // 8 k-rows per 1024-byte atom, atoms along k are SBO = 1024 B apart (cute/arch/mma_sm100_desc.hpp).
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
@@ -58,11 +71,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
 // quarter each own 32 of the 64 key columns of a block (and 32 of the 64 output columns); the row maximum and the
 // final row sum are exchanged through shared memory behind a 64-thread named barrier.  Two warps per scheduler hide
 // the MUFU / tcgen05.ld latencies that a single in-order warp exposes (round-1 profile: IPC 0.2 with SPLIT 1).
-template <int SPLIT>
+// F16 = 1: the operands are ONE fp16 plane each (Q, K, V from the QKV GEMM epilogue, P from the softmax) and every
+// product is a single MMA term.  The CPU study tools/attn_precision_study.py (CPU fp32 arithmetic, 10-step CFM) puts the mel
+// RMS of that format at 2e-5 against fp32 -- 50x inside the 1e-3 bar -- while it cuts the tensor work and the
+// shared-memory operand traffic of this kernel by 3x.  F16 = 0 (default until measured on the GPU): bf16 hi/lo planes,
+// three terms.
+template <int SPLIT, int F16>
 __global__ void __launch_bounds__(64 + 128 * SPLIT, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const AttnTcDev p) {
   constexpr int NSW = 4 * SPLIT;            // softmax warps
   constexpr int NC = 64 / SPLIT;            // key columns (and output columns) per softmax thread
+  constexpr int NPL = F16 ? 1 : 2;          // planes per operand
+  constexpr int STAGES = F16 ? AT_STAGES_F16 : AT_STAGES;
+  constexpr int Q_BYTES = NPL * 2 * AT_TILE, KV_STAGE = NPL * 2 * AT_TILE, P_BYTES = NPL * 2 * AT_TILE;
   const int seq = blockIdx.z, head = blockIdx.y;
   const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
   const int q0 = blockIdx.x * AT_BM;
@@ -73,14 +94,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   // keep the __shared__ address space (LDS/STS instead of generic LD/ST): offset the shared pointer, do not round-trip through an integer
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                                   // [hi: 128 rows][lo: 128 rows]
-  uint8_t* sKV = sQ + AT_Q_BYTES;                       // stages of [Khi][Klo][Vhi][Vlo]
-  uint8_t* sP = sKV + AT_STAGES * AT_KV_STAGE;          // [hi: 128 rows][lo: 128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
+  uint8_t* sQ = smem;                                   // [hi: 128 rows][lo: 128 rows]   (F16: one plane)
+  uint8_t* sKV = sQ + Q_BYTES;                          // stages of [Khi][Klo][Vhi][Vlo] (F16: [K][V])
+  uint8_t* sP = sKV + STAGES * KV_STAGE;                // [hi: 128 rows][lo: 128 rows]   (F16: one plane)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
   uint64_t* q_full = bars;                  // 1
   uint64_t* kv_full = bars + 1;             // [STAGES]
-  uint64_t* kv_empty = kv_full + AT_STAGES; // [STAGES]
-  uint64_t* s_full = kv_empty + AT_STAGES;  // [2]
+  uint64_t* kv_empty = kv_full + STAGES;    // [STAGES]
+  uint64_t* s_full = kv_empty + STAGES;     // [2]
   uint64_t* s_empty = s_full + 2;           // [2]
   uint64_t* p_full = s_empty + 2;           // 1
   uint64_t* pv_full = p_full + 1;           // 1
@@ -91,7 +112,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NSW); }
     mbar_init(p_full, NSW); mbar_init(pv_full, 1); mbar_init(pv_empty, NSW);
     fence_mbar_init();
@@ -107,65 +128,80 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer ===============================================================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
       const int qc = p.q_col + head * 64;
       tma_load_2d(sQ, &tm_hi, q_full, qc, qrow0);
       tma_load_2d(sQ + AT_TILE, &tm_hi, q_full, qc, qrow0 + 64);
-      tma_load_2d(sQ + 2 * AT_TILE, &tm_lo, q_full, qc, qrow0);
-      tma_load_2d(sQ + 3 * AT_TILE, &tm_lo, q_full, qc, qrow0 + 64);
+      if (!F16) {
+        tma_load_2d(sQ + 2 * AT_TILE, &tm_lo, q_full, qc, qrow0);
+        tma_load_2d(sQ + 3 * AT_TILE, &tm_lo, q_full, qc, qrow0 + 64);
+      }
       const int kc = p.k_col + head * 64, vc = p.v_col + head * 64;
       for (int j = 0; j < nblk; ++j) {
-        const int s = j % AT_STAGES;
-        mbar_wait(&kv_empty[s], ((j / AT_STAGES) & 1) ^ 1);
-        uint8_t* st = sKV + s * AT_KV_STAGE;
-        mbar_arrive_expect_tx(&kv_full[s], AT_KV_STAGE);
+        const int s = j % STAGES;
+        mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
+        uint8_t* st = sKV + s * KV_STAGE;
+        mbar_arrive_expect_tx(&kv_full[s], KV_STAGE);
         const int r = krow0 + j * AT_BN;
-        tma_load_2d(st, &tm_hi, &kv_full[s], kc, r);
-        tma_load_2d(st + AT_TILE, &tm_lo, &kv_full[s], kc, r);
-        tma_load_2d(st + 2 * AT_TILE, &tm_hi, &kv_full[s], vc, r);
-        tma_load_2d(st + 3 * AT_TILE, &tm_lo, &kv_full[s], vc, r);
+        if (F16) {
+          tma_load_2d(st, &tm_hi, &kv_full[s], kc, r);
+          tma_load_2d(st + AT_TILE, &tm_hi, &kv_full[s], vc, r);
+        } else {
+          tma_load_2d(st, &tm_hi, &kv_full[s], kc, r);
+          tma_load_2d(st + AT_TILE, &tm_lo, &kv_full[s], kc, r);
+          tma_load_2d(st + 2 * AT_TILE, &tm_hi, &kv_full[s], vc, r);
+          tma_load_2d(st + 3 * AT_TILE, &tm_lo, &kv_full[s], vc, r);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =================================================================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN);                 // A K-major, B K-major
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BM, 64) | (1u << 16);      // B (= V) MN-major
+      constexpr uint32_t idesc_s = F16 ? umma_idesc_f16(AT_BM, AT_BN) : umma_idesc_bf16(AT_BM, AT_BN);   // A, B K-major
+      constexpr uint32_t idesc_pv = (F16 ? umma_idesc_f16(AT_BM, 64) : umma_idesc_bf16(AT_BM, 64)) | (1u << 16);   // B (= V) MN-major
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 2 * AT_TILE;
       const uint32_t p_hi = smem_u32(sP), p_lo = p_hi + 2 * AT_TILE;
       mbar_wait(q_full, 0);
       auto issue_s = [&](int j) {
-        const int s = j % AT_STAGES;
-        mbar_wait(&kv_full[s], (j / AT_STAGES) & 1);
+        const int s = j % STAGES;
+        mbar_wait(&kv_full[s], (j / STAGES) & 1);
         mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t k_hi = smem_u32(sKV + s * AT_KV_STAGE), k_lo = k_hi + AT_TILE;
+        const uint32_t k_hi = smem_u32(sKV + s * KV_STAGE), k_lo = k_hi + AT_TILE;
         const uint32_t d = (j & 1) ? tS1 : tS0;
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const uint64_t dkh = umma_desc_sw128(k_hi + k4 * 32), dkl = umma_desc_sw128(k_lo + k4 * 32);
           const uint64_t dqh = umma_desc_sw128(q_hi + k4 * 32), dql = umma_desc_sw128(q_lo + k4 * 32);
-          umma_bf16(d, dql, dkh, idesc_s, k4 != 0 ? 1u : 0u);
-          umma_bf16(d, dqh, dkl, idesc_s, 1u);
-          umma_bf16(d, dqh, dkh, idesc_s, 1u);
+          if (F16) {
+            umma_bf16(d, dqh, dkh, idesc_s, k4 != 0 ? 1u : 0u);     // kind::f16 covers fp16 and bf16 operands alike
+          } else {
+            umma_bf16(d, dql, dkh, idesc_s, k4 != 0 ? 1u : 0u);
+            umma_bf16(d, dqh, dkl, idesc_s, 1u);
+            umma_bf16(d, dqh, dkh, idesc_s, 1u);
+          }
         }
         umma_commit(&s_full[j & 1]);
       };
       issue_s(0);
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) issue_s(j + 1);            // S of the next block overlaps the softmax of this one
-        const int s = j % AT_STAGES;
+        const int s = j % STAGES;
         mbar_wait(p_full, j & 1);                    // P_j is in smem
         mbar_wait(pv_empty, (j & 1) ^ 1);            // PV accumulator of block j-1 has been read
         tcgen05_fence_after();
-        const uint32_t v_hi = smem_u32(sKV + s * AT_KV_STAGE + 2 * AT_TILE), v_lo = v_hi + AT_TILE;
+        const uint32_t v_hi = smem_u32(sKV + s * KV_STAGE + NPL * AT_TILE), v_lo = v_hi + AT_TILE;
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {             // 16 keys per step: 32 B along P rows, 2048 B along V rows
           const uint64_t dvh = umma_desc_sw128_mn(v_hi + k4 * 2048), dvl = umma_desc_sw128_mn(v_lo + k4 * 2048);
           const uint64_t dph = umma_desc_sw128(p_hi + k4 * 32), dpl = umma_desc_sw128(p_lo + k4 * 32);
-          umma_bf16(tPV, dpl, dvh, idesc_pv, k4 != 0 ? 1u : 0u);
-          umma_bf16(tPV, dph, dvl, idesc_pv, 1u);
-          umma_bf16(tPV, dph, dvh, idesc_pv, 1u);
+          if (F16) {
+            umma_bf16(tPV, dph, dvh, idesc_pv, k4 != 0 ? 1u : 0u);
+          } else {
+            umma_bf16(tPV, dpl, dvh, idesc_pv, k4 != 0 ? 1u : 0u);
+            umma_bf16(tPV, dph, dvl, idesc_pv, 1u);
+            umma_bf16(tPV, dph, dvh, idesc_pv, 1u);
+          }
         }
         umma_commit(pv_full);                        // PV_j ready, P smem free
         umma_commit(&kv_empty[s]);                   // K/V stage free
@@ -252,12 +288,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       for (int cq = 0; cq < NC / 8; ++cq) {
         uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          split_pair_at(__uint_as_float(r[cq * 8 + e * 2]), __uint_as_float(r[cq * 8 + e * 2 + 1]), hi[e], lo[e]);
+        for (int e = 0; e < 4; ++e) {
+          if (F16) hi[e] = pack_half2(__uint_as_float(r[cq * 8 + e * 2]), __uint_as_float(r[cq * 8 + e * 2 + 1]));
+          else split_pair_at(__uint_as_float(r[cq * 8 + e * 2]), __uint_as_float(r[cq * 8 + e * 2 + 1]), hi[e], lo[e]);
+        }
         const int ch = half * (NC / 8) + cq;
         const uint32_t off = ((uint32_t)(ch ^ (row & 7))) << 4;
         *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(prow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (!F16) *reinterpret_cast<uint4*>(prow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -316,8 +354,10 @@ void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
   if (ctx.dry) return;
   static bool attr = false;
   if (!attr) {
-    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_F16));
+    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_F16));
     attr = true;
   }
   AttnTcDev p;
@@ -331,8 +371,13 @@ void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
   ctx.launches++;
   if (ctx.timer) ctx.timer->begin(K_FLASH, ctx.stream);
   dim3 grid((a.max_q_len + AT_BM - 1) / AT_BM, a.n_heads, a.n_seq);
-  if (variant == 1) attn_tc_kernel<1><<<grid, 192, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
-  else attn_tc_kernel<2><<<grid, 320, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
+  if (a.f16) {       // single fp16 plane per operand (a.tm_hi maps it; a.tm_lo is not read)
+    if (variant == 1) attn_tc_kernel<1, 1><<<grid, 192, AT_SMEM_F16, ctx.stream>>>(*a.tm_hi, *a.tm_hi, p);
+    else attn_tc_kernel<2, 1><<<grid, 320, AT_SMEM_F16, ctx.stream>>>(*a.tm_hi, *a.tm_hi, p);
+  } else {
+    if (variant == 1) attn_tc_kernel<1, 0><<<grid, 192, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
+    else attn_tc_kernel<2, 0><<<grid, 320, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
+  }
   if (ctx.timer) ctx.timer->end(K_FLASH, ctx.stream);
   CBX_CHECK(cudaGetLastError());
 }

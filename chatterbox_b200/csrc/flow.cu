@@ -247,7 +247,7 @@ void flow_encode(cbx_handle* h, Ctx& ctx, const int* tokens, const cbx_layout& L
 }
 
 // ---- CFM estimator ---------------------------------------------------------------------------------
-struct EstBufs { float *h1, *h2, *hn, *qkv, *att, *ff; __nv_bfloat16 *qkv_hi, *qkv_lo; CUtensorMap tm_hi, tm_lo; bool tc; };
+struct EstBufs { float *h1, *h2, *hn, *qkv, *att, *ff; __nv_bfloat16 *qkv_hi, *qkv_lo; CUtensorMap tm_hi, tm_lo; bool tc; bool f16; };
 
 static void cfm_resnet(Ctx& ctx, CfmResnet& r, const float* in, int lda, int cin, float* out, int ldo, const float* tvec,
                        const cbx_layout& L, EstBufs& b) {
@@ -274,10 +274,11 @@ static void cfm_tfmr(Ctx& ctx, CfmTfmr& t, float* x, int ldx, const cbx_layout& 
     GemmDev gq = gemm_args_linear(nullptr, 256, rows, t.qkv, nullptr, 0);
     gq.Ahi = hn_hi; gq.Alo = hn_lo; gq.ldab = 256;
     gq.Chi = b.qkv_hi; gq.Clo = b.qkv_lo; gq.ldcb = 1536;
+    gq.c_half = b.f16 ? 1 : 0;        // one fp16 plane at qkv_hi (tm_hi maps the same bytes: 2-byte elements, 1536 per row)
     gemm(ctx, gq, t.qkv);
     AttnTcArgs a;
     a.tm_hi = &b.tm_hi; a.tm_lo = &b.tm_lo; a.q_col = 0; a.k_col = 512; a.v_col = 1024; a.O = nullptr; a.ldo = 512;
-    a.Ohi = at_hi; a.Olo = at_lo;
+    a.Ohi = at_hi; a.Olo = at_lo; a.f16 = b.f16 ? 1 : 0;
     a.n_seq = L.n_seq; a.n_heads = 8; a.q_start = L.start; a.q_len = L.len; a.kv_start = L.start; a.kv_len = L.len;
     a.max_q_len = L.max_len; a.scale = 0.125f;
     attention_tc(ctx, a);
@@ -383,6 +384,7 @@ void cfm_solve(cbx_handle* h, Ctx& ctx, const float* mu, const float* spk, const
   b.hn = ctx.ws.get<float>((size_t)rows3 * 256); b.qkv = ctx.ws.get<float>((size_t)rows3 * 1536);
   b.att = ctx.ws.get<float>((size_t)rows3 * 512); b.ff = ctx.ws.get<float>((size_t)rows3 * 1024);
   b.tc = (ctx.attn_impl == 0 && ctx.gemm_impl == 0);
+  b.f16 = b.tc && ctx.attn_f16 != 0;
   b.qkv_hi = reinterpret_cast<__nv_bfloat16*>(b.qkv);                 // the planes reuse the fp32 qkv buffer
   b.qkv_lo = b.qkv_hi + (size_t)rows3 * 1536;
   if (b.tc && !ctx.dry) { make_plane_tmap(&b.tm_hi, b.qkv_hi, rows3, 1536); make_plane_tmap(&b.tm_lo, b.qkv_lo, rows3, 1536); }

@@ -386,6 +386,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
             for (int u = 0; u < 8; ++u) {
               float v = (xv[u] * a_mul + a_add) * g.out_scale;
               if (!((vmask >> (r0 + u)) & 1u)) v = 0.f;
+              if (g.c_half) {          // one fp16 plane
+                if (colok && (r0 + u) < rows_here) reinterpret_cast<__half*>(hb)[(long)(r0 + u) * g.ldcb] = __float2half_rn(v);
+                continue;
+              }
               __nv_bfloat16 h, l;
               split_bf16(v, h, l);
               if (colok && (r0 + u) < rows_here) { hb[(long)(r0 + u) * g.ldcb] = h; lb[(long)(r0 + u) * g.ldcb] = l; }
@@ -782,6 +786,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
   CBX_REQUIRE(g.Kpad % 64 == 0 && g.Npad % 64 == 0, "padded weight dims");
   if (g.a_mode == A_TAPS) CBX_REQUIRE(g.ctap % 64 == 0, "TAPS mode needs 64-channel chunks");
   if (ctx.dry) return;
+  CBX_REQUIRE(!g.c_half || (ctx.gemm_impl == 0 && g.Chi && !g.C && !g.C2 && !g.res && g.M > 8), "fp16 plane output needs the tcgen05 planes-only epilogue");
   ctx.launches++;
   if (ctx.gemm_impl == 1) {
     dim3 grid((g.M + 63) / 64, (g.Npad + 63) / 64);

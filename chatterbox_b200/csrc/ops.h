@@ -63,6 +63,9 @@ struct GemmDev {
   // A operand already split into bf16 hi/lo planes [M][ldab] by the producing kernel (Linear only): both planes are
   // fetched by TMA straight into the UMMA layout and the converter warps have nothing to do in the main loop
   const __nv_bfloat16* Ahi; const __nv_bfloat16* Alo; int ldab;
+  // Chi-only epilogue: store ONE fp16 value per element into Chi (reinterpreted as __half[M][ldcb]) instead of the bf16
+  // hi/lo pair (operand format of the single-term tcgen05 attention)
+  int c_half;
 };
 
 struct Arena {  // bump allocator over caller-owned workspace; dry=true only counts
@@ -117,6 +120,7 @@ struct Ctx {
   bool dry = false;       // size-only pass: no launches
   int gemm_impl = 0;      // 0 = tcgen05 (default), 1 = SIMT reference tiles (debug, env CBX_GEMM=simt)
   int attn_impl = 0;      // 0 = tensor-core flash (default), 1 = SIMT reference (debug, env CBX_ATTN=simt)
+  int attn_f16 = 0;       // CFM attention operands: 0 = bf16 hi/lo planes, 3 MMA terms (default), 1 = one fp16 plane, 1 term
   long launches = 0;      // kernels launched through this context
 };
 
@@ -155,6 +159,7 @@ struct AttnTcArgs {
   int q_col, k_col, v_col;                    // column of head 0 of Q / K / V inside the planes
   float* O; int ldo;
   __nv_bfloat16* Ohi = nullptr; __nv_bfloat16* Olo = nullptr;   // optional: write the output as bf16 planes [rows][ldo]
+  int f16 = 0;              // 1: Q/K/V are ONE fp16 plane (tm_hi maps it), single-term products (see attn_tc.cu)
   int n_seq, n_heads;
   const int* q_start; const int* q_len; const int* kv_start; const int* kv_len;
   int max_q_len; float scale;

@@ -152,6 +152,12 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_attention_precision(self, fmt="bf16x3"):
+        """Operand format of the CFM (flow) attention: 'bf16x3' = bf16 hi/lo planes, three MMA terms (default, fp32-faithful);
+        'fp16' = one fp16 plane per operand, one term (tools/attn_precision_study.py: mel RMS 2e-5 vs the 1e-3 bar)."""
+        assert fmt in ("bf16x3", "fp16")
+        self.h.set_option("attn_prec", fmt)
+
     def set_decode_graph(self, on=True):
         """Launch-bound small batches: steps 2..n of every cbx_t3_decode call replay a CUDA graph captured from step 1
         (stream capture needs a non-default stream, so decode then runs on a side stream)."""
