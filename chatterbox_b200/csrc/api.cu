@@ -28,7 +28,7 @@ static Ctx make_ctx(cbx_handle* h, void* ws, size_t ws_bytes, cbx_stream stream,
   Ctx c;
   c.stream = reinterpret_cast<cudaStream_t>(stream);
   c.ws.base = static_cast<char*>(ws); c.ws.cap = ws_bytes; c.ws.dry = dry; c.dry = dry;
-  c.gemm_impl = h->gemm_impl; c.attn_impl = h->attn_impl; c.attn_f16 = h->attn_f16;
+  c.gemm_impl = h->gemm_impl; c.attn_impl = h->attn_impl; c.attn_f16 = h->attn_f16; c.cfm_act_f16 = h->cfm_act_f16;
   c.timer = (h->timer.cls != K_NONE && !dry) ? &h->timer : nullptr;
   return c;
 }
@@ -87,6 +87,7 @@ int cbx_set_option(cbx_handle* h, const char* key, const char* value) {
   else if (k == "attn") h->attn_impl = (v == "simt") ? 1 : 0;
   else if (k == "decode_graph") h->decode_graph = (v == "1" || v == "on") ? 1 : 0;
   else if (k == "attn_prec") h->attn_f16 = (v == "fp16") ? 1 : 0;     // CFM attention operand format (default bf16x3)
+  else if (k == "cfm_act") h->cfm_act_f16 = (v == "fp16") ? 1 : 0;   // CFM transformer-block GEMM inputs (default bf16x2)
   else if (k == "time_kernel") {
     h->timer.drain(); h->timer.ms = 0.0; h->timer.n = 0; h->timer.work = 0.0; h->timer.bytes = 0.0;
     h->timer.cls = v == "gemm_tc" ? K_GEMM_TC : v == "gemv" ? K_GEMV : v == "flash" ? K_FLASH : v == "paged" ? K_PAGED : K_NONE;

@@ -29,6 +29,7 @@ struct AttnTcDev {
   const int* q_start; const int* q_len; const int* kv_start; const int* kv_len;
   float scale_log2e;      // softmax scale * log2(e)
   int q_col, k_col, v_col;   // column offsets of head 0 inside the packed planes
+  __half* O16;               // F16 variant only: when set, O is written as one fp16 plane [rows][ldo]
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {      // ex2.approx: 2 ulp, -inf -> 0
@@ -314,7 +315,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     if (q0 + row < qlen) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
       const long off = (long)(qrow0 + row) * p.ldo + head * 64 + col0;
-      if (p.Ohi) {
+      if (F16 && p.O16) {              // (the fp16 output plane only exists together with the fp16 operand format)
+        uint4* d16 = reinterpret_cast<uint4*>(p.O16 + off);
+#pragma unroll
+        for (int i = 0; i < NC; i += 8)
+          d16[i / 8] = make_uint4(pack_half2(o[i] * inv, o[i + 1] * inv), pack_half2(o[i + 2] * inv, o[i + 3] * inv),
+                                  pack_half2(o[i + 4] * inv, o[i + 5] * inv), pack_half2(o[i + 6] * inv, o[i + 7] * inv));
+      } else if (p.Ohi) {
         uint4* dh = reinterpret_cast<uint4*>(p.Ohi + off);
         uint4* dl = reinterpret_cast<uint4*>(p.Olo + off);
 #pragma unroll
@@ -332,6 +339,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         for (int i = 0; i < NC; i += 4)
           *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
       }
+    } else if (F16 && p.O16) {
+      uint4* d16 = reinterpret_cast<uint4*>(p.O16 + (long)(qrow0 + row) * p.ldo + head * 64 + col0);
+#pragma unroll
+      for (int i = 0; i < NC / 8; ++i) d16[i] = make_uint4(0, 0, 0, 0);       // finite padding rows, see below
     } else if (p.Ohi) {
       // Padding rows of the sequence's last 128-row tile (packed layouts start every sequence on a tile boundary): keep
       // them finite.  They flow through the out GEMM into x, come back as K/V padding rows of the next block, and a NaN
@@ -361,7 +372,7 @@ void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
     attr = true;
   }
   AttnTcDev p;
-  p.O = a.O; p.ldo = a.ldo; p.Ohi = a.Ohi; p.Olo = a.Olo; p.q_start = a.q_start; p.q_len = a.q_len; p.kv_start = a.kv_start; p.kv_len = a.kv_len;
+  p.O = a.O; p.ldo = a.ldo; p.Ohi = a.Ohi; p.Olo = a.Olo; p.O16 = a.O16; p.q_start = a.q_start; p.q_len = a.q_len; p.kv_start = a.kv_start; p.kv_len = a.kv_len;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.q_col = a.q_col; p.k_col = a.k_col; p.v_col = a.v_col;
   // CBX_ATTN_TC=2 selects two softmax threads per query row.  Measured on B200 (B=32 flow stage): 1170 ms vs 1123 ms

@@ -65,7 +65,7 @@ void rmsnorm(Ctx& ctx, const float* x, int ldx, const float* w, float* y, int ld
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx, const float* w, const float* b, float* y,
                                                         int ldy, int rows, int dim, float eps, int act, float out_scale,
                                                         const float* seq_add, int seq_add_ld, int has_seq, SeqMap seq,
-                                                        __nv_bfloat16* yhi, __nv_bfloat16* ylo) {
+                                                        __nv_bfloat16* yhi, __nv_bfloat16* ylo, __half* y16) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -77,9 +77,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx,
   float* yr = y + (long)r * ldy;
   __nv_bfloat16* hr = yhi ? yhi + (long)r * ldy : nullptr;
   __nv_bfloat16* lr = yhi ? ylo + (long)r * ldy : nullptr;
+  __half* r16 = y16 ? y16 + (long)r * ldy : nullptr;
   if (!valid) {
     for (int i = lane; i < dim; i += 32) {
-      if (yhi) { hr[i] = __float2bfloat16(0.f); lr[i] = __float2bfloat16(0.f); } else yr[i] = 0.f;
+      if (r16) r16[i] = __float2half_rn(0.f);
+      else if (yhi) { hr[i] = __float2bfloat16(0.f); lr[i] = __float2bfloat16(0.f); } else yr[i] = 0.f;
     }
     return;
   }
@@ -95,17 +97,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx,
     v = act_apply(act, v, 0.f);
     if (seq_add) v += seq_add[(long)s * seq_add_ld + i];
     v *= out_scale;
-    if (yhi) { __nv_bfloat16 h, l; split_bf16(v, h, l); hr[i] = h; lr[i] = l; } else yr[i] = v;
+    if (r16) r16[i] = __float2half_rn(v);
+    else if (yhi) { __nv_bfloat16 h, l; split_bf16(v, h, l); hr[i] = h; lr[i] = l; } else yr[i] = v;
   }
 }
 void layernorm(Ctx& ctx, const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int dim,
                float eps, int act, float out_scale, const float* seq_add, int seq_add_ld, const SeqMap* seq,
-               __nv_bfloat16* yhi, __nv_bfloat16* ylo) {
+               __nv_bfloat16* yhi, __nv_bfloat16* ylo, __half* y16) {
   if (ctx.dry || rows == 0) return;
   ctx.launches++;
   SeqMap sm; if (seq) sm = *seq;
   layernorm_kernel<<<(rows + 7) / 8, 256, 0, ctx.stream>>>(x, ldx, w, b, y, ldy, rows, dim, eps, act, out_scale, seq_add,
-                                                          seq_add_ld, seq ? 1 : 0, sm, yhi, ylo);
+                                                          seq_add_ld, seq ? 1 : 0, sm, yhi, ylo, y16);
   CBX_CHECK(cudaGetLastError());
 }
 

@@ -70,7 +70,7 @@ struct cbx_handle {
   cbx::T3Model t3;
   cbx::FlowModel flow;
   cbx::HiftModel hift;
-  int gemm_impl = 0, attn_impl = 0, attn_f16 = 0;
+  int gemm_impl = 0, attn_impl = 0, attn_f16 = 0, cfm_act_f16 = 0;
   long long launches = 0;
   cbx::KTimer timer;
   // "decode_graph" option: steps 2..n of a cbx_t3_decode call replay a CUDA graph captured from step 1 (launch-bound

@@ -247,7 +247,7 @@ void flow_encode(cbx_handle* h, Ctx& ctx, const int* tokens, const cbx_layout& L
 }
 
 // ---- CFM estimator ---------------------------------------------------------------------------------
-struct EstBufs { float *h1, *h2, *hn, *qkv, *att, *ff; __nv_bfloat16 *qkv_hi, *qkv_lo; CUtensorMap tm_hi, tm_lo; bool tc; bool f16; };
+struct EstBufs { float *h1, *h2, *hn, *qkv, *att, *ff; __nv_bfloat16 *qkv_hi, *qkv_lo; CUtensorMap tm_hi, tm_lo; bool tc; bool f16; bool a16; };
 
 static void cfm_resnet(Ctx& ctx, CfmResnet& r, const float* in, int lda, int cin, float* out, int ldo, const float* tvec,
                        const cbx_layout& L, EstBufs& b) {
@@ -270,30 +270,42 @@ static void cfm_tfmr(Ctx& ctx, CfmTfmr& t, float* x, int ldx, const cbx_layout& 
     __nv_bfloat16* hn_hi = reinterpret_cast<__nv_bfloat16*>(b.hn);  __nv_bfloat16* hn_lo = hn_hi + R * 256;
     __nv_bfloat16* at_hi = reinterpret_cast<__nv_bfloat16*>(b.att); __nv_bfloat16* at_lo = at_hi + R * 512;
     __nv_bfloat16* ff_hi = reinterpret_cast<__nv_bfloat16*>(b.ff);  __nv_bfloat16* ff_lo = ff_hi + R * 1024;
-    layernorm(ctx, x, ldx, t.ln1_w.p, t.ln1_b.p, nullptr, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr, hn_hi, hn_lo);
+    // b.a16 (opt-in, tools/attn_precision_study.py: all block GEMM inputs as ONE fp16 value keep the mel RMS at 1.4e-4):
+    // the same dataflow with one fp16 plane per activation -- half the activation bytes, one MMA term per K step.
+    __half* hn16 = reinterpret_cast<__half*>(b.hn);
+    __half* at16 = reinterpret_cast<__half*>(b.att);
+    __half* ff16 = reinterpret_cast<__half*>(b.ff);
+    auto feed = [&](GemmDev& g, __nv_bfloat16* hi, __nv_bfloat16* lo, __half* h16, int ld) {
+      if (b.a16) { g.A16 = h16; g.lda16 = ld; } else { g.Ahi = hi; g.Alo = lo; g.ldab = ld; }
+    };
+    if (b.a16) layernorm(ctx, x, ldx, t.ln1_w.p, t.ln1_b.p, nullptr, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr, nullptr, nullptr, hn16);
+    else layernorm(ctx, x, ldx, t.ln1_w.p, t.ln1_b.p, nullptr, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr, hn_hi, hn_lo);
     GemmDev gq = gemm_args_linear(nullptr, 256, rows, t.qkv, nullptr, 0);
-    gq.Ahi = hn_hi; gq.Alo = hn_lo; gq.ldab = 256;
+    feed(gq, hn_hi, hn_lo, hn16, 256);
     gq.Chi = b.qkv_hi; gq.Clo = b.qkv_lo; gq.ldcb = 1536;
     gq.c_half = b.f16 ? 1 : 0;        // one fp16 plane at qkv_hi (tm_hi maps the same bytes: 2-byte elements, 1536 per row)
     gemm(ctx, gq, t.qkv);
     AttnTcArgs a;
     a.tm_hi = &b.tm_hi; a.tm_lo = &b.tm_lo; a.q_col = 0; a.k_col = 512; a.v_col = 1024; a.O = nullptr; a.ldo = 512;
-    a.Ohi = at_hi; a.Olo = at_lo; a.f16 = b.f16 ? 1 : 0;
+    if (b.a16) a.O16 = at16; else { a.Ohi = at_hi; a.Olo = at_lo; }
+    a.f16 = b.f16 ? 1 : 0;
     a.n_seq = L.n_seq; a.n_heads = 8; a.q_start = L.start; a.q_len = L.len; a.kv_start = L.start; a.kv_len = L.len;
     a.max_q_len = L.max_len; a.scale = 0.125f;
     attention_tc(ctx, a);
     GemmDev go = gemm_args_linear(nullptr, 512, rows, t.out, x, ldx);
-    go.Ahi = at_hi; go.Alo = at_lo; go.ldab = 512;
+    feed(go, at_hi, at_lo, at16, 512);
     go.res = x; go.ldr = ldx;
     gemm(ctx, go, t.out);
-    layernorm(ctx, x, ldx, t.ln3_w.p, t.ln3_b.p, nullptr, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr, hn_hi, hn_lo);
+    if (b.a16) layernorm(ctx, x, ldx, t.ln3_w.p, t.ln3_b.p, nullptr, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr, nullptr, nullptr, hn16);
+    else layernorm(ctx, x, ldx, t.ln3_w.p, t.ln3_b.p, nullptr, 256, rows, 256, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr, hn_hi, hn_lo);
     GemmDev g1 = gemm_args_linear(nullptr, 256, rows, t.ff1, nullptr, 0);
-    g1.Ahi = hn_hi; g1.Alo = hn_lo; g1.ldab = 256;
+    feed(g1, hn_hi, hn_lo, hn16, 256);
     g1.Chi = ff_hi; g1.Clo = ff_lo; g1.ldcb = 1024;
+    g1.c_half = b.a16 ? 1 : 0;        // ff16 aliases ff_hi
     g1.act = ACT_GELU;
     gemm(ctx, g1, t.ff1);
     GemmDev g2 = gemm_args_linear(nullptr, 1024, rows, t.ff2, x, ldx);
-    g2.Ahi = ff_hi; g2.Alo = ff_lo; g2.ldab = 1024;
+    feed(g2, ff_hi, ff_lo, ff16, 1024);
     g2.res = x; g2.ldr = ldx;
     gemm(ctx, g2, t.ff2);
     return;
@@ -385,6 +397,7 @@ void cfm_solve(cbx_handle* h, Ctx& ctx, const float* mu, const float* spk, const
   b.att = ctx.ws.get<float>((size_t)rows3 * 512); b.ff = ctx.ws.get<float>((size_t)rows3 * 1024);
   b.tc = (ctx.attn_impl == 0 && ctx.gemm_impl == 0);
   b.f16 = b.tc && ctx.attn_f16 != 0;
+  b.a16 = b.f16 && ctx.cfm_act_f16 != 0;      // fp16 activations ride on the fp16 attention variant
   b.qkv_hi = reinterpret_cast<__nv_bfloat16*>(b.qkv);                 // the planes reuse the fp32 qkv buffer
   b.qkv_lo = b.qkv_hi + (size_t)rows3 * 1536;
   if (b.tc && !ctx.dry) { make_plane_tmap(&b.tm_hi, b.qkv_hi, rows3, 1536); make_plane_tmap(&b.tm_lo, b.qkv_lo, rows3, 1536); }

@@ -169,8 +169,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     const int t = threadIdx.x;            // 0..255
     const int c4 = t & 15;                // float4 chunk inside the 64-wide K block
     const int rsub = t >> 4;              // 0..15
-    if (g.a_tma == 2) {
-      // A arrives as bf16 planes by TMA: nothing to convert, go wait for the accumulator
+    if (g.a_tma >= 2) {
+      // A arrives as bf16 planes (2) or one fp16 plane (3) by TMA: nothing to convert, go wait for the accumulator
     } else if (g.a_tma) {
       // ===================== converters: smem fp32 tile -> bf16 hi/lo planes, in place ===================
       // software pipelined: the LDS of K block kb+1 are in flight while block kb is converted and stored.
@@ -442,9 +442,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
-        mbar_arrive_expect_tx(&tma_full[s], g.a_tma ? (Cfg::A_BYTES + Cfg::W_BYTES) : Cfg::W_BYTES);
+        mbar_arrive_expect_tx(&tma_full[s], g.a_tma == 3 ? (16384 + Cfg::W_BYTES) : g.a_tma ? (Cfg::A_BYTES + Cfg::W_BYTES) : Cfg::W_BYTES);
         tma_load_2d(a_st + Cfg::A_BYTES, &tmapW, &tma_full[s], kb * TC_BK, n0);
-        if (g.a_tma == 2) {
+        if (g.a_tma == 3) {
+          tma_load_2d(a_st, &tmapA, &tma_full[s], kb * TC_BK, m0);             // the fp16 plane
+        } else if (g.a_tma == 2) {
           tma_load_2d(a_st, &tmapA, &tma_full[s], kb * TC_BK, m0);             // hi plane, SWIZZLE_128B
           tma_load_2d(a_st + 16384, &tmapA2, &tma_full[s], kb * TC_BK, m0);    // lo plane
         } else if (g.a_tma) {
@@ -458,11 +460,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     // ===================== MMA issuer (one elected thread) ============================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      constexpr uint32_t idesc_a16 = idesc & ~(7u << 7);     // a_format = F16 (0), b_format stays BF16: A fp16 x W bf16
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&tma_full[s], ph);      // W tile landed (and A planes in plane mode)
-        if (g.a_tma != 2) mbar_wait(&conv_full[s], ph);     // bf16 planes of A written by the converters
+        if (g.a_tma < 2) mbar_wait(&conv_full[s], ph);      // bf16 planes of A written by the converters
         tcgen05_fence_after();
         if (dbg && kb < 8) g.dbg[32 + kb] = clock64();
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
@@ -471,6 +474,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
 #pragma unroll
         for (int k4 = 0; k4 < TC_BK / 16; ++k4) {   // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
           const uint64_t db = umma_desc_sw128(wb + k4 * 32);
+          if (g.a_tma == 3) {     // one fp16 plane: a single term
+            umma_bf16(tmem_base, umma_desc_sw128(a_hi + k4 * 32), db, idesc_a16, (kb | k4) != 0 ? 1u : 0u);
+            continue;
+          }
           // small plane first so the fp32 accumulator adds the correction before the leading term
           umma_bf16(tmem_base, umma_desc_sw128(a_lo + k4 * 32), db, idesc, (kb | k4) != 0 ? 1u : 0u);
           umma_bf16(tmem_base, umma_desc_sw128(a_hi + k4 * 32), db, idesc, 1u);
@@ -743,7 +750,12 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
   g.a_tma = (g.a_mode == A_TAPS && g.stride == 1 && (g.lda % 4) == 0 && (g.c_in % 4) == 0 &&
              (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && g.M_in > 0) ? 1 : 0;
   CUtensorMap tmA, tmA2;
-  if (g.Ahi) {
+  if (g.A16) {
+    CBX_REQUIRE(g.ntaps == 1 && !g.has_seq && (g.lda16 % 8) == 0, "fp16 plane operand needs a plain Linear");
+    g.a_tma = 3;
+    make_plane_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(g.A16), g.M, g.k_total, 128, g.lda16);   // 2-byte elements
+    tmA2 = tmA;
+  } else if (g.Ahi) {
     CBX_REQUIRE(g.ntaps == 1 && !g.has_seq && g.Alo && (g.ldab % 8) == 0, "plane operand needs a plain Linear");
     g.a_tma = 2;
     make_plane_tmap(&tmA, g.Ahi, g.M, g.k_total, 128, g.ldab);
@@ -758,10 +770,10 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
     // algorithmic HBM bytes: weights once (bf16), the activation matrix once (fp32 or hi+lo planes = 4 B per element),
     // every output element once per destination, the residual once
     const double a_rows = (g.a_mode == A_TAPS && g.ntaps > 1) ? (double)g.M_in : (double)g.M * g.stride;
-    double b = (double)g.Npad * g.Kpad * 2.0 + a_rows * (double)g.c_in * 4.0;
+    double b = (double)g.Npad * g.Kpad * 2.0 + a_rows * (double)g.c_in * (g.A16 ? 2.0 : 4.0);
     const double out_elems = (double)g.M * (double)(g.swiglu ? g.n_out / 2 : g.n_out);
     if (g.C) b += out_elems * 4.0;
-    if (g.Chi) b += out_elems * 4.0;
+    if (g.Chi) b += out_elems * (g.c_half ? 2.0 : 4.0);
     if (g.C2) b += out_elems * 4.0;
     if (g.res) b += out_elems * 4.0;
     if (g.accumulate) b += out_elems * 4.0;
@@ -793,7 +805,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     gemm_simt_kernel<<<grid, 256, 0, ctx.stream>>>(g);
   } else {
     const bool plain = !g.has_seq && g.a_mode == A_TAPS && g.ntaps == 1 && g.stride == 1 && g.pad == 0 &&
-                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.Chi && !g.Ahi &&
+                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.Chi && !g.Ahi && !g.A16 &&
                        ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
     if (plain && g.M <= 8) {
       if (g.M <= 2) launch_gemv<2>(ctx, g);

@@ -66,6 +66,9 @@ struct GemmDev {
   // Chi-only epilogue: store ONE fp16 value per element into Chi (reinterpreted as __half[M][ldcb]) instead of the bf16
   // hi/lo pair (operand format of the single-term tcgen05 attention)
   int c_half;
+  // A operand as ONE fp16 plane [M][lda16] written by the producer (plain Linear): a single TMA box per K block and a
+  // single MMA term (A fp16 x W bf16).  Only where the precision study allows it (CFM transformer blocks).
+  const __half* A16; int lda16;
 };
 
 struct Arena {  // bump allocator over caller-owned workspace; dry=true only counts
@@ -121,6 +124,7 @@ struct Ctx {
   int gemm_impl = 0;      // 0 = tcgen05 (default), 1 = SIMT reference tiles (debug, env CBX_GEMM=simt)
   int attn_impl = 0;      // 0 = tensor-core flash (default), 1 = SIMT reference (debug, env CBX_ATTN=simt)
   int attn_f16 = 0;       // CFM attention operands: 0 = bf16 hi/lo planes, 3 MMA terms (default), 1 = one fp16 plane, 1 term
+  int cfm_act_f16 = 0;    // CFM transformer-block GEMM inputs: 0 = bf16 hi/lo planes, 2 terms (default), 1 = one fp16 plane
   long launches = 0;      // kernels launched through this context
 };
 
@@ -160,6 +164,7 @@ struct AttnTcArgs {
   float* O; int ldo;
   __nv_bfloat16* Ohi = nullptr; __nv_bfloat16* Olo = nullptr;   // optional: write the output as bf16 planes [rows][ldo]
   int f16 = 0;              // 1: Q/K/V are ONE fp16 plane (tm_hi maps it), single-term products (see attn_tc.cu)
+  __half* O16 = nullptr;    // optional: write the output as one fp16 plane [rows][ldo]
   int n_seq, n_heads;
   const int* q_start; const int* q_len; const int* kv_start; const int* kv_len;
   int max_q_len; float scale;
@@ -190,7 +195,8 @@ void rmsnorm(Ctx& ctx, const float* x, int ldx, const float* w, float* y, int ld
              __nv_bfloat16* yhi = nullptr, __nv_bfloat16* ylo = nullptr);   // yhi/ylo: bf16 planes [rows][ldy] instead of y
 void layernorm(Ctx& ctx, const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int dim,
                float eps, int act, float out_scale, const float* seq_add, int seq_add_ld, const SeqMap* seq,
-               __nv_bfloat16* yhi = nullptr, __nv_bfloat16* ylo = nullptr);   // yhi/ylo: bf16 planes instead of fp32 y
+               __nv_bfloat16* yhi = nullptr, __nv_bfloat16* ylo = nullptr,    // yhi/ylo: bf16 planes instead of fp32 y
+               __half* y16 = nullptr);                                        // y16: one fp16 plane instead
 void fill(Ctx& ctx, float* p, long n, float v);
 
 }  // namespace cbx

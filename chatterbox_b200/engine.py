@@ -158,6 +158,13 @@ class Engine:
         assert fmt in ("bf16x3", "fp16")
         self.h.set_option("attn_prec", fmt)
 
+    def set_cfm_activation_precision(self, fmt="bf16x2"):
+        """Operand format of the CFM transformer-block GEMM inputs (LayerNorm outputs, attention output, GELU output):
+        'bf16x2' = bf16 hi/lo planes, two MMA terms (default); 'fp16' = one fp16 plane, one term (study: mel RMS 1.4e-4
+        with fp16 attention as well).  The residual stream stays fp32 either way."""
+        assert fmt in ("bf16x2", "fp16")
+        self.h.set_option("cfm_act", fmt)
+
     def set_decode_graph(self, on=True):
         """Launch-bound small batches: steps 2..n of every cbx_t3_decode call replay a CUDA graph captured from step 1
         (stream capture needs a non-default stream, so decode then runs on a side stream)."""
