@@ -72,10 +72,31 @@ void cbx_destroy(cbx_handle* h) {
   cudaSetDevice(h->device);
   for (void* p : h->owned) cudaFree(p);
   if (h->decode_exec) cudaGraphExecDestroy(h->decode_exec);
-  auto fw = [](Weight& w) { free_weight(w); };
+  for (cudaEvent_t e : h->timer.ev) cudaEventDestroy(e);
+  auto fw = [](Weight& w) { free_weight(w); };      // no-op for weights that were never packed
   for (auto& l : h->t3.layers) { fw(l.qkv); fw(l.o); fw(l.gu); fw(l.down); }
   fw(h->t3.head); fw(h->t3.spkr); fw(h->t3.pq); fw(h->t3.pk); fw(h->t3.pv); fw(h->t3.pproj);
-  delete h;   // remaining packed weights are released with the context (process lifetime objects)
+  FlowModel& f = h->flow;
+  fw(f.spk_affine); fw(f.enc_proj); fw(f.embed.lin); fw(f.up_embed.lin); fw(f.pre_conv1); fw(f.pre_conv2); fw(f.up_conv);
+  auto fenc = [&](EncLayer& e) { fw(e.qkv); fw(e.out); fw(e.pos); fw(e.w1); fw(e.w2); };
+  for (auto& e : f.enc) fenc(e);
+  for (auto& e : f.up_enc) fenc(e);
+  fw(f.time1); fw(f.time2); fw(f.time_mixer);
+  auto fstage = [&](CfmStage& st) {
+    fw(st.res.conv1); fw(st.res.conv2); fw(st.res.res); fw(st.res.mlp);
+    for (auto& t : st.t) { fw(t.qkv); fw(t.out); fw(t.ff1); fw(t.ff2); }
+  };
+  fstage(f.down); for (auto& st : f.mid) fstage(st); fstage(f.up);
+  fw(f.down_conv); fw(f.up_conv2); fw(f.final_conv); fw(f.final_proj);
+  HiftModel& v = h->hift;
+  for (auto& w : v.f0conv) fw(w);
+  fw(v.conv_pre); fw(v.conv_post);
+  for (auto& w : v.ups) fw(w);
+  for (auto& w : v.src_down) fw(w);
+  auto frb = [&](HiftResBlock& rb) { for (auto& w : rb.c1) fw(w); for (auto& w : rb.c2) fw(w); };
+  for (auto& rb : v.src_rb) frb(rb);
+  for (auto& rb : v.rb) frb(rb);
+  delete h;
 }
 
 const char* cbx_last_error(cbx_handle* h) { return h ? h->err.c_str() : "null handle"; }
