@@ -123,3 +123,38 @@ def test_multilingual_shim_rules():
     tts = ChatterboxMultilingualTTS.__new__(ChatterboxMultilingualTTS)
     with pytest.raises(ValueError):
         tts.generate("hola", language_id="xx")
+
+
+def test_synthesize_batch_chunking_and_order():
+    """Host logic of the batched flow/vocoder stages (no GPU): chunks respect the frame budgets, every utterance comes
+    back in its own slot, empty utterances yield empty waveforms."""
+    from chatterbox_b200.tts import synthesize_batch
+
+    class FakeEngine:
+        device = torch.device("cpu")
+
+        def __init__(self):
+            self.flow_calls, self.hift_calls = [], []
+
+        def flow_mel(self, speech, refs, n_timesteps=None):
+            self.flow_calls.append([int(s.numel()) for s in speech])
+            return [torch.full((80, 2 * int(s.numel())), float(s.numel())) for s in speech]
+
+        def hift(self, mels, seed=0, trim_fade=True):
+            self.hift_calls.append([int(m.shape[-1]) for m in mels])
+            return [torch.full((480 * int(m.shape[-1]),), float(m[0, 0])) for m in mels], None
+
+    eng = FakeEngine()
+    lens = [5, 0, 40, 17, 33, 8]
+    speech = [torch.zeros(n, dtype=torch.long) for n in lens]
+    refs = [dict(prompt_token=torch.zeros(1, 10, dtype=torch.long))] * len(lens)
+    wavs = synthesize_batch(eng, speech, refs, flow_frames_per_chunk=150, hift_frames_per_chunk=100)
+    for n, w in zip(lens, wavs):
+        assert w.numel() == 960 * n
+        assert n == 0 or float(w[0]) == float(n)                 # slot b holds utterance b
+    for call in eng.flow_calls:                                   # 2 * (prompt + tokens) frames per utterance
+        assert len(call) == 1 or sum(2 * (10 + n) for n in call) <= 150
+    assert sorted(sum(eng.flow_calls, [])) == sorted(lens)
+    for call in eng.hift_calls:
+        assert len(call) == 1 or sum(call) <= 100
+    assert sorted(sum(eng.hift_calls, [])) == sorted(2 * n for n in lens if n > 0)
