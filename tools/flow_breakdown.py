@@ -7,6 +7,10 @@ from chatterbox_b200 import Engine, S3Gen
 B = int(os.environ.get("FB", 32))
 eng = Engine(0)
 s3 = S3Gen(eng, W.make_flow_weights(0), W.make_hift_weights(0))
+if os.environ.get("ATTN_PREC"):          # fp16 | bf16x3 (opt-in operand formats)
+    eng.set_attention_precision(os.environ["ATTN_PREC"])
+if os.environ.get("CFM_ACT"):            # fp16 | bf16x2
+    eng.set_cfm_activation_precision(os.environ["CFM_ACT"])
 _, cg = W.make_conds(1234)
 g = torch.Generator().manual_seed(3)
 toks = [torch.randint(0, 6561, (int(n),), generator=g) for n in torch.randint(75, 1000, (B,), generator=g)]
