@@ -50,7 +50,15 @@ int cbx_create(int device, cbx_handle** out);
 void cbx_destroy(cbx_handle* h);
 const char* cbx_last_error(cbx_handle* h);
 int cbx_version(void);
-/* debug switches: key "gemm" = "tc"|"simt", key "attn" = "tc"|"simt" (SIMT = reference kernels for bisecting) */
+/* options (all per handle):
+ *   "gemm" = "tc"|"simt", "attn" = "tc"|"simt"   SIMT = plain reference kernels for bisecting (debug)
+ *   "time_kernel" = class name                   see cbx_timer_read below
+ *   "decode_graph" = "1"|"0"                     steps 2..n of a cbx_t3_decode call replay a CUDA graph of step 1 (default 0;
+ *                                                the call must then be issued on a capturable, non-default stream)
+ *   "attn_prec" = "bf16x3"|"fp16"                operand format of the CFM attention: bf16 hi/lo planes, 3 MMA terms (default)
+ *                                                or one fp16 plane, 1 term (opt-in)
+ *   "cfm_act" = "bf16x2"|"fp16"                  operand format of the CFM transformer-block GEMM inputs (default bf16 hi/lo);
+ *                                                "fp16" takes effect together with attn_prec = fp16 */
 int cbx_set_option(cbx_handle* h, const char* key, const char* value);
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 long long cbx_launch_count(cbx_handle* h);
