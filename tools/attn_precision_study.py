@@ -98,3 +98,27 @@ def study_gemm_inputs():
 
 if __name__ == "__main__" and os.environ.get("GEMM_STUDY", "1") == "1":
     study_gemm_inputs()
+
+
+def study_hift():
+    """Third question: the vocoder's conv inputs as one fp16 value?  No: max |dwav| 7e-4 against the 1e-4 bar."""
+    from oracle.hift_ref import HiFTOracle
+    hsd = W.make_hift_weights(0)
+    ho = HiFTOracle(hsd)
+    g = torch.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "s3gen_golden.pt"))
+    mel = g["cases"][0]["mel"]
+    torch.manual_seed(1)
+    wav_ref, s = ho.inference(mel, trim_fade=False)
+    conv, convt = F.conv1d, F.conv_transpose1d
+    for name, dt in [("fp16", torch.float16), ("bf16", torch.bfloat16)]:
+        F.conv1d = lambda x, w, b=None, *a, _dt=dt, **k: conv(x.to(_dt).float(), w, b, *a, **k)
+        F.conv_transpose1d = lambda x, w, b=None, *a, _dt=dt, **k: convt(x.to(_dt).float(), w, b, *a, **k)
+        try:
+            wav, _ = ho.inference(mel, s=s, trim_fade=False)
+        finally:
+            F.conv1d, F.conv_transpose1d = conv, convt
+        print(f"HiFT conv inputs as one {name} value: max|dwav| = {(wav - wav_ref).abs().max().item():.3e} (bar 1e-4)")
+
+
+if __name__ == "__main__" and os.environ.get("HIFT_STUDY", "1") == "1":
+    study_hift()
