@@ -27,7 +27,9 @@ class T3State(C.Structure):
                 ("x", C.c_void_p), ("logits", C.c_void_p), ("ldl", C.c_int),
                 ("cfg_weight", C.c_float), ("rep_penalty", C.c_float), ("temperature", C.c_float),
                 ("min_p", C.c_float), ("top_p", C.c_float),
-                ("q_noise", C.c_void_p), ("seed", C.c_ulonglong), ("sampler", C.c_int), ("top_k", C.c_int)]
+                ("q_noise", C.c_void_p), ("seed", C.c_ulonglong), ("sampler", C.c_int), ("top_k", C.c_int),
+                ("act_utt", C.c_void_p), ("n_act", C.c_void_p), ("src_slot", C.c_void_p), ("slot_row", C.c_void_p),
+                ("m_live", C.c_void_p), ("force_tokens", C.c_void_p), ("sampled_out", C.c_void_p)]
 
 
 class HiftGeom(C.Structure):
@@ -50,8 +52,7 @@ SYMBOLS = {
     "cbx_finalize_weights": (_I, [_P, C.c_char_p]),
     "cbx_t3_cond_encode": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _S, _P]),
     "cbx_t3_prefill": (_I, [_P, C.POINTER(T3State), _I, _P, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _S, _P]),
-    "cbx_t3_decode": (_I, [_P, C.POINTER(T3State), _P, _P, _I, _I, _P, _S, _P]),
-    "cbx_t3_compact": (_I, [_P, C.POINTER(T3State), _P, _I, _P, _S, _P]),
+    "cbx_t3_decode": (_I, [_P, C.POINTER(T3State), _I, _I, _P, _S, _P]),
     "cbx_t3_workspace_bytes": (_S, [_P, _I, _I]),
     "cbx_flow_encode": (_I, [_P, _P, C.POINTER(Layout), C.POINTER(Layout), _P, _P, _P, _P, _S, _P]),
     "cbx_cfm_solve": (_I, [_P, _P, _P, _P, _P, C.POINTER(Layout), C.POINTER(Layout), _I, _F, _I, _P, _S, _P]),
@@ -63,6 +64,8 @@ SYMBOLS = {
                            _I, _F, _P, _I, _I, _P, _I, _P]),
     "cbx_test_attention": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, C.POINTER(Layout), _F, _I, _P, C.c_longlong, _I, _I, _I, _P]),
     "cbx_test_attention_tc": (_I, [_P, _P, _P, _I, C.POINTER(Layout), _F, _P, _S, _P]),
+    "cbx_test_paged_decode": (_I, [_P, _P, _P, _I, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _S, _P]),
+    "cbx_test_gemm_splitk": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _S, _P]),
 }
 
 _lib = None

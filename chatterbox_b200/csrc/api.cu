@@ -56,22 +56,30 @@ int cbx_create(int device, cbx_handle** out) {
   if (cudaSetDevice(device) != cudaSuccess) return CBX_ERR_CUDA;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CBX_ERR_CUDA;
+  if (prop.major != 10) return CBX_ERR_CUDA;          // libcbx is built for sm_100a only; no handle is handed out
   cbx_handle* h = new cbx_handle();
   h->device = device;
-  if (prop.major != 10) { h->err = "libcbx is built for sm_100a only"; }
   const char* e = getenv("CBX_GEMM");
   if (e && std::string(e) == "simt") h->gemm_impl = 1;
   e = getenv("CBX_ATTN");
   if (e && std::string(e) == "simt") h->attn_impl = 1;
+  e = getenv("CBX_DECODE_GRAPH");
+  if (e) h->decode_graph = atoi(e);
+  try {        // per-device kernel attributes, before any launch or stream capture
+    gemm_init(); attention_tc_init(); paged_attention_init(); t3_sample_init();
+  } catch (const std::exception& ex) {
+    delete h;
+    return CBX_ERR_CUDA;
+  }
   *out = h;
-  return prop.major == 10 ? CBX_OK : CBX_ERR_CUDA;
+  return CBX_OK;
 }
 
 void cbx_destroy(cbx_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (void* p : h->owned) cudaFree(p);
-  if (h->decode_exec) cudaGraphExecDestroy(h->decode_exec);
+  for (auto& kv : h->decode_graphs) cudaGraphExecDestroy(kv.second.exec);
   for (cudaEvent_t e : h->timer.ev) cudaEventDestroy(e);
   auto fw = [](Weight& w) { free_weight(w); };      // no-op for weights that were never packed
   for (auto& l : h->t3.layers) { fw(l.qkv); fw(l.o); fw(l.gu); fw(l.down); }
@@ -186,34 +194,13 @@ int cbx_t3_prefill(cbx_handle* h, const cbx_t3_state* st, int n_tok, const int* 
   h->launches += c.launches;
   CBX_GUARD_END(h)
 }
-int cbx_t3_decode(cbx_handle* h, const cbx_t3_state* st, const int* act_utt, const int* slot_row, int n_act, int n_steps,
-                  void* ws, size_t ws_bytes, cbx_stream stream) {
+int cbx_t3_decode(cbx_handle* h, const cbx_t3_state* st, int capacity, int n_steps, void* ws, size_t ws_bytes,
+                  cbx_stream stream) {
   if (!h || !st) return CBX_ERR_INVALID;
   CBX_GUARD_BEGIN
   Ctx c = make_ctx(h, ws, ws_bytes, stream);
-  t3_decode(h, c, *st, act_utt, slot_row, n_act, n_steps);
+  t3_decode(h, c, *st, capacity, n_steps);
   h->launches += c.launches;
-  CBX_GUARD_END(h)
-}
-__global__ void gather_rows_generic_kernel(const float* src, float* dst, const int* idx, int ld) {
-  const int r = blockIdx.x;
-  const float* s = src + (long)idx[r] * ld;
-  for (int i = threadIdx.x; i < ld; i += blockDim.x) dst[(long)r * ld + i] = s[i];
-}
-int cbx_t3_compact(cbx_handle* h, const cbx_t3_state* st, const int* keep_slot, int n_keep, void* ws, size_t ws_bytes,
-                   cbx_stream stream) {
-  if (!h || !st) return CBX_ERR_INVALID;
-  CBX_GUARD_BEGIN
-  Ctx c = make_ctx(h, ws, ws_bytes, stream);
-  if (n_keep > 0) {
-    float* tx = c.ws.get<float>((size_t)n_keep * 1024);
-    float* tl = c.ws.get<float>((size_t)n_keep * st->ldl);
-    gather_rows_generic_kernel<<<n_keep, 256, 0, c.stream>>>(st->x, tx, keep_slot, 1024);
-    gather_rows_generic_kernel<<<n_keep, 256, 0, c.stream>>>(st->logits, tl, keep_slot, st->ldl);
-    CBX_CHECK(cudaMemcpyAsync(st->x, tx, (size_t)n_keep * 1024 * 4, cudaMemcpyDeviceToDevice, c.stream));
-    CBX_CHECK(cudaMemcpyAsync(st->logits, tl, (size_t)n_keep * st->ldl * 4, cudaMemcpyDeviceToDevice, c.stream));
-    h->launches += 2;
-  }
   CBX_GUARD_END(h)
 }
 size_t cbx_t3_workspace_bytes(cbx_handle* h, int n_tok_prefill, int n_rows) {
@@ -228,8 +215,8 @@ size_t cbx_t3_workspace_bytes(cbx_handle* h, int n_tok_prefill, int n_rows) {
                nullptr, nullptr);
     size_t a = c.ws.peak;
     Ctx d = make_ctx(h, nullptr, 0, nullptr, true);
-    t3_decode(h, d, st, nullptr, nullptr, st.n_utts, 1);
-    size_t b = d.ws.peak + (size_t)n_rows * (1024 + 8256) * 4 + 4096;   // + compaction staging
+    t3_decode(h, d, st, st.n_utts, 1);
+    size_t b = d.ws.peak + 4096;
     Ctx e = make_ctx(h, nullptr, 0, nullptr, true);
     t3_cond_encode(h, e, nullptr, nullptr, 512, nullptr, 1, nullptr);
     size_t m = a > b ? a : b;
@@ -371,6 +358,55 @@ int cbx_test_attention_tc(cbx_handle* h, const float* qkv, float* O, int n_heads
   a.kv_start = L->start; a.kv_len = L->len; a.max_q_len = L->max_len; a.scale = scale;
   attention_tc(c, a);
   CBX_CHECK(cudaStreamSynchronize(c.stream));
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+
+/* paged decode attention over a caller-built cache (layer 0 of a 1-layer pool) */
+int cbx_test_paged_decode(cbx_handle* h, const float* qkv, void* pages, int kv_dtype, int n_pages, const int* page_table,
+                          int max_pages, const int* slot_row, const int* positions, int n_slots, int nsplit, int impl,
+                          int fuse_rope, const float* cos_t, const float* sin_t, float* out, void* ws, size_t ws_bytes,
+                          cbx_stream stream) {
+  if (!h) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  PagedKV kv;
+  kv.pages = pages; kv.n_pages = n_pages; kv.kv_fp32 = kv_dtype; kv.n_layers = 1; kv.n_heads = 16; kv.page_tokens = 32;
+  kv.page_table = page_table; kv.max_pages_per_row = max_pages;
+  float* scratch = c.ws.get<float>((size_t)n_slots * 16 * nsplit * 66);
+  PagedOpts po;
+  po.fuse_rope = fuse_rope; po.cos_t = cos_t; po.sin_t = sin_t; po.impl = impl;
+  paged_decode_attention(c, qkv, 3072, kv, 0, slot_row, n_slots, positions, out, 1024, scratch, nsplit, nullptr, nullptr, &po);
+  CBX_CHECK(cudaStreamSynchronize(c.stream));
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+
+/* C[M][N] (N <= 1024) = A[M][K] x W[N][K]^T through the decode path: A as bf16 hi/lo planes, split-K partial sums,
+ * fixed-order reduction in resid_norm */
+int cbx_test_gemm_splitk(cbx_handle* h, const float* A, const float* w_host, int M, int N, int K, int splitk, int tile_bn,
+                         float* C, void* ws, size_t ws_bytes, cbx_stream stream) {
+  if (!h) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  CBX_REQUIRE(N <= 1024 && N % 4 == 0 && K % 64 == 0, "test shape");
+  Weight W;
+  pack_linear(W, w_host, nullptr, N, K);
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  __nv_bfloat16* hi = c.ws.get<__nv_bfloat16>((size_t)M * K);
+  __nv_bfloat16* lo = c.ws.get<__nv_bfloat16>((size_t)M * K);
+  float* part = c.ws.get<float>((size_t)splitk * M * N);
+  pack_hilo(c, A, K, M, K, hi, lo, M, K);
+  GemmDev g = gemm_args_linear(nullptr, K, M, W, part, N);
+  g.Ahi = hi; g.Alo = lo; g.ldab = K; g.bias = nullptr;
+  g.splitk = splitk; g.split_stride = (long)M * N; g.tile_bn = tile_bn;
+  gemm(c, g, W);
+  CBX_CHECK(cudaMemsetAsync(C, 0, (size_t)M * N * 4, c.stream));
+  ResidNormDev rn;
+  memset(&rn, 0, sizeof(rn));
+  rn.x = C; rn.ldx = N; rn.part = part; rn.nsplit = splitk; rn.split_stride = (long)M * N; rn.ldp = N; rn.dim = N;
+  resid_norm(c, rn, M);
+  CBX_CHECK(cudaStreamSynchronize(c.stream));
+  free_weight(W);
   h->launches += c.launches;
   CBX_GUARD_END(h)
 }

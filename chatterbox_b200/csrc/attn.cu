@@ -11,6 +11,8 @@
 //                           read exactly once, 16-byte coalesced loads, flash-decoding split over CTAs).
 //  * rope_store_kernel      llama3 RoPE on q,k (in place) + append k,v to the paged cache.
 #include "ops.h"
+#include <cstdlib>
+#include <string>
 
 namespace cbx {
 
@@ -340,6 +342,10 @@ struct PagedDev {
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;   // when set: the output as bf16 hi/lo planes (operand of the o GEMM)
   float* scratch;                     // [slots][H][nsplit][66] partial (m, l, o[64])
   int nsplit; float scale;
+  // bulk-copy kernel only: fuse_rope = 1 -> qkv holds the raw projections of the step's token; the kernel rotates q and k
+  // (llama3 RoPE tables cos_t / sin_t [pos][32]), appends k / v to the cache and attends to them from registers
+  int fuse_rope; const float* cos_t; const float* sin_t;
+  const int* n_live;                  // optional device scalar: slots >= *n_live are retired (CTA exits)
 };
 
 template <typename T>
@@ -347,6 +353,7 @@ __global__ void __launch_bounds__(128) paged_decode_kernel(const PagedDev p) {
   constexpr int LPT = KvTraits<T>::LPT, DPL = KvTraits<T>::DPL, TPI = 32 / LPT;   // tokens per warp-iteration
   constexpr int NP = DPL / KvPiece<T>::N;                                      // 16-byte pieces per lane and row
   const int slot = blockIdx.x, head = blockIdx.y, split = blockIdx.z;
+  if (p.n_live && slot >= *p.n_live) return;
   const int row = p.slot_row[slot];
   const int S = p.positions[row] + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -450,9 +457,194 @@ __global__ void __launch_bounds__(128) paged_decode_kernel(const PagedDev p) {
   }
 }
 
+
+// ================================================================================================
+// paged_bulk_kernel: the decode-step attention of the fused T3 layer.
+//   One CTA per (slot, head, split).  A producer warp streams the row's pages with the bulk-copy engine
+//   (cp.async.bulk global -> shared, mbarrier complete_tx): with the layer-major pool one (page, head) slab of K is
+//   32 tokens x 64 dims = 4 KB (bf16) of contiguous HBM, V likewise, so a stage is two bulk copies and no thread ever
+//   touches a global K/V address.  Four consumer warps fold the staged tiles into an online softmax (4 lanes per
+//   token, shuffle-reduced scores, exp in fp32) -- 8 stages x 8 KB in flight per CTA, 3 CTAs per SM.
+//   fuse_rope: RoPE on q and on the step's k, the KV-cache append and the attention over the new token all happen
+//   here (the token's k / v never make a round trip through the cache before they are used).
+// Algorithmic HBM bytes: every K/V byte of rows [0, pos] once + 3 x 64 floats of q/k/v per (slot, head).
+// ================================================================================================
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename T> struct BulkCfg;
+template <> struct BulkCfg<__nv_bfloat16> { static constexpr int NST = 8; };
+template <> struct BulkCfg<float> { static constexpr int NST = 4; };
+constexpr int PB_TOK = 32;                    // tokens per page (required by this kernel)
+constexpr int PB_THREADS = 160;               // 4 consumer warps + 1 producer warp
+
+template <typename T> constexpr int pb_smem_bytes() { return BulkCfg<T>::NST * 2 * PB_TOK * 64 * (int)sizeof(T) + 256; }
+
+template <typename T>
+__global__ void __launch_bounds__(PB_THREADS) paged_bulk_kernel(const PagedDev p) {
+  constexpr int NST = BulkCfg<T>::NST;
+  constexpr int SLAB = PB_TOK * 64 * (int)sizeof(T);      // one (page, head) slab of K or of V
+  constexpr int STAGE = 2 * SLAB;
+  constexpr int DPL = 16, NPC = DPL / KvPiece<T>::N;      // dims per lane, 16-byte pieces per lane
+  const int slot = blockIdx.x, head = blockIdx.y, split = blockIdx.z;
+  if (p.n_live && slot >= *p.n_live) return;
+  extern __shared__ __align__(128) uint8_t pb_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(pb_smem + NST * STAGE);
+  uint64_t* empty = full + NST;
+  const int row = p.slot_row[slot];
+  const int pos = p.positions[row];
+  const int S = pos + 1;
+  const int npg = (S + PB_TOK - 1) / PB_TOK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.n_heads;
+  const long slab_e = (long)PB_TOK * 64;                  // elements per slab
+  const long page_stride = 2L * H * slab_e;
+  const T* base = reinterpret_cast<const T*>(p.pages) + (long)p.layer * p.n_pages * page_stride + (long)head * slab_e;
+  const int* pt = p.page_table + (long)row * p.max_pages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    // ===================== producer: bulk copies of this CTA's pages (split, split + nsplit, ...) ==========
+    if (lane == 0) {
+      int i = 0;
+      for (int pj = split; pj < npg; pj += p.nsplit, ++i) {
+        const int s = i % NST;
+        mbar_wait(&empty[s], ((i / NST) & 1) ^ 1);
+        const T* kp = base + (long)pt[pj] * page_stride;
+        uint8_t* st = pb_smem + s * STAGE;
+        mbar_arrive_expect_tx(&full[s], STAGE);
+        bulk_g2s(st, kp, SLAB, &full[s]);
+        bulk_g2s(st + SLAB, kp + (long)H * slab_e, SLAB, &full[s]);
+      }
+    }
+    return;
+  }
+  // ===================== consumers ========================================================================
+  const int sub = lane & 3, grp = lane >> 2;              // 4 lanes per token, 8 tokens per warp and page
+  float q[DPL], kn[DPL], vn[DPL];
+  {
+    const float* qp = p.qkv + (long)slot * p.ldqkv + head * 64;
+    const int d0 = sub * DPL;
+    if (p.fuse_rope) {
+      // rotate_half convention (modeling_llama.py:138-167): out = x*cos + rotate_half(x)*sin, products rounded
+      // separately like the reference's elementwise ops (no fused multiply-add)
+      const float* kq = qp + H * 64;
+      const float* vq = qp + 2 * H * 64;
+      const int pd0 = d0 < 32 ? d0 + 32 : d0 - 32;
+      const float sgn = d0 < 32 ? -1.f : 1.f;
+      const float* ct = p.cos_t + (long)pos * 32 + (d0 & 31);
+      const float* sn = p.sin_t + (long)pos * 32 + (d0 & 31);
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) {
+        const float c = ct[i], s = sn[i];
+        q[i] = __fadd_rn(__fmul_rn(qp[d0 + i], c), __fmul_rn(sgn * qp[pd0 + i], s)) * p.scale;
+        float kr = __fadd_rn(__fmul_rn(kq[d0 + i], c), __fmul_rn(sgn * kq[pd0 + i], s));
+        float vr = vq[d0 + i];
+        if (sizeof(T) == 2) { kr = __bfloat162float(__float2bfloat16_rn(kr)); vr = __bfloat162float(__float2bfloat16_rn(vr)); }
+        kn[i] = kr; vn[i] = vr;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) { q[i] = qp[d0 + i] * p.scale; kn[i] = 0.f; vn[i] = 0.f; }
+    }
+  }
+  // the CTA that owns the page of the new token appends it to the cache (the lanes that attend to it)
+  const int new_pg = pos >> 5, new_t = pos & 31;
+  const bool own_new = p.fuse_rope && (new_pg % p.nsplit) == split && warp == (new_t >> 3) && grp == (new_t & 7);
+  if (own_new) {
+    T* kd = const_cast<T*>(base) + (long)pt[new_pg] * page_stride + (long)new_t * 64 + sub * DPL;
+    T* vd = kd + (long)H * slab_e;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) { kd[i] = (T)kn[i]; vd[i] = (T)vn[i]; }
+  }
+  float m = -INFINITY, l = 0.f, o[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) o[i] = 0.f;
+  {
+    int i = 0;
+    for (int pj = split; pj < npg; pj += p.nsplit, ++i) {
+      const int s = i % NST;
+      mbar_wait(&full[s], (i / NST) & 1);
+      const int tl = warp * 8 + grp;                      // token inside the page
+      const int tok = pj * PB_TOK + tl;
+      const uint4* kp = reinterpret_cast<const uint4*>(pb_smem + s * STAGE + (tl * 64 + sub * DPL) * (int)sizeof(T));
+      const uint4* vp = reinterpret_cast<const uint4*>(pb_smem + s * STAGE + SLAB + (tl * 64 + sub * DPL) * (int)sizeof(T));
+      float kx[DPL], vx[DPL];
+      uint4 kr[NPC], vr[NPC];
+#pragma unroll
+      for (int j = 0; j < NPC; ++j) { kr[j] = kp[j]; vr[j] = vp[j]; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);              // the stage's bytes are in registers
+#pragma unroll
+      for (int j = 0; j < NPC; ++j) { KvPiece<T>::decode(kr[j], kx + j * KvPiece<T>::N); KvPiece<T>::decode(vr[j], vx + j * KvPiece<T>::N); }
+      const bool is_new = p.fuse_rope && tok == pos;      // taken from registers, its cache slot is being written now
+      if (is_new) {
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) { kx[j] = kn[j]; vx[j] = vn[j]; }
+      }
+      float sc = 0.f;
+      if (tok < S) {
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) sc = fmaf(q[j], kx[j], sc);
+      }
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      if (tok < S) {
+        const float mn = fmaxf(m, sc);
+        const float c = (m == -INFINITY) ? 0.f : expf(m - mn);
+        const float e = expf(sc - mn);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) o[j] = o[j] * c + e * vx[j];
+        l = l * c + e; m = mn;
+      }
+    }
+  }
+  // ---- merge the 32 token streams of this CTA (consumer warps only: named barrier 1, 128 threads)
+  float* sm_m = reinterpret_cast<float*>(pb_smem);        // the K/V ring is drained: reuse it
+  float* sm_l = sm_m + 128;
+  float* sm_o = sm_l + 128;
+  asm volatile("bar.sync 1, 128;" ::: "memory");         // every consumer is past its last stage read
+  sm_m[threadIdx.x] = m; sm_l[threadIdx.x] = l;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) sm_o[threadIdx.x * DPL + i] = o[i];
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (threadIdx.x < 64) {
+    const int d = threadIdx.x;
+    const int osub = d / DPL, oi = d % DPL;
+    float mt = -INFINITY;
+    for (int g = 0; g < 32; ++g) mt = fmaxf(mt, sm_m[g * 4 + osub]);
+    float lt = 0.f, ot = 0.f;
+    for (int g = 0; g < 32; ++g) {
+      const int th = g * 4 + osub;
+      const float ms = sm_m[th];
+      if (ms == -INFINITY) continue;
+      const float c = expf(ms - mt);
+      lt += sm_l[th] * c;
+      ot += sm_o[th * DPL + oi] * c;
+    }
+    if (p.nsplit == 1) {
+      const float ov = lt > 0.f ? ot / lt : 0.f;
+      const long oidx = (long)slot * p.ldo + head * 64 + d;
+      if (p.out_hi) { __nv_bfloat16 hh, ll; split_bf16(ov, hh, ll); p.out_hi[oidx] = hh; p.out_lo[oidx] = ll; }
+      else p.out[oidx] = ov;
+    } else {
+      float* sp = p.scratch + (((long)slot * H + head) * p.nsplit + split) * 66;
+      sp[2 + d] = ot;
+      if (d == 0) { sp[0] = mt; sp[1] = lt; }
+    }
+  }
+}
+
 __global__ void paged_combine_kernel(const float* scratch, float* out, int ldo, int H, int nsplit,
-                                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, const int* n_live) {
   const int slot = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
+  if (n_live && slot >= *n_live) return;
   const float* sp = scratch + ((long)slot * H + head) * nsplit * 66;
   float mt = -INFINITY;
   for (int s = 0; s < nsplit; ++s) mt = fmaxf(mt, sp[s * 66]);
@@ -470,9 +662,14 @@ __global__ void paged_combine_kernel(const float* scratch, float* out, int ldo, 
   else out[oi] = ov;
 }
 
+void paged_attention_init() {     // per device, before any stream capture
+  CBX_CHECK(cudaFuncSetAttribute(paged_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes<__nv_bfloat16>()));
+  CBX_CHECK(cudaFuncSetAttribute(paged_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes<float>()));
+}
+
 void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* slot_row,
                             int n_slots, const int* positions, float* out, int ldo, float* scratch, int nsplit,
-                            __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                            __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, const PagedOpts* opts) {
   if (ctx.dry) return;
   PagedDev p;
   p.out_hi = out_hi; p.out_lo = out_lo;
@@ -483,15 +680,26 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
   CBX_REQUIRE((1 << p.page_shift) == kv.page_tokens, "page_tokens must be a power of two"); p.page_table = kv.page_table; p.max_pages = kv.max_pages_per_row;
   p.slot_row = slot_row; p.positions = positions; p.out = out; p.ldo = ldo; p.scratch = scratch; p.nsplit = nsplit;
   p.scale = 0.125f;
+  p.fuse_rope = opts ? opts->fuse_rope : 0; p.cos_t = opts ? opts->cos_t : nullptr; p.sin_t = opts ? opts->sin_t : nullptr;
+  p.n_live = opts ? opts->n_live : nullptr;
+  // default: the bulk-copy (TMA engine) kernel; CBX_PAGED=ldg keeps the round-1 __ldg kernel for A/B runs
+  static const bool force_ldg = getenv("CBX_PAGED") && std::string(getenv("CBX_PAGED")) == "ldg";
+  const bool bulk = kv.page_tokens == PB_TOK && !(force_ldg && !p.fuse_rope) && !(opts && opts->impl == 1);
+  CBX_REQUIRE(bulk || !p.fuse_rope, "fused RoPE + KV append needs the bulk-copy kernel (32-token pages)");
   dim3 grid(n_slots, kv.n_heads, nsplit);
   ctx.launches++;
   if (ctx.timer) ctx.timer->begin(K_PAGED, ctx.stream);
-  if (kv.kv_fp32) paged_decode_kernel<float><<<grid, 128, 0, ctx.stream>>>(p);
-  else paged_decode_kernel<__nv_bfloat16><<<grid, 128, 0, ctx.stream>>>(p);
+  if (bulk) {
+    if (kv.kv_fp32) paged_bulk_kernel<float><<<grid, PB_THREADS, pb_smem_bytes<float>(), ctx.stream>>>(p);
+    else paged_bulk_kernel<__nv_bfloat16><<<grid, PB_THREADS, pb_smem_bytes<__nv_bfloat16>(), ctx.stream>>>(p);
+  } else {
+    if (kv.kv_fp32) paged_decode_kernel<float><<<grid, 128, 0, ctx.stream>>>(p);
+    else paged_decode_kernel<__nv_bfloat16><<<grid, 128, 0, ctx.stream>>>(p);
+  }
   if (ctx.timer) ctx.timer->end(K_PAGED, ctx.stream);
   if (nsplit > 1) {
     ctx.launches++;
-    paged_combine_kernel<<<dim3(n_slots, kv.n_heads), 64, 0, ctx.stream>>>(scratch, out, ldo, kv.n_heads, nsplit, out_hi, out_lo);
+    paged_combine_kernel<<<dim3(n_slots, kv.n_heads), 64, 0, ctx.stream>>>(scratch, out, ldo, kv.n_heads, nsplit, out_hi, out_lo, p.n_live);
   }
   CBX_CHECK(cudaGetLastError());
 }

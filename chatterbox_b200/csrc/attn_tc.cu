@@ -361,16 +361,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
 // ---- host --------------------------------------------------------------------------------------------
 
+void attention_tc_init() {      // per device
+  CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+  CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+  CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_F16));
+  CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_F16));
+}
+
 void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
   if (ctx.dry) return;
-  static bool attr = false;
-  if (!attr) {
-    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_F16));
-    CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_F16));
-    attr = true;
-  }
   AttnTcDev p;
   p.O = a.O; p.ldo = a.ldo; p.Ohi = a.Ohi; p.Olo = a.Olo; p.O16 = a.O16; p.q_start = a.q_start; p.q_len = a.q_len; p.kv_start = a.kv_start; p.kv_len = a.kv_len;
   p.scale_log2e = a.scale * 1.4426950408889634f;

@@ -275,12 +275,14 @@ __global__ void __launch_bounds__(1024) t3_sample_kernel(T3SampleDev p) {
   float* skey = sh + 64;                        // [SV_PAD] sort keys (top-k / top-p only)
   int* sidx = reinterpret_cast<int*>(skey + SV_PAD);   // [SV_PAD]
   const int j = blockIdx.x;
+  if (p.n_act && j >= *p.n_act) return;         // retired slot (device-side compaction, t3_compact_kernel)
   const int utt = p.act_utt[j];
   if (p.done[utt]) return;
   const int V = p.vocab;                        // 8194, Turbo 6563 (tables keep the SV stride)
   const bool turbo = p.turbo != 0;
   const int rows_per = p.cfg ? 2 : 1;
-  const float* lc = p.logits + (long)(j * rows_per) * p.ldl;
+  // logits were written at the slot the utterance had BEFORE this step's compaction
+  const float* lc = p.logits + (long)((p.src_slot ? p.src_slot[j] : j) * rows_per) * p.ldl;
   const float* lu = p.cfg ? lc + p.ldl : nullptr;
   const int step = p.n_gen[utt];
   unsigned char* seen = p.seen + (long)utt * SV;
@@ -404,7 +406,11 @@ __global__ void __launch_bounds__(1024) t3_sample_kernel(T3SampleDev p) {
     if (threadIdx.x == 0) bi[0] = besti;
   }
   __syncthreads();
-  const int tok = bi[0];
+  int tok = bi[0];
+  if (p.force_tokens) {           // teacher forcing (parity tests): record the engine's own pick, feed the given id
+    if (threadIdx.x == 0 && p.sampled_out) p.sampled_out[(long)utt * p.max_tokens + step] = tok;
+    tok = p.force_tokens[(long)utt * p.max_tokens + step];
+  }
   // 7: bookkeeping + next embedding (speech_emb[tok] + speech_pos[step+1], both CFG rows)
   // inference_turbo samples its first token from the prefill without an EOS check (t3.py:428-433)
   const bool finished = (tok == p.eos_id && !(turbo && step == 0)) || (step + 1 >= p.max_new[utt]);
@@ -427,13 +433,130 @@ __global__ void __launch_bounds__(1024) t3_sample_kernel(T3SampleDev p) {
     for (int r = 0; r < rows_per; ++r) p.x[((long)(j * rows_per + r)) * 1024 + d] = v;
   }
 }
+constexpr int T3_SAMPLE_SMEM = (SV + 64 + SV_PAD) * 4 + SV_PAD * 4;
+void t3_sample_init() {     // per device, before any launch / stream capture
+  CBX_CHECK(cudaFuncSetAttribute(t3_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SAMPLE_SMEM));
+}
 void t3_sample(Ctx& ctx, const T3SampleDev& p, int n_act) {
   if (ctx.dry || n_act == 0) return;
-  static bool attr = false;
-  const int smem = (SV + 64 + SV_PAD) * 4 + SV_PAD * 4;
-  if (!attr) { CBX_CHECK(cudaFuncSetAttribute(t3_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+  const int smem = T3_SAMPLE_SMEM;
   ctx.launches++;
   t3_sample_kernel<<<n_act, 1024, smem, ctx.stream>>>(p);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ================================================================================================
+// T3 decode: device-side retirement of finished utterances (replaces the host sync of t3.py:366).
+// Stable compaction of the active list, once per step, one CTA: act_utt[0, n_act) loses the utterances whose `done`
+// flag the sampler set in the previous step; src_slot[j] = slot the survivor had before (its logits still live
+// there), slot_row[j*rp + r] = physical KV row, m_live = live decode rows (GEMM row tiles above it exit).
+// ================================================================================================
+__global__ void __launch_bounds__(1024) t3_compact_kernel(int* act_utt, int* n_act, int* src_slot, int* slot_row, int* m_live,
+                                                          const int* done, int rows_per) {
+  __shared__ int wsum[32];
+  __shared__ int s_base;
+  const int n = *n_act;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < n; c0 += 1024) {
+    const int j = c0 + threadIdx.x;
+    const int utt = j < n ? act_utt[j] : -1;
+    const int keep = (utt >= 0 && !done[utt]) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int wpre = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();                       // every entry of this chunk is in a register before anyone writes
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += wsum[w];
+    int total = 0;
+    for (int w = 0; w < 32; ++w) total += wsum[w];
+    const int base = s_base;
+    if (keep) {
+      const int d = base + woff + wpre;    // d <= j: only positions that have already been read are overwritten
+      act_utt[d] = utt; src_slot[d] = j;
+      for (int r = 0; r < rows_per; ++r) slot_row[d * rows_per + r] = utt * rows_per + r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *n_act = s_base; *m_live = s_base * rows_per; }
+}
+void t3_compact(Ctx& ctx, int* act_utt, int* n_act, int* src_slot, int* slot_row, int* m_live, const int* done, int rows_per) {
+  if (ctx.dry) return;
+  ctx.launches++;
+  t3_compact_kernel<<<1, 1024, 0, ctx.stream>>>(act_utt, n_act, src_slot, slot_row, m_live, done, rows_per);
+  CBX_CHECK(cudaGetLastError());
+}
+
+// ================================================================================================
+// resid_norm: the glue between two GEMMs of a decode layer in ONE pass over the row (dim <= 1024):
+//   x[r] += bias + sum_z part[z][r]      (split-K partial sums of the o / down projection, fixed order -> deterministic)
+//   y[r]  = norm(x[r]) * w (+ b)         RMSNorm (Llama) or LayerNorm (GPT-2), written as the bf16 hi/lo planes the
+//                                        next GEMM loads by TMA (or fp32 for the GEMV path)
+// Replaces: residual add in the GEMM epilogue + rmsnorm kernel.  Bytes: (nsplit + 2) x 4 KB in, 4 KB (+ 4 KB) out per row.
+// ================================================================================================
+__global__ void __launch_bounds__(256) resid_norm_kernel(const ResidNormDev p) {
+  __shared__ float sh[32];
+  const int r = blockIdx.x;
+  if (p.m_live && r >= *p.m_live) return;
+  const int i = threadIdx.x * 4;
+  const bool on = i < p.dim;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* xr = p.x + (long)r * p.ldx;
+  if (on) {
+    v = *reinterpret_cast<const float4*>(xr + i);
+    if (p.nsplit > 0) {
+      if (p.bias) { const float4 b = *reinterpret_cast<const float4*>(p.bias + i); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+      for (int z = 0; z < p.nsplit; ++z) {
+        const float4 a = *reinterpret_cast<const float4*>(p.part + (long)z * p.split_stride + (long)r * p.ldp + i);
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      }
+      *reinterpret_cast<float4*>(xr + i) = v;
+    }
+  }
+  if (!p.w) return;
+  float o[4];
+  if (p.layernorm) {
+    const float mean = block_sum(on ? (v.x + v.y) + (v.z + v.w) : 0.f, sh) / p.dim;
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    const float var = block_sum(on ? (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) : 0.f, sh) / p.dim;
+    const float inv = rsqrtf(var + p.eps);
+    if (on) {
+      const float4 w = *reinterpret_cast<const float4*>(p.w + i);
+      const float4 b = *reinterpret_cast<const float4*>(p.b + i);
+      o[0] = d0 * inv * w.x + b.x; o[1] = d1 * inv * w.y + b.y; o[2] = d2 * inv * w.z + b.z; o[3] = d3 * inv * w.w + b.w;
+    }
+  } else {
+    const float ss = block_sum(on ? (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w) : 0.f, sh);
+    const float inv = rsqrtf(ss / p.dim + p.eps);
+    if (on) {
+      const float4 w = *reinterpret_cast<const float4*>(p.w + i);
+      o[0] = w.x * (v.x * inv); o[1] = w.y * (v.y * inv); o[2] = w.z * (v.z * inv); o[3] = w.w * (v.w * inv);
+    }
+  }
+  if (!on) return;
+  if (p.yhi) {
+    uint32_t h0, l0, h1, l1;
+    {
+      __nv_bfloat16 a, b, c, d;
+      split_bf16(o[0], a, b); split_bf16(o[1], c, d);
+      h0 = pack_bf16(a, c); l0 = pack_bf16(b, d);
+      split_bf16(o[2], a, b); split_bf16(o[3], c, d);
+      h1 = pack_bf16(a, c); l1 = pack_bf16(b, d);
+    }
+    *reinterpret_cast<uint2*>(p.yhi + (long)r * p.ldy + i) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(p.ylo + (long)r * p.ldy + i) = make_uint2(l0, l1);
+  } else {
+    *reinterpret_cast<float4*>(p.y + (long)r * p.ldy + i) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+void resid_norm(Ctx& ctx, const ResidNormDev& p, int rows) {
+  if (ctx.dry || rows == 0) return;
+  CBX_REQUIRE(p.dim <= 1024 && p.dim % 4 == 0, "resid_norm handles rows of <= 1024 floats");
+  ctx.launches++;
+  resid_norm_kernel<<<rows, 256, 0, ctx.stream>>>(p);
   CBX_CHECK(cudaGetLastError());
 }
 

@@ -7,6 +7,8 @@
 
 namespace cbx {
 
+struct DecodeGraph { cudaGraphExec_t exec = nullptr; long launches = 0; };   // one captured decode step
+
 struct HostTensor { std::vector<float> data; std::vector<int64_t> shape; };
 
 struct DevVec {   // small fp32 parameter vector on the device
@@ -73,10 +75,10 @@ struct cbx_handle {
   int gemm_impl = 0, attn_impl = 0, attn_f16 = 0, cfm_act_f16 = 0;
   long long launches = 0;
   cbx::KTimer timer;
-  // "decode_graph" option: steps 2..n of a cbx_t3_decode call replay a CUDA graph captured from step 1 (launch-bound
-  // small batches).  The executable of the previous call is released at the next call / destroy.
-  int decode_graph = 0;
-  cudaGraphExec_t decode_exec = nullptr;
+  // "decode_graph" option (default on): a decode step is captured once per (state, capacity, workspace) into a CUDA
+  // graph and replayed for every step; the executables are cached on the handle.
+  int decode_graph = 1;
+  std::map<uint64_t, cbx::DecodeGraph> decode_graphs;
   std::vector<void*> owned;                      // device allocations to free
 };
 
@@ -88,8 +90,7 @@ void t3_cond_encode(cbx_handle* h, Ctx& ctx, const float* spk, const int* prompt
 void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, const int* tok_row, const int* tok_pos,
                 const int* row_start, const int* row_len, int max_row_len, const float* cond, const int* row_voice,
                 int len_cond, const int* text_flat, const int* text_start, const int* n_text, const int* row_uncond);
-void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, const int* act_utt, const int* slot_row, int n_act,
-               int n_steps);
+void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap, int n_steps);
 void flow_finalize(cbx_handle* h);
 void flow_encode(cbx_handle* h, Ctx& ctx, const int* tokens, const cbx_layout& L1, const cbx_layout& L2,
                  const float* xvec, float* mu, float* spk);

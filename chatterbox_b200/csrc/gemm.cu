@@ -144,7 +144,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;             // N tiles fastest: CTAs sharing an A tile run together (L2 reuse)
   const int m0 = blockIdx.y * TC_BM;
-  const int KB = g.Kpad / TC_BK;
+  if (g.m_live && m0 >= *g.m_live) return;    // device-side retirement: the row tile holds no live decode row
+  // split-K: blockIdx.z owns K blocks [kb0, kb0 + KB) and writes its partial sums to C + z * split_stride (plain
+  // stores in a fixed order: the reduction happens in the consumer kernel, deterministically)
+  const int KBt = g.Kpad / TC_BK;
+  const int kb0 = (g.splitk > 1) ? (int)((long)blockIdx.z * KBt / g.splitk) : 0;
+  const int KB = (g.splitk > 1) ? (int)((long)(blockIdx.z + 1) * KBt / g.splitk) - kb0 : KBt;
+  float* const Cz = g.C ? g.C + (long)blockIdx.z * g.split_stride : nullptr;
   const bool dbg = g.dbg && blockIdx.y == gridDim.y / 2 && blockIdx.x == 0;
   if (dbg && threadIdx.x == 0) g.dbg[5] = clock64();
 
@@ -193,7 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
 #pragma unroll
         for (int p = 0; p < 8; ++p) v[p] = *reinterpret_cast<const float4*>(a_st + (p * 16 + rsub) * 256 + c4 * 16);
         if (need_mask) {
-          const int toff = ((kb * TC_BK) / g.ctap) * g.dil;
+          const int toff = (((kb0 + kb) * TC_BK) / g.ctap) * g.dil;
 #pragma unroll
           for (int p = 0; p < 8; ++p)
             if (toff < lo_rel[p] || toff >= hi_rel[p]) v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -232,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
-        const int k0 = kb * TC_BK + c4 * 4;
+        const int k0 = (kb0 + kb) * TC_BK + c4 * 4;
         float4 v[8];
 #pragma unroll 1
         for (int p = 0; p < 8; ++p) {
@@ -346,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
             }
           }
           const float a_mul = pre ? 1.0f : g.alpha, a_add = pre ? 0.0f : bias;
-          float* cbase = g.C + grow0 * g.ldc + n;
+          float* cbase = Cz + grow0 * g.ldc + n;
 #pragma unroll
           for (int r0 = 0; r0 < 32; r0 += 8) {
             if (r0 >= rows_here) break;
@@ -443,14 +449,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&tma_full[s], g.a_tma == 3 ? (16384 + Cfg::W_BYTES) : g.a_tma ? (Cfg::A_BYTES + Cfg::W_BYTES) : Cfg::W_BYTES);
-        tma_load_2d(a_st + Cfg::A_BYTES, &tmapW, &tma_full[s], kb * TC_BK, n0);
+        tma_load_2d(a_st + Cfg::A_BYTES, &tmapW, &tma_full[s], (kb0 + kb) * TC_BK, n0);
         if (g.a_tma == 3) {
-          tma_load_2d(a_st, &tmapA, &tma_full[s], kb * TC_BK, m0);             // the fp16 plane
+          tma_load_2d(a_st, &tmapA, &tma_full[s], (kb0 + kb) * TC_BK, m0);             // the fp16 plane
         } else if (g.a_tma == 2) {
-          tma_load_2d(a_st, &tmapA, &tma_full[s], kb * TC_BK, m0);             // hi plane, SWIZZLE_128B
-          tma_load_2d(a_st + 16384, &tmapA2, &tma_full[s], kb * TC_BK, m0);    // lo plane
+          tma_load_2d(a_st, &tmapA, &tma_full[s], (kb0 + kb) * TC_BK, m0);             // hi plane, SWIZZLE_128B
+          tma_load_2d(a_st + 16384, &tmapA2, &tma_full[s], (kb0 + kb) * TC_BK, m0);    // lo plane
         } else if (g.a_tma) {
-          const int k0 = kb * TC_BK;
+          const int k0 = (kb0 + kb) * TC_BK;
           const int tap = k0 / g.ctap, c = k0 - tap * g.ctap;
           tma_load_2d(a_st, &tmapA, &tma_full[s], c, (int)(in_row0 + (long)tap * g.dil));
         }
@@ -740,12 +746,16 @@ static void make_a_tmap(CUtensorMap* tm, const GemmDev& g) {
   if (r != CUDA_SUCCESS) throw std::runtime_error("cbx: cuTensorMapEncodeTiled (A operand) failed");
 }
 
+// opt every tcgen05 instantiation into its dynamic shared memory size on the CURRENT device (called once per handle,
+// before any launch or stream capture)
+template <int BN, int DUAL> static void set_tc_attr() {
+  CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, DUAL>::SMEM));
+}
+void gemm_init() {
+  set_tc_attr<64, 0>(); set_tc_attr<64, 1>(); set_tc_attr<128, 0>(); set_tc_attr<128, 1>(); set_tc_attr<256, 0>();
+}
+
 template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Weight& W, int tmap_idx) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, DUAL>::SMEM));
-    attr_set = true;
-  }
   // TMA-fed A operand: plain strided fp32 rows (Linear, stride-1 conv taps)
   g.a_tma = (g.a_mode == A_TAPS && g.stride == 1 && (g.lda % 4) == 0 && (g.c_in % 4) == 0 &&
              (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && g.M_in > 0) ? 1 : 0;
@@ -764,7 +774,12 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
     if (g.a_tma) make_a_tmap(&tmA, g); else tmA = W.tmap[tmap_idx];
     tmA2 = tmA;
   }
-  dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM);
+  if (g.splitk < 1) g.splitk = 1;
+  if (g.splitk > 1) {
+    CBX_REQUIRE(g.C && !g.bias && !g.res && !g.C2 && !g.Chi && !g.accumulate && !g.swiglu && g.act == ACT_NONE && g.alpha == 1.0f &&
+                g.out_scale == 1.0f && g.splitk <= g.Kpad / TC_BK, "split-K writes raw partial sums");
+  }
+  dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM, g.splitk);
   if (ctx.timer && ctx.timer->cls == K_GEMM_TC) {
     ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
     // algorithmic HBM bytes: weights once (bf16), the activation matrix once (fp32 or hi+lo planes = 4 B per element),
@@ -820,7 +835,10 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
       const long t256 = (g.Npad % 256 == 0) ? (long)mt * (g.Npad / 256) : 0;
       // fewest waves first: two CTAs per SM when there are >= 2 tiles per SM, else the widest tile that still spreads
       // over at least half of the SMs (per-tile time is latency-bound, so fewer, fatter tiles beat a second wave)
-      if (tile_mode == 0 && t128 >= 2 * 148) launch_tc<128, 1>(ctx, g, W, 1);
+      if (g.tile_bn == 64) { if (g.tile_dual) launch_tc<64, 1>(ctx, g, W, 0); else launch_tc<64, 0>(ctx, g, W, 0); }
+      else if (g.tile_bn == 128 && t128 > 0) { if (g.tile_dual) launch_tc<128, 1>(ctx, g, W, 1); else launch_tc<128, 0>(ctx, g, W, 1); }
+      else if (g.tile_bn == 256 && t256 > 0) launch_tc<256, 0>(ctx, g, W, 2);
+      else if (tile_mode == 0 && t128 >= 2 * 148) launch_tc<128, 1>(ctx, g, W, 1);
       else if (t256 >= 120) launch_tc<256, 0>(ctx, g, W, 2);
       else if (t128 >= 74) launch_tc<128, 0>(ctx, g, W, 1);
       else if (tile_mode == 0 && t64 >= 2 * 148) launch_tc<64, 1>(ctx, g, W, 0);

@@ -7,6 +7,10 @@ namespace cbx {
 struct T3SampleDev {
   const float* logits; int ldl;          // [n_slots][ldl]; slots (2j, 2j+1) = (cond, uncond) rows of active utt j
   const int* act_utt;                    // [n_act] active utterance ids
+  const int* n_act;                      // device scalar: live entries of act_utt (CTAs beyond it exit); may be null
+  const int* src_slot;                   // [n_act] slot whose logits row belongs to active entry j (set by t3_compact); may be null
+  const int* force_tokens;               // optional [B][max_tokens]: teacher forcing (feed these ids, tests only)
+  int* sampled_out;                      // with force_tokens: the ids the sampler itself picked
   int cfg; int n_utts;
   float cfg_weight, rep_penalty, temperature, min_p, top_p;
   int eos_id;
@@ -35,6 +39,19 @@ void t3_embed(Ctx& ctx, float* out, int n_tok, const int* tok_row, const int* to
               const int* row_uncond, const float* text_emb, int text_vocab, const float* text_pos,
               const float* speech_emb, const float* speech_pos, int bos_id, const float* wpe = nullptr);
 void t3_sample(Ctx& ctx, const T3SampleDev& p, int n_act);
+void t3_sample_init();
+void t3_compact(Ctx& ctx, int* act_utt, int* n_act, int* src_slot, int* slot_row, int* m_live, const int* done, int rows_per);
+struct ResidNormDev {
+  float* x; int ldx;                     // residual stream, updated in place when nsplit > 0
+  const float* part; int nsplit; long split_stride; int ldp;   // split-K partial sums [nsplit][rows][ldp]
+  const float* bias;                     // bias of the projection that produced `part` (GPT-2), or null
+  const float* w; const float* b;        // norm weight (null: residual update only) and LayerNorm bias
+  int layernorm; float eps;
+  __nv_bfloat16* yhi; __nv_bfloat16* ylo; float* y; int ldy;   // bf16 hi/lo planes, or fp32 when yhi == null
+  int dim;
+  const int* m_live;                     // optional device scalar: rows >= *m_live exit
+};
+void resid_norm(Ctx& ctx, const ResidNormDev& p, int rows);
 void add_pos_bias(Ctx& ctx, const float* qkv, int ld, const float* u, const float* v, float* qu, float* qv, long rows);
 void relpos_table(Ctx& ctx, float* pe, int T, int d_model);
 void upsample2(Ctx& ctx, const float* x, float* y, int C, const int* tile_seq2, const int* start2, const int* len2,

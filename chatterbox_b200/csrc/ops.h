@@ -69,6 +69,12 @@ struct GemmDev {
   // A operand as ONE fp16 plane [M][lda16] written by the producer (plain Linear): a single TMA box per K block and a
   // single MMA term (A fp16 x W bf16).  Only where the precision study allows it (CFM transformer blocks).
   const __half* A16; int lda16;
+  // split-K (decode GEMMs with few row tiles): grid.z = splitk CTAs per output tile, raw fp32 partial sums at
+  // C + z * split_stride (elements); the consumer (resid_norm) adds them in a fixed order
+  int splitk; long split_stride;
+  const int* m_live;        // optional device scalar: row tiles with m0 >= *m_live exit at once (device-side retirement)
+  int tile_bn;              // 0 = heuristic; 64 | 128 | 256 forces the N tile (decode shapes are tuned by measurement)
+  int tile_dual;            // with tile_bn: 1 = the two-CTAs-per-SM configuration
 };
 
 struct Arena {  // bump allocator over caller-owned workspace; dry=true only counts
@@ -138,6 +144,7 @@ void free_weight(Weight& W);
 void make_tmaps_for(Weight& W);   // (re)build the TMA maps of a weight whose .w/.Npad/.Kpad are set
 
 // ---- GEMM ---------------------------------------------------------------------------------------
+void gemm_init();   // per device: dynamic shared memory opt-in of every tcgen05 instantiation
 GemmDev gemm_args_linear(const float* A, int lda, int M, const Weight& W, float* C, int ldc);
 void gemm(Ctx& ctx, GemmDev g, const Weight& W);
 
@@ -170,6 +177,7 @@ struct AttnTcArgs {
   int max_q_len; float scale;
 };
 void attention_tc(Ctx& ctx, const AttnTcArgs& a);
+void attention_tc_init();
 void make_plane_tmap(CUtensorMap* tm, const __nv_bfloat16* base, long rows, int cols, int box_rows = 64, int ld = 0);
 void attention_generic(Ctx& ctx, const float* Q, const float* K, const float* V, float* O, int n_q, int n_kv,
                        int n_heads, int head_dim, int ldq, int ldk, int ldv, int ldo, float scale);
@@ -183,9 +191,17 @@ struct PagedKV {
   const int* page_table;  // [rows][max_pages_per_row]
   int max_pages_per_row;
 };
+struct PagedOpts {
+  int fuse_rope = 0;                  // qkv holds the raw projections: rotate q/k, append k/v, attend (bulk kernel only)
+  const float* cos_t = nullptr; const float* sin_t = nullptr;   // [pos][32] RoPE tables
+  const int* n_live = nullptr;        // device scalar: slots >= *n_live exit (device-side retirement)
+  int impl = 0;                       // 1 = round-1 __ldg kernel (tests / A-B runs)
+};
+void paged_attention_init();
 void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* slot_row,
                             int n_slots, const int* positions, float* out, int ldo, float* scratch, int nsplit,
-                            __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);   // planes instead of out
+                            __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr,   // planes instead of out
+                            const PagedOpts* opts = nullptr);
 void rope_and_store_kv(Ctx& ctx, float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* tok_row,
                        const int* tok_pos, int pos_is_per_row, int n_tok, const float* cos_t, const float* sin_t);
 

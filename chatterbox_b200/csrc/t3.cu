@@ -6,6 +6,7 @@
 // fused c_attn with bias, learned absolute positions (wpe) added to the input embeddings, gelu_new MLP, no RoPE, no CFG,
 // speech head with bias over 6563 ids.  Same kernels, same paged KV cache; the RoPE tables are the identity.
 #include "engine.h"
+#include <cstdlib>
 
 namespace cbx {
 
@@ -316,120 +317,179 @@ void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, cons
   gemm(ctx, gemm_args_linear(hn, 1024, R, m.head, st.logits, st.ldl), m.head);
 }
 
-void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, const int* act_utt, const int* slot_row, int n_act,
-               int n_steps) {
+// ---- decode step -------------------------------------------------------------------------------------
+// One step of the sampling loop of T3.inference (t3.py:338-386) / T3.inference_turbo (t3.py:426-461) for `cap` slots:
+//   t3_compact (device-side retirement) -> sampler (token i, next input embedding) ->
+//   L x [ resid_norm -> QKV GEMM -> paged attention with fused RoPE + KV append (bulk-copy staged K/V) ->
+//         O GEMM (split-K partials) -> resid_norm -> gate/up GEMM (SwiGLU / gelu_new epilogue) -> down GEMM (split-K) ]
+//   -> resid_norm (final norm) -> speech head.
+// Every launch argument of a step is constant across steps (the moving parts -- active list, positions, tokens, done
+// flags -- live in device memory), so a step is captured once into a CUDA graph per (state, capacity) and replayed.
+struct DecodeTiles { int qkv_bn, qkv_dual, o_bn, o_split, gu_bn, gu_dual, down_bn, down_split, head_bn; };
+
+static DecodeTiles decode_tiles(int S) {
+  // measured on the B200 with tools/gemm_decode_sweep.py (profiles/r2_gemm_decode_sweep.txt); env overrides for sweeps
+  DecodeTiles t;
+  const int mt = (S + 127) / 128;
+  t.qkv_bn = mt >= 3 ? 64 : 64;  t.qkv_dual = mt >= 4 ? 1 : 0;
+  t.o_bn = 64;   t.o_split = mt >= 3 ? 2 : 4;
+  t.gu_bn = mt >= 2 ? 128 : 64;  t.gu_dual = mt >= 3 ? 1 : 0;
+  t.down_bn = 64; t.down_split = mt >= 3 ? 4 : 8;
+  t.head_bn = 0;
+  static const char* ov = getenv("CBX_DECODE_TILES");     // "qkv_bn,qkv_dual,o_bn,o_split,gu_bn,gu_dual,down_bn,down_split"
+  if (ov) {
+    int v[8];
+    if (sscanf(ov, "%d,%d,%d,%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4, v + 5, v + 6, v + 7) == 8) {
+      t.qkv_bn = v[0]; t.qkv_dual = v[1]; t.o_bn = v[2]; t.o_split = v[3]; t.gu_bn = v[4]; t.gu_dual = v[5]; t.down_bn = v[6]; t.down_split = v[7];
+    }
+  }
+  return t;
+}
+
+static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap) {
   T3Model& m = h->t3;
-  CBX_REQUIRE(m.ready, "t3 weights not finalized");
   const int rows_per = st.cfg ? 2 : 1;
-  const int S = n_act * rows_per;
+  const int S = cap * rows_per;
+  const size_t mark = ctx.ws.mark();
+  const DecodeTiles tl = decode_tiles(S);
+  const int max_split = 8;
   float* xn = ctx.ws.get<float>((size_t)S * 1024);
   float* qkv = ctx.ws.get<float>((size_t)S * 3072);
   float* att = ctx.ws.get<float>((size_t)S * 1024);
   float* act = ctx.ws.get<float>((size_t)S * 4096);
+  float* part = ctx.ws.get<float>((size_t)max_split * S * 1024);
   int nsplit = 1;
-  if (S * 16 < 592) { nsplit = (592 + S * 16 - 1) / (S * 16); if (nsplit > 16) nsplit = 16; }
+  if (S * 16 < 444) { nsplit = (444 + S * 16 - 1) / (S * 16); if (nsplit > 16) nsplit = 16; }     // 3 CTAs per SM
   float* scratch = ctx.ws.get<float>((size_t)S * 16 * nsplit * 66);
   PagedKV kv = paged_of(st, m.n_layers);
   T3SampleDev sp;
-  sp.logits = st.logits; sp.ldl = st.ldl; sp.act_utt = act_utt; sp.cfg = st.cfg; sp.n_utts = st.n_utts;
+  memset(&sp, 0, sizeof(sp));
+  sp.logits = st.logits; sp.ldl = st.ldl; sp.act_utt = st.act_utt; sp.n_act = st.n_act; sp.src_slot = st.src_slot;
+  sp.force_tokens = st.force_tokens; sp.sampled_out = st.sampled_out;
+  sp.cfg = st.cfg; sp.n_utts = st.n_utts;
   sp.cfg_weight = st.cfg_weight; sp.rep_penalty = st.rep_penalty; sp.temperature = st.temperature;
   sp.min_p = st.min_p; sp.top_p = st.top_p; sp.eos_id = 6562;
   sp.tokens = st.tokens; sp.max_tokens = st.max_tokens; sp.n_gen = st.n_gen; sp.max_new = st.max_new; sp.done = st.done;
   sp.seen = st.seen; sp.positions = st.positions; sp.base_pos = st.base_pos; sp.x = st.x;
   sp.speech_emb = m.speech_emb.p; sp.speech_pos = m.speech_pos.p; sp.q_noise = st.q_noise; sp.seed = st.seed;
   sp.vocab = m.vocab; sp.turbo = m.gpt ? 1 : 0; sp.top_k = st.top_k; sp.bos_id = 6561; sp.wpe = m.gpt ? m.wpe.p : nullptr;
-  CBX_REQUIRE((st.sampler != 0) == m.gpt, "cbx_t3_state.sampler does not match the loaded backbone (1 = Turbo)");
-  CBX_REQUIRE(!(m.gpt && st.cfg), "the Turbo backbone runs without CFG rows");
   float* x = st.x;
-  // Tensor-core batches (S > 8): every GEMM operand travels as bf16 hi/lo planes written by its producer (RMSNorm,
-  // paged attention, SwiGLU epilogue) and is loaded by TMA -- no fp32->bf16 converter pass in the GEMM main loop.
-  // Small batches keep fp32 activations for the GEMV kernels.
+  // Tensor-core batches (S > 8): every GEMM operand travels as bf16 hi/lo planes written by its producer (resid_norm,
+  // paged attention, SwiGLU epilogue) and is loaded by TMA.  Small batches keep fp32 activations for the GEMV kernels.
   const bool planes = (S > 8 && ctx.gemm_impl == 0);
+  const int* m_live = planes ? st.m_live : nullptr;
   __nv_bfloat16* xn_hi = reinterpret_cast<__nv_bfloat16*>(xn);   __nv_bfloat16* xn_lo = xn_hi + (size_t)S * 1024;
   __nv_bfloat16* at_hi = reinterpret_cast<__nv_bfloat16*>(att);  __nv_bfloat16* at_lo = at_hi + (size_t)S * 1024;
   __nv_bfloat16* ac_hi = reinterpret_cast<__nv_bfloat16*>(act);  __nv_bfloat16* ac_lo = ac_hi + (size_t)S * 4096;
-  auto one_step = [&]() {
-    t3_sample(ctx, sp, n_act);
-    for (int l = 0; l < m.n_layers; ++l) {
-      T3Layer& ly = m.layers[l];
-      if (m.gpt) {
-        gpt_block(ctx, ly, x, S, xn, qkv, att, act, planes, true, [&](__nv_bfloat16* ah, __nv_bfloat16* al) {
-          rope_and_store_kv(ctx, qkv, 3072, kv, l, slot_row, st.positions, 1, S, m.rope_cos.p, m.rope_sin.p);
-          paged_decode_attention(ctx, qkv, 3072, kv, l, slot_row, S, st.positions, ah ? nullptr : att, 1024, scratch, nsplit, ah, al);
-        });
-        continue;
-      }
-      if (planes) {
-        rmsnorm(ctx, x, 1024, ly.ln1.p, nullptr, 1024, S, 1024, 1e-5f, nullptr, xn_hi, xn_lo);
-        GemmDev gq = gemm_args_linear(nullptr, 1024, S, ly.qkv, qkv, 3072);
-        gq.Ahi = xn_hi; gq.Alo = xn_lo; gq.ldab = 1024;
-        gemm(ctx, gq, ly.qkv);
-        rope_and_store_kv(ctx, qkv, 3072, kv, l, slot_row, st.positions, 1, S, m.rope_cos.p, m.rope_sin.p);
-        paged_decode_attention(ctx, qkv, 3072, kv, l, slot_row, S, st.positions, nullptr, 1024, scratch, nsplit, at_hi, at_lo);
-        GemmDev go = gemm_args_linear(nullptr, 1024, S, ly.o, x, 1024);
-        go.Ahi = at_hi; go.Alo = at_lo; go.ldab = 1024;
-        go.res = x; go.ldr = 1024;
-        gemm(ctx, go, ly.o);
-        rmsnorm(ctx, x, 1024, ly.ln2.p, nullptr, 1024, S, 1024, 1e-5f, nullptr, xn_hi, xn_lo);
-        GemmDev gg = gemm_args_linear(nullptr, 1024, S, ly.gu, nullptr, 0);
-        gg.Ahi = xn_hi; gg.Alo = xn_lo; gg.ldab = 1024;
-        gg.swiglu = 1; gg.Chi = ac_hi; gg.Clo = ac_lo; gg.ldcb = 4096;
-        gemm(ctx, gg, ly.gu);
-        GemmDev gd = gemm_args_linear(nullptr, 4096, S, ly.down, x, 1024);
-        gd.Ahi = ac_hi; gd.Alo = ac_lo; gd.ldab = 4096;
-        gd.res = x; gd.ldr = 1024;
-        gemm(ctx, gd, ly.down);
-        continue;
-      }
-      rmsnorm(ctx, x, 1024, ly.ln1.p, xn, 1024, S, 1024, 1e-5f, nullptr);
-      gemm(ctx, gemm_args_linear(xn, 1024, S, ly.qkv, qkv, 3072), ly.qkv);
-      rope_and_store_kv(ctx, qkv, 3072, kv, l, slot_row, st.positions, 1, S, m.rope_cos.p, m.rope_sin.p);
-      paged_decode_attention(ctx, qkv, 3072, kv, l, slot_row, S, st.positions, att, 1024, scratch, nsplit);
-      GemmDev go = gemm_args_linear(att, 1024, S, ly.o, x, 1024);
-      go.res = x; go.ldr = 1024;
-      gemm(ctx, go, ly.o);
-      rmsnorm(ctx, x, 1024, ly.ln2.p, xn, 1024, S, 1024, 1e-5f, nullptr);
-      GemmDev gg = gemm_args_linear(xn, 1024, S, ly.gu, act, 4096);
-      gg.swiglu = 1;
-      gemm(ctx, gg, ly.gu);
-      GemmDev gd = gemm_args_linear(act, 4096, S, ly.down, x, 1024);
-      gd.res = x; gd.ldr = 1024;
-      gemm(ctx, gd, ly.down);
-    }
-    if (m.gpt) layernorm(ctx, x, 1024, m.final_norm.p, m.final_norm_b.p, xn, 1024, S, 1024, 1e-5f, ACT_NONE, 1.f, nullptr, 0, nullptr);
-    else rmsnorm(ctx, x, 1024, m.final_norm.p, xn, 1024, S, 1024, 1e-5f, nullptr);
-    gemm(ctx, gemm_args_linear(xn, 1024, S, m.head, st.logits, st.ldl), m.head);
-  
+  PagedOpts po;
+  po.fuse_rope = 1; po.cos_t = m.rope_cos.p; po.sin_t = m.rope_sin.p; po.n_live = st.m_live;
+
+  t3_compact(ctx, st.act_utt, st.n_act, st.src_slot, st.slot_row, st.m_live, st.done, rows_per);
+  t3_sample(ctx, sp, cap);
+  // norm feeding a GEMM: x (+= split-K partials of the previous projection) -> norm -> planes / fp32
+  auto norm_in = [&](const float* prt, int ns, const float* bias, const DevVec& w, const DevVec& b) {
+    ResidNormDev rn;
+    memset(&rn, 0, sizeof(rn));
+    rn.x = x; rn.ldx = 1024; rn.part = prt; rn.nsplit = ns; rn.split_stride = (long)S * 1024; rn.ldp = 1024; rn.bias = bias;
+    rn.w = w.p; rn.b = b.p; rn.layernorm = m.gpt ? 1 : 0; rn.eps = 1e-5f;
+    if (planes) { rn.yhi = xn_hi; rn.ylo = xn_lo; } else rn.y = xn;
+    rn.ldy = 1024; rn.dim = 1024; rn.m_live = st.m_live;
+    resid_norm(ctx, rn, S);
   };
-  // Launch-bound small batches (B=1: ~250 launches per step): capture one step into a CUDA graph and replay it.
-  // Every launch parameter of a step is constant within one call (positions / tokens / done flags live on the device),
-  // so the graph of step 1 is valid for steps 2..n-1.  Step 0 runs directly so that lazy one-time setup
-  // (cudaFuncSetAttribute) happens outside the capture.  Needs a capturable (non-legacy) stream and no event timer.
-  const bool use_graph = h->decode_graph && !ctx.dry && !ctx.timer && n_steps >= 3 && ctx.stream != nullptr &&
-                         ctx.stream != cudaStreamLegacy;
+  auto feed = [&](GemmDev& g, const float* a32, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld) {
+    if (planes) { g.A = nullptr; g.Ahi = hi; g.Alo = lo; g.ldab = ld; } else g.A = a32;
+    g.m_live = m_live;
+  };
+  const float* pend = nullptr; int pend_ns = 0; const float* pend_bias = nullptr;   // projection output not yet added to x
+  for (int l = 0; l < m.n_layers; ++l) {
+    T3Layer& ly = m.layers[l];
+    norm_in(pend, pend_ns, pend_bias, ly.ln1, ly.ln1_b);
+    GemmDev gq = gemm_args_linear(xn, 1024, S, ly.qkv, qkv, 3072);
+    feed(gq, xn, xn_hi, xn_lo, 1024);
+    gq.tile_bn = tl.qkv_bn; gq.tile_dual = tl.qkv_dual;
+    gemm(ctx, gq, ly.qkv);
+    paged_decode_attention(ctx, qkv, 3072, kv, l, st.slot_row, S, st.positions, planes ? nullptr : att, 1024, scratch, nsplit,
+                           planes ? at_hi : nullptr, planes ? at_lo : nullptr, &po);
+    GemmDev go = gemm_args_linear(att, 1024, S, ly.o, part, 1024);
+    feed(go, att, at_hi, at_lo, 1024);
+    const float* o_bias = m.gpt ? ly.o.bias : nullptr;
+    go.bias = nullptr;
+    if (planes) { go.splitk = tl.o_split; go.split_stride = (long)S * 1024; go.tile_bn = tl.o_bn; }
+    gemm(ctx, go, ly.o);
+    norm_in(part, planes ? tl.o_split : 1, o_bias, ly.ln2, ly.ln2_b);
+    GemmDev gg = gemm_args_linear(xn, 1024, S, ly.gu, act, 4096);
+    feed(gg, xn, xn_hi, xn_lo, 1024);
+    if (m.gpt) gg.act = ACT_GELU_TANH; else gg.swiglu = 1;
+    if (planes) { gg.C = nullptr; gg.Chi = ac_hi; gg.Clo = ac_lo; gg.ldcb = 4096; }
+    gg.tile_bn = tl.gu_bn; gg.tile_dual = tl.gu_dual;
+    gemm(ctx, gg, ly.gu);
+    GemmDev gd = gemm_args_linear(act, 4096, S, ly.down, part, 1024);
+    feed(gd, act, ac_hi, ac_lo, 4096);
+    pend_bias = m.gpt ? ly.down.bias : nullptr;
+    gd.bias = nullptr;
+    if (planes) { gd.splitk = tl.down_split; gd.split_stride = (long)S * 1024; gd.tile_bn = tl.down_bn; }
+    gemm(ctx, gd, ly.down);
+    pend = part; pend_ns = planes ? tl.down_split : 1;
+  }
+  norm_in(pend, pend_ns, pend_bias, m.final_norm, m.final_norm_b);
+  GemmDev gh = gemm_args_linear(xn, 1024, S, m.head, st.logits, st.ldl);
+  feed(gh, xn, xn_hi, xn_lo, 1024);
+  gemm(ctx, gh, m.head);
+  ctx.ws.reset(mark);
+}
+
+static uint64_t fnv1a(const void* p, size_t n, uint64_t hsh = 1469598103934665603ull) {
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  for (size_t i = 0; i < n; ++i) { hsh ^= b[i]; hsh *= 1099511628211ull; }
+  return hsh;
+}
+
+void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap, int n_steps) {
+  T3Model& m = h->t3;
+  CBX_REQUIRE(m.ready, "t3 weights not finalized");
+  CBX_REQUIRE((st.sampler != 0) == m.gpt, "cbx_t3_state.sampler does not match the loaded backbone (1 = Turbo)");
+  CBX_REQUIRE(!(m.gpt && st.cfg), "the Turbo backbone runs without CFG rows");
+  CBX_REQUIRE(cap >= 1 && cap <= st.n_utts, "decode capacity");
+  if (ctx.dry) { decode_step(h, ctx, st, cap); return; }
+  CBX_REQUIRE(st.act_utt && st.n_act && st.src_slot && st.slot_row && st.m_live, "cbx_t3_state: device-side slot bookkeeping buffers");
+  // One executable graph per (state, capacity, workspace): captured from a single step, replayed for every step.
+  // Needs a capturable (non-legacy) stream and no per-launch event timer.
+  const bool use_graph = h->decode_graph && !ctx.timer && ctx.stream != nullptr && ctx.stream != cudaStreamLegacy;
   if (!use_graph) {
-    for (int step = 0; step < n_steps; ++step) one_step();
+    for (int step = 0; step < n_steps; ++step) decode_step(h, ctx, st, cap);
     return;
   }
-  if (h->decode_exec) { cudaGraphExecDestroy(h->decode_exec); h->decode_exec = nullptr; }   // previous call has drained
-  one_step();
-  const long before = ctx.launches;
-  cudaGraph_t graph = nullptr;
-  CBX_CHECK(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
-  try {
-    one_step();
-  } catch (...) {
-    cudaStreamEndCapture(ctx.stream, &graph);
-    if (graph) cudaGraphDestroy(graph);
-    throw;
+  uint64_t key = fnv1a(&st, sizeof(st));
+  const void* wsb = ctx.ws.base; const size_t wsc = ctx.ws.cap;
+  key = fnv1a(&cap, sizeof(cap), key); key = fnv1a(&wsb, sizeof(wsb), key); key = fnv1a(&wsc, sizeof(wsc), key);
+  key = fnv1a(&ctx.gemm_impl, sizeof(int), key);
+  auto it = h->decode_graphs.find(key);
+  if (it == h->decode_graphs.end()) {
+    if (h->decode_graphs.size() >= 48) {          // bound the cache: drop everything (states of finished batches)
+      for (auto& kvp : h->decode_graphs) cudaGraphExecDestroy(kvp.second.exec);
+      h->decode_graphs.clear();
+    }
+    const long before = ctx.launches;
+    cudaGraph_t graph = nullptr;
+    CBX_CHECK(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      decode_step(h, ctx, st, cap);
+    } catch (...) {
+      cudaStreamEndCapture(ctx.stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CBX_CHECK(cudaStreamEndCapture(ctx.stream, &graph));
+    DecodeGraph dg;
+    dg.launches = ctx.launches - before;
+    ctx.launches = before;
+    cudaError_t ge = cudaGraphInstantiate(&dg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CBX_CHECK(ge);
+    it = h->decode_graphs.emplace(key, dg).first;
   }
-  CBX_CHECK(cudaStreamEndCapture(ctx.stream, &graph));
-  const long per_step = ctx.launches - before;
-  cudaError_t ge = cudaGraphInstantiate(&h->decode_exec, graph, 0);
-  cudaGraphDestroy(graph);
-  CBX_CHECK(ge);
-  for (int step = 1; step < n_steps; ++step) CBX_CHECK(cudaGraphLaunch(h->decode_exec, ctx.stream));
-  ctx.launches += per_step * (long)(n_steps - 2);     // the captured step was counted once, it ran n_steps - 1 times
+  for (int step = 0; step < n_steps; ++step) CBX_CHECK(cudaGraphLaunch(it->second.exec, ctx.stream));
+  ctx.launches += it->second.launches * (long)n_steps;
 }
 
 }  // namespace cbx

@@ -102,7 +102,10 @@ class Engine:
         self._ws = None
         self.t3_layers = 0
         self.t3_turbo = False       # GPT-2 backbone (reference tts_turbo.py): no CFG, learned absolute positions
-        self._decode_stream = None  # set_decode_graph(True): decode steps replay a CUDA graph on a side stream
+        self._decode_stream = torch.cuda.Stream(self.device)   # decode steps replay CUDA graphs: needs a capturable stream
+        self._t3_bufs = {}          # persistent T3 state buffers keyed by shape (stable pointers -> decode graphs are reused)
+        self._pinned = []           # pinned host scalars for the asynchronous n_act snapshots
+        self.decode_steps_per_call = 16
         self.meanflow = False
         # algorithmic-traffic bookkeeping for bench.py's roofline (bytes the paged decode attention must read)
         self.stats = dict(paged_bytes=0.0, paged_launches=0, decode_steps=0, decode_row_steps=0)
@@ -114,7 +117,7 @@ class Engine:
             shape = (C.c_int64 * t.dim())(*t.shape)
             self.h.call("cbx_load_tensor", (prefix + k).encode(), C.c_void_p(t.data_ptr()), t.dim(), shape)
 
-    def load_t3(self, sd, max_pos=4608):
+    def load_t3(self, sd, max_pos=6400):
         """State dict with the reference key names: Llama backbone (`tfmr.layers.*`, t3.py:49-85) or the Turbo GPT-2
         backbone (`tfmr.h.*`, `tfmr.wpe`, tts_turbo.py:151-166; `tfmr.wte` is ignored like the reference deletes it)."""
         sd = {k: v for k, v in sd.items() if not k.startswith("text_head") and not k.startswith("tfmr.embed_tokens")
@@ -129,6 +132,9 @@ class Engine:
             cos, sin = llama3_rope_tables(max_pos)
             self.t3_layers = len({k.split(".")[2] for k in sd if k.startswith("tfmr.layers.")})
         self._load("t3.", {"rope_cos": cos, "rope_sin": sin})
+        self.t3_max_pos = int(cos.shape[0])
+        self.t3_speech_pos_rows = int(sd["speech_pos_emb.emb.weight"].shape[0]) if "speech_pos_emb.emb.weight" in sd else 1 << 30
+        self.t3_text_pos_rows = int(sd["text_pos_emb.emb.weight"].shape[0]) if "text_pos_emb.emb.weight" in sd else 1 << 30
         self.h.call("cbx_finalize_weights", b"t3")
 
     def load_flow(self, sd, max_len=5000):
@@ -166,10 +172,34 @@ class Engine:
         self.h.set_option("cfm_act", fmt)
 
     def set_decode_graph(self, on=True):
-        """Launch-bound small batches: steps 2..n of every cbx_t3_decode call replay a CUDA graph captured from step 1
-        (stream capture needs a non-default stream, so decode then runs on a side stream)."""
+        """Default on: every decode step replays a CUDA graph captured once per (state buffers, capacity); stream
+        capture needs a non-default stream, so decode runs on a side stream.  Off = direct launches (debugging)."""
         self.h.set_option("decode_graph", "1" if on else "0")
-        self._decode_stream = torch.cuda.Stream(self.device) if on else None
+
+    def _t3_state_buffers(self, key, make):
+        """State tensors of a T3 batch; the most recent shape is kept so that a repeated batch shape reuses the same
+        device pointers (and with them the cached decode graphs and the KV pool allocation)."""
+        if key not in self._t3_bufs:
+            self._t3_bufs.clear()            # one shape at a time: the KV pool can be tens of GB
+            self._t3_bufs[key] = make()
+        return self._t3_bufs[key]
+
+    @staticmethod
+    def decode_capacity(n, rows_per):
+        """Slots launched per decode step for <= n live utterances: exact up to 8 rows (GEMV kernels), then powers of two
+        up to one 128-row GEMM tile, then whole tiles."""
+        n = max(1, int(n))
+        rows = n * rows_per
+        if rows <= 8:
+            r = 2 if rows <= 2 else 4 if rows <= 4 else 8
+            return max(1, r // rows_per)
+        per_tile = 128 // rows_per
+        if n <= per_tile:
+            c = 1
+            while c < n:
+                c *= 2
+            return c
+        return ((n + per_tile - 1) // per_tile) * per_tile
 
     # ------------------------------------------------------------------ T3
     def t3_cond(self, speaker_emb, prompt_tokens, emotion_adv):
@@ -189,7 +219,7 @@ class Engine:
 
     def t3_generate(self, text_tokens, cond, voice_ids=None, max_new_tokens=1000, cfg_weight=0.5, temperature=0.8,
                     top_p=1.0, min_p=0.05, repetition_penalty=1.2, q_noise=None, seed=0, kv_dtype="bf16",
-                    max_sync_steps=32, return_state=False, top_k=0):
+                    max_sync_steps=None, return_state=False, top_k=0, force_tokens=None):
         """Batched equivalent of T3.inference (t3.py:225-390) or, with a Turbo checkpoint loaded, of
         T3.inference_turbo (t3.py:392-468: no CFG, processors temperature -> top_k -> top_p -> repetition penalty,
         min_p unused; max_new_tokens counts the token sampled from the prefill, i.e. max_gen_len + 1).
@@ -221,35 +251,70 @@ class Engine:
         # paged KV cache: just enough pages per row for prefill + budget
         pages_per_row = (np.repeat(s0 + np.asarray(max_new, dtype=np.int32), rp) + PAGE_TOKENS - 1) // PAGE_TOKENS
         max_pages = int(pages_per_row.max())
-        page_table = np.zeros((R, max_pages), dtype=np.int32)
-        nxt = 0
-        for r in range(R):
-            page_table[r, :pages_per_row[r]] = np.arange(nxt, nxt + pages_per_row[r])
-            nxt += int(pages_per_row[r])
-        n_pages = nxt
+        first_page = np.concatenate([[0], np.cumsum(pages_per_row)[:-1]]).astype(np.int64)
+        page_table = first_page[:, None] + np.arange(max_pages, dtype=np.int64)[None, :]
+        page_table = np.where(np.arange(max_pages)[None, :] < pages_per_row[:, None], page_table, 0).astype(np.int32)
+        n_pages = int(pages_per_row.sum())
         kvt = torch.float32 if kv_dtype in ("fp32", "f32", torch.float32) else torch.bfloat16
         L = self.t3_layers
-        kv = torch.empty(L, n_pages, 2, 16, PAGE_TOKENS, 64, dtype=kvt, device=dev)     # layer-major (include/cbx.h)
+        max_tokens = int(max(max_new))
+        # position tables of the checkpoint bound what may be generated (reference: learned tables of 2050 / 4100 rows,
+        # RoPE table built for max_pos rows)
+        if int(row_len.max()) + max_tokens > self.t3_max_pos:
+            raise CbxError(f"prefill length {int(row_len.max())} + max_new_tokens {max_tokens} exceeds the {self.t3_max_pos} "
+                           "positions of the T3 position tables")
+        if not turbo and (max_tokens + 1 > self.t3_speech_pos_rows or int(n_text.max()) > self.t3_text_pos_rows):
+            raise CbxError(f"max_new_tokens {max_tokens} / text length {int(n_text.max())} exceed the learned position tables "
+                           f"({self.t3_speech_pos_rows} speech, {self.t3_text_pos_rows} text rows)")
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+        def make():
+            return dict(
+                kv=torch.empty(L, n_pages, 2, 16, PAGE_TOKENS, 64, dtype=kvt, device=dev),      # layer-major (include/cbx.h)
+                page_table=torch.empty(R, max_pages, dtype=torch.int32, device=dev),
+                positions=torch.empty(R, dtype=torch.int32, device=dev), base_pos=torch.empty(R, dtype=torch.int32, device=dev),
+                tokens=torch.empty(B, max_tokens, dtype=torch.int32, device=dev),
+                n_gen=torch.empty(B, dtype=torch.int32, device=dev), max_new=torch.empty(B, dtype=torch.int32, device=dev),
+                done=torch.empty(B, dtype=torch.int32, device=dev),
+                seen=torch.empty(B, SPEECH_VOCAB, dtype=torch.uint8, device=dev),
+                x=torch.empty(R, 1024, dtype=torch.float32, device=dev),
+                logits=torch.empty(R, LDL, dtype=torch.float32, device=dev),
+                act_utt=torch.empty(B, dtype=torch.int32, device=dev), n_act=torch.empty(1, dtype=torch.int32, device=dev),
+                src_slot=torch.empty(B, dtype=torch.int32, device=dev), slot_row=torch.empty(R, dtype=torch.int32, device=dev),
+                m_live=torch.empty(1, dtype=torch.int32, device=dev),
+                force=torch.empty(B, max_tokens, dtype=torch.int32, device=dev),
+                sampled=torch.empty(B, max_tokens, dtype=torch.int32, device=dev))
+
+        st_t = self._t3_state_buffers((B, R, max_tokens, n_pages, max_pages, kvt, L), make)
+        kv = st_t["kv"]
+        st_t["page_table"].copy_(t(page_table))
+        st_t["base_pos"].copy_(t(row_len))
+        st_t["max_new"].copy_(t(np.asarray(max_new, dtype=np.int32)))
+        for k in ("positions", "tokens", "n_gen", "done", "seen", "x", "logits", "src_slot", "sampled"):
+            st_t[k].zero_()
+        st_t["seen"][:, START_SPEECH] = 1          # repetition penalty history starts with BOS (t3.py:316,347)
+        st_t["act_utt"].copy_(torch.arange(B, dtype=torch.int32, device=dev))
+        st_t["slot_row"].copy_(torch.arange(R, dtype=torch.int32, device=dev))
+        st_t["n_act"].fill_(B)
+        st_t["m_live"].fill_(R)
+        forced = None
+        if force_tokens is not None:               # teacher forcing (parity tests): [B][<= max_tokens] ids
+            st_t["force"].zero_()
+            for b in range(B):
+                ft = torch.as_tensor(force_tokens[b]).reshape(-1).to(torch.int32)
+                st_t["force"][b, :ft.numel()] = ft.to(dev)
+            forced = st_t["force"]
         d = dict(tok_row=t(tok_row), tok_pos=t(tok_pos), row_start=t(row_start), row_len=t(row_len),
                  text_flat=t(text_flat), row_text_start=t(row_text_start), row_ntext=t(row_ntext),
-                 row_voice=t(row_voice), row_uncond=t(row_uncond), page_table=t(page_table))
-        max_tokens = int(max(max_new))
-        st_t = dict(
-            positions=torch.zeros(R, dtype=torch.int32, device=dev), base_pos=t(row_len),
-            tokens=torch.zeros(B, max_tokens, dtype=torch.int32, device=dev),
-            n_gen=torch.zeros(B, dtype=torch.int32, device=dev), max_new=t(np.asarray(max_new, dtype=np.int32)),
-            done=torch.zeros(B, dtype=torch.int32, device=dev),
-            seen=torch.zeros(B, SPEECH_VOCAB, dtype=torch.uint8, device=dev),
-            x=torch.zeros(R, 1024, dtype=torch.float32, device=dev),
-            logits=torch.zeros(R, LDL, dtype=torch.float32, device=dev))
-        st_t["seen"][:, START_SPEECH] = 1          # repetition penalty history starts with BOS (t3.py:316,347)
+                 row_voice=t(row_voice), row_uncond=t(row_uncond))
         qn = q_noise.to(dev, torch.float32).contiguous() if q_noise is not None else None
-        st = T3State(B, R, cfg, _ptr(kv), 1 if kvt == torch.float32 else 0, PAGE_TOKENS, _ptr(d["page_table"]), max_pages, n_pages,
+        st = T3State(B, R, cfg, _ptr(kv), 1 if kvt == torch.float32 else 0, PAGE_TOKENS, _ptr(st_t["page_table"]), max_pages, n_pages,
                      _ptr(st_t["positions"]), _ptr(st_t["base_pos"]), _ptr(st_t["tokens"]), max_tokens,
                      _ptr(st_t["n_gen"]), _ptr(st_t["max_new"]), _ptr(st_t["done"]), _ptr(st_t["seen"]),
                      _ptr(st_t["x"]), _ptr(st_t["logits"]), LDL, float(cfg_weight), float(repetition_penalty),
-                     float(temperature), float(min_p), float(top_p), _ptr(qn), int(seed), 1 if turbo else 0, int(top_k))
+                     float(temperature), float(min_p), float(top_p), _ptr(qn), int(seed), 1 if turbo else 0, int(top_k),
+                     _ptr(st_t["act_utt"]), _ptr(st_t["n_act"]), _ptr(st_t["src_slot"]), _ptr(st_t["slot_row"]),
+                     _ptr(st_t["m_live"]), _ptr(forced), _ptr(st_t["sampled"]) if forced is not None else C.c_void_p(0))
         ws = self.workspace(self.h.lib.cbx_t3_workspace_bytes(self.h.h, n_tok, R))
         cond = cond.to(dev, torch.float32).contiguous()
         self.h.call("cbx_t3_prefill", C.byref(st), n_tok, _ptr(d["tok_row"]), _ptr(d["tok_pos"]), _ptr(d["row_start"]),
@@ -258,56 +323,53 @@ class Engine:
                     _ptr(ws), ws.numel(), self._stream())
         if return_state == "prefill":
             return st_t
-        # decode with host-driven retirement of finished utterances
-        if self._decode_stream is not None:
-            self._decode_stream.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(self._decode_stream):
-                self._decode_loop(st, st_t, B, rp, max_new, max_sync_steps, s0, kvt, L, ws)
-            torch.cuda.current_stream(self.device).wait_stream(self._decode_stream)
-        else:
-            self._decode_loop(st, st_t, B, rp, max_new, max_sync_steps, s0, kvt, L, ws)
+        # decode: graph replays on the side stream, finished utterances retire on the device
+        self._decode_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._decode_stream):
+            self._decode_loop(st, st_t, B, rp, max_new, ws)
+        torch.cuda.current_stream(self.device).wait_stream(self._decode_stream)
         toks = st_t["tokens"].cpu()
         n_gen = st_t["n_gen"].cpu()
         out = [toks[b, :int(n_gen[b])].to(torch.int64) for b in range(B)]
+        # algorithmic traffic of the paged decode attention (bench.py roofline): step i of an utterance reads its
+        # s0 + i + 1 cached tokens, K and V, all heads, every layer, both CFG rows
+        elt = 4 if kvt == torch.float32 else 2
+        ng = n_gen.numpy().astype(np.int64)
+        ctx_tok = (s0.astype(np.int64) * ng + ng * (ng + 1) // 2).sum()
+        self.stats["paged_bytes"] += float(ctx_tok) * rp * 2 * 1024 * elt * L
+        self.stats["decode_row_steps"] += int(ng.sum()) * rp
         if return_state:
             return out, st_t
         return out
 
-    def _decode_loop(self, st, st_t, B, rp, max_new, max_sync_steps, s0, kvt, L, ws):
-        dev = self.device
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        act = np.arange(B, dtype=np.int32)
-        n_gen_h = np.zeros(B, dtype=np.int64)
+    def _decode_loop(self, st, st_t, B, rp, max_new, ws):
+        """Host side of the decode loop: no blocking device->host read.  The device retires finished utterances every
+        step (t3_compact_kernel); the host only picks the launch capacity from what it knows for sure -- the budgets --
+        and from asynchronous snapshots of the device's live count (pinned memory + event, polled without waiting)."""
         budget = np.asarray(max_new, dtype=np.int64)
-        import os as _os
-        _trace = _os.environ.get("CBX_TRACE")
-        while len(act):
-            remaining = budget[act] - n_gen_h[act]
-            if _trace:
-                print("[cbx] decode", len(act), int(remaining.min()), int(n_gen_h.max()), flush=True)
-            k = int(max(1, min(max_sync_steps, remaining.min())))
-            d_act = t(act)
-            slot_row = (np.repeat(act * rp, rp) + np.tile(np.arange(rp), len(act))).astype(np.int32)
-            d_slot = t(slot_row)
-            self.h.call("cbx_t3_decode", C.byref(st), _ptr(d_act), _ptr(d_slot), len(act), k, _ptr(ws), ws.numel(),
-                        self._stream())
-            # step j of this call feeds token n_gen+j at rope position S0+n_gen+j and attends S0+n_gen+j+1 tokens
-            elt = 4 if kvt == torch.float32 else 2
-            ctx_tok = (s0[act].astype(np.int64) + n_gen_h[act])[:, None] + np.arange(k)[None, :] + 1
-            self.stats["paged_bytes"] += float(ctx_tok.sum()) * rp * 2 * 1024 * elt * L
-            self.stats["paged_launches"] += k * L
+        total = int(budget.max())
+        steps_done, live_seen = 0, B
+        pending = []
+        while steps_done < total:
+            while pending and pending[0][0].query():
+                ev, buf = pending.pop(0)
+                live_seen = min(live_seen, int(buf[0]))
+                self._pinned.append((ev, buf))
+            live = min(live_seen, int((budget > steps_done).sum()))
+            if live <= 0:
+                break
+            cap = self.decode_capacity(live, rp)
+            k = min(self.decode_steps_per_call, total - steps_done)
+            self.h.call("cbx_t3_decode", C.byref(st), min(cap, B), k, _ptr(ws), ws.numel(), self._stream())
+            steps_done += k
             self.stats["decode_steps"] += k
-            self.stats["decode_row_steps"] += k * len(act) * rp
-            done_h = st_t["done"].cpu().numpy()          # device->host sync every k steps (reference: every step)
-            n_gen_h = st_t["n_gen"].cpu().numpy().astype(np.int64)
-            keep = done_h[act] == 0
-            if keep.all():
-                continue
-            keep_slots = np.repeat(np.nonzero(keep)[0] * rp, rp) + np.tile(np.arange(rp), int(keep.sum()))
-            act = act[keep]
-            if len(act):
-                d_keep = t(keep_slots.astype(np.int32))
-                self.h.call("cbx_t3_compact", C.byref(st), _ptr(d_keep), len(keep_slots), _ptr(ws), ws.numel(), self._stream())
+            self.stats["paged_launches"] += k * self.t3_layers
+            ev, buf = self._pinned.pop() if self._pinned else (torch.cuda.Event(), torch.zeros(1, dtype=torch.int32).pin_memory())
+            buf.copy_(st_t["n_act"], non_blocking=True)
+            ev.record()
+            pending.append((ev, buf))
+        for ev, buf in pending:
+            self._pinned.append((ev, buf))
 
     # ------------------------------------------------------------------ flow
     def flow_mel(self, tokens, ref_dicts, z=None, n_timesteps=None, cfg_rate=0.7, return_mu=False):
@@ -359,11 +421,6 @@ class Engine:
             s2 = int(L2.starts[b])
             out.append(x[s2 + 2 * np_len[b]:s2 + 2 * n[b]].t().contiguous())      # drop prompt frames (flow.py:196)
         return out
-
-    def cfm_nfe(self, mu, spk, cond, x, t_value):
-        """Single estimator evaluation (unit-test hook): Euler step with dt=1 from x=0 is not expressible, so
-        tests use cfm_solve with n_timesteps=1 instead."""
-        raise NotImplementedError
 
     # ------------------------------------------------------------------ HiFT
     def _hift_geom(self, T):

@@ -53,8 +53,8 @@ int cbx_version(void);
 /* options (all per handle):
  *   "gemm" = "tc"|"simt", "attn" = "tc"|"simt"   SIMT = plain reference kernels for bisecting (debug)
  *   "time_kernel" = class name                   see cbx_timer_read below
- *   "decode_graph" = "1"|"0"                     steps 2..n of a cbx_t3_decode call replay a CUDA graph of step 1 (default 0;
- *                                                the call must then be issued on a capturable, non-default stream)
+ *   "decode_graph" = "1"|"0"                     every decode step replays a CUDA graph captured once per (state, capacity)
+ *                                                (default 1; the call must then be issued on a capturable, non-default stream)
  *   "attn_prec" = "bf16x3"|"fp16"                operand format of the CFM attention: bf16 hi/lo planes, 3 MMA terms (default)
  *                                                or one fp16 plane, 1 term (opt-in)
  *   "cfm_act" = "bf16x2"|"fp16"                  operand format of the CFM transformer-block GEMM inputs (default bf16 hi/lo);
@@ -99,6 +99,17 @@ typedef struct {
                               1 = T3.inference_turbo order (temperature, top-k, top-p, repetition penalty; t3.py:396-404);
                               must match the loaded backbone (Llama / GPT-2) */
   int top_k;               /* sampler 1 only; <= 0 disables */
+  /* device-side retirement (replaces the per-step host sync of t3.py:366): caller-owned device buffers that the decode
+   * step keeps up to date.  Before the first cbx_t3_decode: act_utt = 0..n_utts-1, n_act = n_utts; the rest is scratch. */
+  int* act_utt;            /* device [n_utts] active utterance ids, packed at the front (stable order) */
+  int* n_act;              /* device scalar: live entries of act_utt; the host may poll it asynchronously */
+  int* src_slot;           /* device [n_utts] scratch */
+  int* slot_row;           /* device [n_rows] physical KV row of each live slot */
+  int* m_live;             /* device scalar: live decode rows */
+  /* teacher forcing (parity tests): when set, step i of utterance u feeds force_tokens[u][i] (stride max_tokens) and
+   * the id the sampler picked itself goes to sampled_out[u][i] (optional) */
+  const int* force_tokens;
+  int* sampled_out;
 } cbx_t3_state;
 
 /* replaces T3.prepare_conditioning + T3CondEnc.forward + Perceiver.forward
@@ -120,11 +131,12 @@ int cbx_t3_prefill(cbx_handle* h, const cbx_t3_state* st, int n_tok, const int* 
  * penalty, temperature, min-p, top-p, multinomial) then one cached forward, for the n_act active utterances.
  * With st->sampler == 1 it is the loop of T3.inference_turbo (t3.py:426-461): the first token comes from the prefill
  * logits without an EOS check, history for the repetition penalty is BOS for that token and the generated ids after */
-int cbx_t3_decode(cbx_handle* h, const cbx_t3_state* st, const int* act_utt, const int* slot_row, int n_act,
-                  int n_steps, void* ws, size_t ws_bytes, cbx_stream stream);
-/* keep only slots whose utterance is listed in new_act (gathers x / logits rows; keep_slot = old slot index) */
-int cbx_t3_compact(cbx_handle* h, const cbx_t3_state* st, const int* keep_slot, int n_keep_slots, void* ws,
-                   size_t ws_bytes, cbx_stream stream);
+/* `capacity` = slots launched per step: any upper bound of the live utterances (st->n_act after the step's own
+ * compaction); finished utterances are retired on the device every step, the host only shrinks `capacity` when it
+ * learns (asynchronously) that fewer are left.  Each step = one CUDA graph replay (option "decode_graph", default on:
+ * the call must then be issued on a capturable, non-default stream). */
+int cbx_t3_decode(cbx_handle* h, const cbx_t3_state* st, int capacity, int n_steps, void* ws, size_t ws_bytes,
+                  cbx_stream stream);
 size_t cbx_t3_workspace_bytes(cbx_handle* h, int n_tok_prefill, int n_rows);
 
 /* ---- S3Gen flow: token -> mel (reference src/chatterbox/models/s3gen/) ---------------------------- */
@@ -180,6 +192,19 @@ int cbx_test_attention(cbx_handle* h, const float* Q, const float* K, const floa
 /* tcgen05 attention (CFM path): qkv fp32 [rows][3*n_heads*64] (q | k | v), split to bf16 hi/lo planes in ws */
 int cbx_test_attention_tc(cbx_handle* h, const float* qkv, float* O, int n_heads, const cbx_layout* L, float scale,
                           void* ws, size_t ws_bytes, cbx_stream stream);
+
+/* paged decode attention of one layer over a caller-built cache pages[n_pages][2][16][32][64] (kv_dtype 0 = bf16, 1 = fp32):
+ * qkv [n_slots][3072] fp32 (q | k | v of the step's token), out [n_slots][1024].  impl 0 = bulk-copy staged kernel,
+ * 1 = __ldg kernel.  fuse_rope = 1: qkv is un-rotated; the kernel applies RoPE (cos_t / sin_t [pos][32]), appends
+ * k / v at `positions` and attends to them. */
+int cbx_test_paged_decode(cbx_handle* h, const float* qkv, void* pages, int kv_dtype, int n_pages, const int* page_table,
+                          int max_pages, const int* slot_row, const int* positions, int n_slots, int nsplit, int impl,
+                          int fuse_rope, const float* cos_t, const float* sin_t, float* out, void* ws, size_t ws_bytes,
+                          cbx_stream stream);
+/* the decode-path projection: A [M][K] as bf16 hi/lo planes x W [N][K]^T with split-K partial sums reduced in a fixed
+ * order (N <= 1024).  tile_bn 0 = heuristic. */
+int cbx_test_gemm_splitk(cbx_handle* h, const float* A, const float* w_host, int M, int N, int K, int splitk, int tile_bn,
+                         float* C, void* ws, size_t ws_bytes, cbx_stream stream);
 
 #ifdef __cplusplus
 }

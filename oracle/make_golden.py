@@ -187,7 +187,7 @@ def golden_turbo():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(min(16, len(os.sched_getaffinity(0))))
-    which = sys.argv[1:] or ["t3", "s3gen", "variants", "turbo"]
+    which = [a for a in sys.argv[1:] if not a.startswith("long_")] or ([] if sys.argv[1:] else ["t3", "s3gen", "variants", "turbo"])
     if "t3" in which:
         golden_t3()
     if "s3gen" in which:
@@ -196,3 +196,93 @@ if __name__ == "__main__":
         golden_meanflow_and_mtl()
     if "turbo" in which:
         golden_turbo()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Round 2: fixtures at the benchmarked configuration (context >= 1000 tokens, CFM T >= 2000 frames).
+#   python -m oracle.make_golden long_t3 long_flow
+# ------------------------------------------------------------------------------------------------------------------
+LONG_T3_STEPS = 900
+LONG_T3_TAPS = (1, 64, 256, 512, 768, 900)      # logits kept after consuming this many generated tokens
+
+
+def golden_t3_long():
+    """The reference's own T3.inference for 900 greedy steps on a 150-token text (context 188 -> 1088 tokens, the
+    bench regime), then a teacher-forced pass of the reference backbone (`t3.patched_model`, DynamicCache) over the
+    reference's ids that keeps the logits of both CFG rows at LONG_T3_TAPS."""
+    R.install()
+    from chatterbox.models.t3.modules.cond_enc import T3Cond
+    sd = W.make_t3_weights(0)
+    t3 = R.build_t3()
+    t3.load_state_dict(sd, strict=True)
+    c3, _ = W.make_conds()
+    mk = lambda: T3Cond(speaker_emb=c3["speaker_emb"], cond_prompt_speech_tokens=c3["cond_prompt_speech_tokens"],
+                        emotion_adv=c3["emotion_adv"])
+    text = text_pair(41, 150)
+    torch.manual_seed(17)
+    toks = t3.inference(t3_cond=mk(), text_tokens=text, max_new_tokens=LONG_T3_STEPS, temperature=0.8, top_p=1.0,
+                        min_p=1.0, repetition_penalty=1.2, cfg_weight=0.5)
+    ids = toks[0]
+    print("t3 long: generated", ids.numel(), "ids, eos" if (ids == 6562).any() else "no eos", ids[:8].tolist())
+    # teacher-forced pass: same call sequence as t3.py:320-386 (prefill with both BOS embeddings, then one token per step)
+    embeds, _ = t3.prepare_input_embeds(t3_cond=mk(), text_tokens=text,
+                                        speech_tokens=6561 * torch.ones_like(text[:, :1]), cfg_weight=0.5)
+    bos = t3.speech_emb(torch.tensor([[6561]])) + t3.speech_pos_emb.get_fixed_embedding(0)
+    x = torch.cat([embeds, torch.cat([bos, bos])], dim=1)
+    taps = {}
+    with torch.inference_mode():
+        o = t3.patched_model(inputs_embeds=x, past_key_values=None, use_cache=True, output_hidden_states=True,
+                             return_dict=True)
+        past = o.past_key_values
+        for i in range(ids.numel()):
+            e = t3.speech_emb(ids[i].view(1, 1)) + t3.speech_pos_emb.get_fixed_embedding(i + 1)
+            e = torch.cat([e, e])
+            o = t3.patched_model(inputs_embeds=e, past_key_values=past, output_hidden_states=True, return_dict=True)
+            past = o.past_key_values
+            if (i + 1) in LONG_T3_TAPS:
+                taps[i + 1] = o.logits[:, -1, :].clone()
+                print("  tap", i + 1, float(taps[i + 1].abs().max()))
+    torch.save(dict(weights_seed=0, conds_seed=1234, text_tokens=text, tokens=toks.clone(), taps=taps,
+                    s0=int(x.shape[1])), os.path.join(OUT, "t3_long_golden.pt"))
+
+
+def golden_flow_long():
+    """CausalMaskedDiffWithXvec.inference at T = 2(250 + 770) = 2040 mel frames (the bench's long-utterance regime: 32
+    query tiles / 32 key blocks per head in the tcgen05 attention) + one estimator evaluation at t = 0.3."""
+    R.install()
+    fsd = W.make_flow_weights(0)
+    flow = R.build_flow()
+    flow.load_state_dict(fsd, strict=True)
+    np_, n, tok_seed, rng_seed = 250, 770, 15, 31
+    _, cg = W.make_conds(seed=1234, n_gen_prompt=np_)
+    tok = torch.randint(0, 6561, (1, n), generator=torch.Generator().manual_seed(tok_seed))
+    x = fsd["input_embedding.weight"][torch.cat([cg["prompt_token"], tok], 1)]
+    with torch.inference_mode():
+        h, _ = flow.encoder(x, torch.tensor([x.shape[1]]))
+        mu = flow.encoder_proj(h)
+    torch.manual_seed(rng_seed)
+    z = torch.randn(1, 80, 2 * (np_ + n))
+    torch.manual_seed(rng_seed)
+    mel, _ = flow.inference(token=tok, token_len=torch.tensor([n]), prompt_token=cg["prompt_token"],
+                            prompt_token_len=cg["prompt_token_len"], prompt_feat=cg["prompt_feat"],
+                            prompt_feat_len=None, embedding=cg["embedding"], finalize=True, n_timesteps=10)
+    est = flow.decoder.estimator
+    T = mu.shape[1]
+    with torch.inference_mode():
+        spk = flow.spk_embed_affine_layer(F.normalize(cg["embedding"], dim=1))
+        cond = torch.zeros(1, 80, T)
+        cond[:, :, :2 * np_] = cg["prompt_feat"].transpose(1, 2)
+        v = est(z, torch.ones(1, 1, T), mu.transpose(1, 2).contiguous(), torch.tensor([0.3]), spk, cond)
+    print("flow long", mel.shape, float(mel.std()), float(v.std()))
+    torch.save(dict(weights_seed=0, n_prompt=np_, n=n, tok_seed=tok_seed, rng_seed=rng_seed, tokens=tok,
+                    mu_sample=mu[:, ::16].clone(), mel=mel.clone(), nfe_t=0.3, nfe_v=v.clone(),
+                    # z is re-drawn from rng_seed by the test (torch CPU randn is reproducible); checksum to be sure
+                    z_head=z[..., :8].clone(), z_sum=float(z.double().sum())),
+               os.path.join(OUT, "flow_long_golden.pt"))
+
+
+if __name__ == "__main__" and any(a.startswith("long_") for a in sys.argv[1:]):
+    if "long_t3" in sys.argv[1:]:
+        golden_t3_long()
+    if "long_flow" in sys.argv[1:]:
+        golden_flow_long()

@@ -204,3 +204,113 @@ def test_linear_gemm_dual_cta_tiles():
     ref = F.gelu((A.double() @ w.double().t().cuda() + b.double().cuda()).float()) + res
     err = relerr(C_, ref)
     assert err < 3e-5, f"rel err {err}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: decode-path kernels
+# ---------------------------------------------------------------------------------------------------------------------
+def _paged_case(S_list, kv_dtype, seed, fuse):
+    """Random paged cache for rows with context lengths S_list (token S-1 is the step's own token)."""
+    from chatterbox_b200.engine import llama3_rope_tables
+    g = torch.Generator().manual_seed(seed)
+    R = len(S_list)
+    pages_per_row = [(s + 31) // 32 + 1 for s in S_list]
+    n_pages = sum(pages_per_row)
+    perm = torch.randperm(n_pages, generator=g)                 # pages of a row are scattered over the pool
+    max_pages = max(pages_per_row)
+    pt = torch.zeros(R, max_pages, dtype=torch.int32)
+    o = 0
+    for r in range(R):
+        pt[r, :pages_per_row[r]] = perm[o:o + pages_per_row[r]].to(torch.int32)
+        o += pages_per_row[r]
+    dt = torch.float32 if kv_dtype == "fp32" else torch.bfloat16
+    pool = (torch.randn(n_pages, 2, 16, 32, 64, generator=g) * 0.7).to(dt)
+    qkv = torch.randn(R, 3072, generator=g)
+    cos, sin = llama3_rope_tables(max(S_list) + 8)
+    return pt, pool, qkv, cos, sin
+
+
+def _paged_reference(pt, pool, qkv, cos, sin, S_list, fuse):
+    """fp64 softmax(q k^T / 8) v per row and head from the gathered cache (+ RoPE / append of the new token when fused)."""
+    R = len(S_list)
+    out = torch.zeros(R, 1024, dtype=torch.float64)
+    new_k = torch.zeros(R, 16, 64)
+    for r, S in enumerate(S_list):
+        pos = S - 1
+        pages = pt[r, :(S + 31) // 32].long()
+        K = pool[pages, 0].double().permute(1, 0, 2, 3).reshape(16, -1, 64)[:, :S].clone()      # [16, S, 64]
+        V = pool[pages, 1].double().permute(1, 0, 2, 3).reshape(16, -1, 64)[:, :S].clone()
+        q = qkv[r, :1024].view(16, 64)
+        if fuse:
+            c = torch.cat([cos[pos], cos[pos]]); s = torch.cat([sin[pos], sin[pos]])
+            rot = lambda x: x * c + torch.cat([-x[:, 32:], x[:, :32]], -1) * s
+            q = rot(q)
+            k = rot(qkv[r, 1024:2048].view(16, 64)).to(pool.dtype)
+            v = qkv[r, 2048:].view(16, 64).to(pool.dtype)
+            new_k[r] = k.float()
+            K[:, pos] = k.double(); V[:, pos] = v.double()
+        sc = torch.einsum("hd,hsd->hs", q.double(), K) * 0.125
+        p = torch.softmax(sc, -1)
+        out[r] = torch.einsum("hs,hsd->hd", p, V).reshape(-1)
+    return out, new_k
+
+
+@pytest.mark.parametrize("kv_dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("impl,fuse", [(0, 0), (0, 1), (1, 0)])
+@pytest.mark.parametrize("nsplit", [1, 4, 16])
+def test_paged_decode_attention_long_ragged(kv_dtype, impl, fuse, nsplit):
+    """paged decode attention (bulk-copy staged kernel, with and without the fused RoPE + KV append, and the round-1 __ldg
+    kernel) against fp64 SDPA at the bench's context lengths: ragged rows S in {1, 33, 1000, 1190, ...}, every split count
+    the engine uses."""
+    import ctypes as C
+    from gpu_util import _ptr
+    eng = _eng()
+    S_list = [1, 33, 1000, 1190, 32, 64, 65, 517]
+    pt, pool, qkv, cos, sin = _paged_case(S_list, kv_dtype, 11 + nsplit, fuse)
+    ref, new_k = _paged_reference(pt, pool, qkv, cos, sin, S_list, fuse)
+    R = len(S_list)
+    d = lambda t: t.cuda().contiguous()
+    pool_d, qkv_d, pt_d, cos_d, sin_d = d(pool), d(qkv), d(pt), d(cos), d(sin)
+    slot_row = torch.arange(R, dtype=torch.int32).cuda()
+    pos_d = torch.tensor([s - 1 for s in S_list], dtype=torch.int32).cuda()
+    out = torch.zeros(R, 1024, device="cuda")
+    ws = torch.empty(R * 16 * nsplit * 66 * 4 + 4096, dtype=torch.uint8, device="cuda")
+    eng.h.call("cbx_test_paged_decode", _ptr(qkv_d), _ptr(pool_d), 1 if kv_dtype == "fp32" else 0, pool.shape[0], _ptr(pt_d),
+               pt.shape[1], _ptr(slot_row), _ptr(pos_d), R, nsplit, impl, fuse, _ptr(cos_d), _ptr(sin_d), _ptr(out), _ptr(ws),
+               ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 2e-5, f"{kv_dtype} impl{impl} fuse{fuse} nsplit{nsplit}: max|dO| = {err}"
+    if fuse:            # the step's k / v landed in the cache at `pos`, rotated
+        pool_after = pool_d.cpu()
+        for r, S in enumerate(S_list):
+            pos = S - 1
+            page = int(pt[r, pos // 32])
+            kk = pool_after[page, 0, :, pos % 32].float()
+            vv = pool_after[page, 1, :, pos % 32].float()
+            assert (kk - new_k[r]).abs().max().item() < (1e-6 if kv_dtype == "fp32" else 1e-2)
+            assert torch.equal(vv, qkv[r, 2048:].view(16, 64).to(pool.dtype).float())
+
+
+@pytest.mark.parametrize("M,K,N,splitk,bn", [(512, 1024, 1024, 2, 64), (512, 4096, 1024, 4, 64), (300, 4096, 1024, 8, 64),
+                                              (128, 1024, 1024, 4, 64), (512, 1024, 1024, 1, 128), (40, 4096, 768, 8, 64)])
+def test_gemm_splitk_partials_reduce_deterministically(M, K, N, splitk, bn):
+    """decode-path projection: bf16 hi/lo planes by TMA, split-K partial sums, fixed-order reduction (resid_norm)."""
+    import ctypes as C
+    from gpu_util import _ptr, bf16r, relerr
+    eng = _eng()
+    g = torch.Generator().manual_seed(M + K + splitk)
+    A = torch.randn(M, K, generator=g).cuda()
+    w = bf16r(torch.randn(N, K, generator=g) / math.sqrt(K)).contiguous()
+    outs = []
+    for _ in range(2):
+        Cc = torch.full((M, N), float("nan"), device="cuda")
+        ws = torch.empty(M * K * 4 + splitk * M * N * 4 + 8192, dtype=torch.uint8, device="cuda")
+        eng.h.call("cbx_test_gemm_splitk", _ptr(A), C.c_void_p(w.data_ptr()), M, N, K, splitk, bn, _ptr(Cc), _ptr(ws), ws.numel(),
+                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        outs.append(Cc)
+    ref = A.double() @ w.double().t().cuda()
+    err = relerr(outs[0], ref)
+    assert err < 2e-5, f"rel err {err}"
+    assert torch.equal(outs[0], outs[1])           # bit-identical run to run
