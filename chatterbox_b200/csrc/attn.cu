@@ -480,101 +480,140 @@ template <> struct BulkCfg<__nv_bfloat16> { static constexpr int NST = 8; };
 template <> struct BulkCfg<float> { static constexpr int NST = 4; };
 constexpr int PB_TOK = 32;                    // tokens per page (required by this kernel)
 constexpr int PB_THREADS = 160;               // 4 consumer warps + 1 producer warp
+constexpr int PB_OCC = 3;                     // persistent CTAs per SM
 
-template <typename T> constexpr int pb_smem_bytes() { return BulkCfg<T>::NST * 2 * PB_TOK * 64 * (int)sizeof(T) + 256; }
+template <typename T> constexpr int pb_smem_bytes() { return BulkCfg<T>::NST * 2 * PB_TOK * 64 * (int)sizeof(T) + 256 + 4 * 4 * 18 * 4; }
 
+// Persistent: gridDim.x CTAs walk the (slot, head, split) work items with a fixed stride.  The producer warp runs ahead
+// of the consumers ACROSS items (the stage ring and its mbarrier phases never reset), so while the consumers merge one
+// row's partial results and set up the next row's query, that row's first pages are already landing in shared memory.
 template <typename T>
-__global__ void __launch_bounds__(PB_THREADS) paged_bulk_kernel(const PagedDev p) {
+__global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const PagedDev p, const int n_items) {
   constexpr int NST = BulkCfg<T>::NST;
   constexpr int SLAB = PB_TOK * 64 * (int)sizeof(T);      // one (page, head) slab of K or of V
   constexpr int STAGE = 2 * SLAB;
   constexpr int DPL = 16, NPC = DPL / KvPiece<T>::N;      // dims per lane, 16-byte pieces per lane
-  const int slot = blockIdx.x, head = blockIdx.y, split = blockIdx.z;
-  if (p.n_live && slot >= *p.n_live) return;
   extern __shared__ __align__(128) uint8_t pb_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(pb_smem + NST * STAGE);
   uint64_t* empty = full + NST;
-  const int row = p.slot_row[slot];
-  const int pos = p.positions[row];
-  const int S = pos + 1;
-  const int npg = (S + PB_TOK - 1) / PB_TOK;
+  float* mrg = reinterpret_cast<float*>(pb_smem + NST * STAGE + 256);     // [4 warps][4 subs][18]: m, l, o[16]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.n_heads;
+  const int per_slot = H * p.nsplit;
+  const int n_live = p.n_live ? *p.n_live : 0x7fffffff;
   const long slab_e = (long)PB_TOK * 64;                  // elements per slab
   const long page_stride = 2L * H * slab_e;
-  const T* base = reinterpret_cast<const T*>(p.pages) + (long)p.layer * p.n_pages * page_stride + (long)head * slab_e;
-  const int* pt = p.page_table + (long)row * p.max_pages;
+  const T* layer_base = reinterpret_cast<const T*>(p.pages) + (long)p.layer * p.n_pages * page_stride;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
     fence_mbar_init();
   }
   __syncthreads();
   if (warp == 4) {
-    // ===================== producer: bulk copies of this CTA's pages (split, split + nsplit, ...) ==========
+    // ===================== producer: bulk copies of every item's pages (split, split + nsplit, ...) ==========
     if (lane == 0) {
-      int i = 0;
-      for (int pj = split; pj < npg; pj += p.nsplit, ++i) {
-        const int s = i % NST;
-        mbar_wait(&empty[s], ((i / NST) & 1) ^ 1);
-        const T* kp = base + (long)pt[pj] * page_stride;
-        uint8_t* st = pb_smem + s * STAGE;
-        mbar_arrive_expect_tx(&full[s], STAGE);
-        bulk_g2s(st, kp, SLAB, &full[s]);
-        bulk_g2s(st + SLAB, kp + (long)H * slab_e, SLAB, &full[s]);
+      uint32_t gi = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int slot = it / per_slot;
+        if (slot >= n_live) break;                        // items are slot-major: nothing live beyond this one
+        const int rem = it - slot * per_slot;
+        const int head = rem / p.nsplit, split = rem - head * p.nsplit;
+        const int row = p.slot_row[slot];
+        const int npg = (p.positions[row] + PB_TOK) / PB_TOK;
+        const int* pt = p.page_table + (long)row * p.max_pages;
+        const T* base = layer_base + (long)head * slab_e;
+        for (int pj = split; pj < npg; pj += p.nsplit, ++gi) {
+          const int s = gi % NST;
+          mbar_wait(&empty[s], ((gi / NST) & 1) ^ 1);
+          const T* kp = base + (long)pt[pj] * page_stride;
+          uint8_t* st = pb_smem + s * STAGE;
+          mbar_arrive_expect_tx(&full[s], STAGE);
+          bulk_g2s(st, kp, SLAB, &full[s]);
+          bulk_g2s(st + SLAB, kp + (long)H * slab_e, SLAB, &full[s]);
+        }
       }
     }
     return;
   }
   // ===================== consumers ========================================================================
   const int sub = lane & 3, grp = lane >> 2;              // 4 lanes per token, 8 tokens per warp and page
-  float q[DPL], kn[DPL], vn[DPL];
-  {
-    const float* qp = p.qkv + (long)slot * p.ldqkv + head * 64;
-    const int d0 = sub * DPL;
-    if (p.fuse_rope) {
-      // rotate_half convention (modeling_llama.py:138-167): out = x*cos + rotate_half(x)*sin, products rounded
-      // separately like the reference's elementwise ops (no fused multiply-add)
-      const float* kq = qp + H * 64;
-      const float* vq = qp + 2 * H * 64;
-      const int pd0 = d0 < 32 ? d0 + 32 : d0 - 32;
-      const float sgn = d0 < 32 ? -1.f : 1.f;
-      const float* ct = p.cos_t + (long)pos * 32 + (d0 & 31);
-      const float* sn = p.sin_t + (long)pos * 32 + (d0 & 31);
+  const int d0 = sub * DPL;
+  uint32_t gi = 0;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int slot = it / per_slot;
+    if (slot >= n_live) break;
+    const int rem = it - slot * per_slot;
+    const int head = rem / p.nsplit, split = rem - head * p.nsplit;
+    const int row = p.slot_row[slot];
+    const int pos = p.positions[row];
+    const int S = pos + 1;
+    const int npg = (S + PB_TOK - 1) / PB_TOK;
+    const int* pt = p.page_table + (long)row * p.max_pages;
+    const T* base = layer_base + (long)head * slab_e;
+    float q[DPL], kn[DPL], vn[DPL];
+    {
+      const float* qp = p.qkv + (long)slot * p.ldqkv + head * 64;
+      float4 qa[4];
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) {
-        const float c = ct[i], s = sn[i];
-        q[i] = __fadd_rn(__fmul_rn(qp[d0 + i], c), __fmul_rn(sgn * qp[pd0 + i], s)) * p.scale;
-        float kr = __fadd_rn(__fmul_rn(kq[d0 + i], c), __fmul_rn(sgn * kq[pd0 + i], s));
-        float vr = vq[d0 + i];
-        if (sizeof(T) == 2) { kr = __bfloat162float(__float2bfloat16_rn(kr)); vr = __bfloat162float(__float2bfloat16_rn(vr)); }
-        kn[i] = kr; vn[i] = vr;
+      for (int i = 0; i < 4; ++i) qa[i] = *reinterpret_cast<const float4*>(qp + d0 + 4 * i);
+      if (p.fuse_rope) {
+        // rotate_half convention (modeling_llama.py:138-167): out = x*cos + rotate_half(x)*sin, products rounded
+        // separately like the reference's elementwise ops (no fused multiply-add)
+        const float* kq = qp + H * 64;
+        const float* vq = qp + 2 * H * 64;
+        const int pd0 = d0 < 32 ? d0 + 32 : d0 - 32;
+        const float sgn = d0 < 32 ? -1.f : 1.f;
+        const float* ct = p.cos_t + (long)pos * 32 + (d0 & 31);
+        const float* sn = p.sin_t + (long)pos * 32 + (d0 & 31);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 qb = *reinterpret_cast<const float4*>(qp + pd0 + 4 * i4);
+          const float4 ka = *reinterpret_cast<const float4*>(kq + d0 + 4 * i4);
+          const float4 kb = *reinterpret_cast<const float4*>(kq + pd0 + 4 * i4);
+          const float4 va = *reinterpret_cast<const float4*>(vq + d0 + 4 * i4);
+          const float4 c4 = *reinterpret_cast<const float4*>(ct + 4 * i4);
+          const float4 s4 = *reinterpret_cast<const float4*>(sn + 4 * i4);
+          const float xq[4] = {qa[i4].x, qa[i4].y, qa[i4].z, qa[i4].w}, yq[4] = {qb.x, qb.y, qb.z, qb.w};
+          const float xk[4] = {ka.x, ka.y, ka.z, ka.w}, yk[4] = {kb.x, kb.y, kb.z, kb.w};
+          const float xv[4] = {va.x, va.y, va.z, va.w};
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = 4 * i4 + e;
+            q[i] = __fadd_rn(__fmul_rn(xq[e], cc[e]), __fmul_rn(sgn * yq[e], ss[e])) * p.scale;
+            float kr = __fadd_rn(__fmul_rn(xk[e], cc[e]), __fmul_rn(sgn * yk[e], ss[e]));
+            float vr = xv[e];
+            if (sizeof(T) == 2) { kr = __bfloat162float(__float2bfloat16_rn(kr)); vr = __bfloat162float(__float2bfloat16_rn(vr)); }
+            kn[i] = kr; vn[i] = vr;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          q[4 * i4] = qa[i4].x * p.scale; q[4 * i4 + 1] = qa[i4].y * p.scale; q[4 * i4 + 2] = qa[i4].z * p.scale; q[4 * i4 + 3] = qa[i4].w * p.scale;
+        }
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) { kn[i] = 0.f; vn[i] = 0.f; }
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < DPL; ++i) { q[i] = qp[d0 + i] * p.scale; kn[i] = 0.f; vn[i] = 0.f; }
     }
-  }
-  // the CTA that owns the page of the new token appends it to the cache (the lanes that attend to it)
-  const int new_pg = pos >> 5, new_t = pos & 31;
-  const bool own_new = p.fuse_rope && (new_pg % p.nsplit) == split && warp == (new_t >> 3) && grp == (new_t & 7);
-  if (own_new) {
-    T* kd = const_cast<T*>(base) + (long)pt[new_pg] * page_stride + (long)new_t * 64 + sub * DPL;
-    T* vd = kd + (long)H * slab_e;
+    // the item that owns the page of the new token appends it to the cache (the lanes that attend to it)
+    const int new_pg = pos >> 5, new_t = pos & 31;
+    if (p.fuse_rope && (new_pg % p.nsplit) == split && warp == (new_t >> 3) && grp == (new_t & 7)) {
+      T* kd = const_cast<T*>(base) + (long)pt[new_pg] * page_stride + (long)new_t * 64 + d0;
+      T* vd = kd + (long)H * slab_e;
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) { kd[i] = (T)kn[i]; vd[i] = (T)vn[i]; }
-  }
-  float m = -INFINITY, l = 0.f, o[DPL];
+      for (int i = 0; i < DPL; ++i) { kd[i] = (T)kn[i]; vd[i] = (T)vn[i]; }
+    }
+    float m = -INFINITY, l = 0.f, o[DPL];
 #pragma unroll
-  for (int i = 0; i < DPL; ++i) o[i] = 0.f;
-  {
-    int i = 0;
-    for (int pj = split; pj < npg; pj += p.nsplit, ++i) {
-      const int s = i % NST;
-      mbar_wait(&full[s], (i / NST) & 1);
+    for (int i = 0; i < DPL; ++i) o[i] = 0.f;
+    for (int pj = split; pj < npg; pj += p.nsplit, ++gi) {
+      const int s = gi % NST;
+      mbar_wait(&full[s], (gi / NST) & 1);
       const int tl = warp * 8 + grp;                      // token inside the page
       const int tok = pj * PB_TOK + tl;
-      const uint4* kp = reinterpret_cast<const uint4*>(pb_smem + s * STAGE + (tl * 64 + sub * DPL) * (int)sizeof(T));
-      const uint4* vp = reinterpret_cast<const uint4*>(pb_smem + s * STAGE + SLAB + (tl * 64 + sub * DPL) * (int)sizeof(T));
+      const uint4* kp = reinterpret_cast<const uint4*>(pb_smem + s * STAGE + (tl * 64 + d0) * (int)sizeof(T));
+      const uint4* vp = reinterpret_cast<const uint4*>(pb_smem + s * STAGE + SLAB + (tl * 64 + d0) * (int)sizeof(T));
       float kx[DPL], vx[DPL];
       uint4 kr[NPC], vr[NPC];
 #pragma unroll
@@ -583,8 +622,7 @@ __global__ void __launch_bounds__(PB_THREADS) paged_bulk_kernel(const PagedDev p
       if (lane == 0) mbar_arrive(&empty[s]);              // the stage's bytes are in registers
 #pragma unroll
       for (int j = 0; j < NPC; ++j) { KvPiece<T>::decode(kr[j], kx + j * KvPiece<T>::N); KvPiece<T>::decode(vr[j], vx + j * KvPiece<T>::N); }
-      const bool is_new = p.fuse_rope && tok == pos;      // taken from registers, its cache slot is being written now
-      if (is_new) {
+      if (p.fuse_rope && tok == pos) {                    // taken from registers, its cache slot is being written now
 #pragma unroll
         for (int j = 0; j < DPL; ++j) { kx[j] = kn[j]; vx[j] = vn[j]; }
       }
@@ -604,39 +642,52 @@ __global__ void __launch_bounds__(PB_THREADS) paged_bulk_kernel(const PagedDev p
         l = l * c + e; m = mn;
       }
     }
-  }
-  // ---- merge the 32 token streams of this CTA (consumer warps only: named barrier 1, 128 threads)
-  float* sm_m = reinterpret_cast<float*>(pb_smem);        // the K/V ring is drained: reuse it
-  float* sm_l = sm_m + 128;
-  float* sm_o = sm_l + 128;
-  asm volatile("bar.sync 1, 128;" ::: "memory");         // every consumer is past its last stage read
-  sm_m[threadIdx.x] = m; sm_l[threadIdx.x] = l;
+    // ---- merge the 32 token streams of this CTA: 8 lane groups per warp by shuffles, then the 4 warps through smem
 #pragma unroll
-  for (int i = 0; i < DPL; ++i) sm_o[threadIdx.x * DPL + i] = o[i];
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  if (threadIdx.x < 64) {
-    const int d = threadIdx.x;
-    const int osub = d / DPL, oi = d % DPL;
-    float mt = -INFINITY;
-    for (int g = 0; g < 32; ++g) mt = fmaxf(mt, sm_m[g * 4 + osub]);
-    float lt = 0.f, ot = 0.f;
-    for (int g = 0; g < 32; ++g) {
-      const int th = g * 4 + osub;
-      const float ms = sm_m[th];
-      if (ms == -INFINITY) continue;
-      const float c = expf(ms - mt);
-      lt += sm_l[th] * c;
-      ot += sm_o[th * DPL + oi] * c;
+    for (int ofs = 4; ofs < 32; ofs <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, ofs);
+      const float l2 = __shfl_xor_sync(0xffffffffu, l, ofs);
+      const float mn = fmaxf(m, m2);
+      const float c1 = (m == -INFINITY) ? 0.f : expf(m - mn);
+      const float c2 = (m2 == -INFINITY) ? 0.f : expf(m2 - mn);
+      l = l * c1 + l2 * c2;
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) o[j] = o[j] * c1 + __shfl_xor_sync(0xffffffffu, o[j], ofs) * c2;
+      m = mn;
     }
-    if (p.nsplit == 1) {
-      const float ov = lt > 0.f ? ot / lt : 0.f;
-      const long oidx = (long)slot * p.ldo + head * 64 + d;
-      if (p.out_hi) { __nv_bfloat16 hh, ll; split_bf16(ov, hh, ll); p.out_hi[oidx] = hh; p.out_lo[oidx] = ll; }
-      else p.out[oidx] = ov;
-    } else {
-      float* sp = p.scratch + (((long)slot * H + head) * p.nsplit + split) * 66;
-      sp[2 + d] = ot;
-      if (d == 0) { sp[0] = mt; sp[1] = lt; }
+    asm volatile("bar.sync 1, 128;" ::: "memory");       // the previous item's merge buffer has been read
+    if (grp == 0) {
+      float* w = mrg + (warp * 4 + sub) * 18;
+      w[0] = m; w[1] = l;
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) w[2 + j] = o[j];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x < 64) {
+      const int d = threadIdx.x;
+      const int osub = d / DPL, oi = d % DPL;
+      float mt = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) mt = fmaxf(mt, mrg[(w * 4 + osub) * 18]);
+      float lt = 0.f, ot = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float* r = mrg + (w * 4 + osub) * 18;
+        if (r[0] == -INFINITY) continue;
+        const float c = expf(r[0] - mt);
+        lt += r[1] * c;
+        ot += r[2 + oi] * c;
+      }
+      if (p.nsplit == 1) {
+        const float ov = lt > 0.f ? ot / lt : 0.f;
+        const long oidx = (long)slot * p.ldo + head * 64 + d;
+        if (p.out_hi) { __nv_bfloat16 hh, ll; split_bf16(ov, hh, ll); p.out_hi[oidx] = hh; p.out_lo[oidx] = ll; }
+        else p.out[oidx] = ov;
+      } else {
+        float* sp = p.scratch + (((long)slot * H + head) * p.nsplit + split) * 66;
+        sp[2 + d] = ot;
+        if (d == 0) { sp[0] = mt; sp[1] = lt; }
+      }
     }
   }
 }
@@ -690,8 +741,12 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
   ctx.launches++;
   if (ctx.timer) ctx.timer->begin(K_PAGED, ctx.stream);
   if (bulk) {
-    if (kv.kv_fp32) paged_bulk_kernel<float><<<grid, PB_THREADS, pb_smem_bytes<float>(), ctx.stream>>>(p);
-    else paged_bulk_kernel<__nv_bfloat16><<<grid, PB_THREADS, pb_smem_bytes<__nv_bfloat16>(), ctx.stream>>>(p);
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; CBX_CHECK(cudaGetDevice(&dev)); CBX_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    const int n_items = n_slots * kv.n_heads * nsplit;
+    const int g = n_items < PB_OCC * n_sm ? n_items : PB_OCC * n_sm;
+    if (kv.kv_fp32) paged_bulk_kernel<float><<<g, PB_THREADS, pb_smem_bytes<float>(), ctx.stream>>>(p, n_items);
+    else paged_bulk_kernel<__nv_bfloat16><<<g, PB_THREADS, pb_smem_bytes<__nv_bfloat16>(), ctx.stream>>>(p, n_items);
   } else {
     if (kv.kv_fp32) paged_decode_kernel<float><<<grid, 128, 0, ctx.stream>>>(p);
     else paged_decode_kernel<__nv_bfloat16><<<grid, 128, 0, ctx.stream>>>(p);

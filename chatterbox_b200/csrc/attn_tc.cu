@@ -20,8 +20,10 @@ constexpr int AT_KV_STAGE = 4 * AT_TILE;             // K hi, K lo, V hi, V lo =
 constexpr int AT_P_BYTES = 2 * 2 * AT_TILE;          // P hi, P lo (128 rows each) = 32 KB
 constexpr int AT_SMEM = AT_Q_BYTES + AT_STAGES * AT_KV_STAGE + AT_P_BYTES + 1024 + 256 + 2048;   // + barriers + row exchange
 // F16 variant (one fp16 plane per operand, one MMA term): half the tile bytes, twice the K/V stages
-constexpr int AT_STAGES_F16 = 6;
-constexpr int AT_SMEM_F16 = AT_Q_BYTES / 2 + AT_STAGES_F16 * (AT_KV_STAGE / 2) + AT_P_BYTES / 2 + 1024 + 256 + 2048;
+// OCC = CTAs per SM of the F16 variant: 1 -> 6 K/V stages (128 KB), 2 -> 4 stages (99 KB per CTA; two CTAs share the SM so one
+// CTA's softmax (MUFU / ALU) runs under the other's MMAs, and every scheduler holds two softmax warps)
+__host__ __device__ constexpr int at_stages_f16(int occ) { return occ == 2 ? 4 : 6; }
+__host__ __device__ constexpr int at_smem_f16(int occ) { return AT_Q_BYTES / 2 + at_stages_f16(occ) * (AT_KV_STAGE / 2) + AT_P_BYTES / 2 + 1024 + 256 + 2048; }
 
 struct AttnTcDev {
   float* O; int ldo;
@@ -77,13 +79,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
 // RMS of that format at 2e-5 against fp32 -- 50x inside the 1e-3 bar -- while it cuts the tensor work and the
 // shared-memory operand traffic of this kernel by 3x.  F16 = 0 (default until measured on the GPU): bf16 hi/lo planes,
 // three terms.
-template <int SPLIT, int F16>
-__global__ void __launch_bounds__(64 + 128 * SPLIT, 1)
+template <int SPLIT, int F16, int OCC>
+__global__ void __launch_bounds__(64 + 128 * SPLIT, OCC)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const AttnTcDev p) {
   constexpr int NSW = 4 * SPLIT;            // softmax warps
   constexpr int NC = 64 / SPLIT;            // key columns (and output columns) per softmax thread
   constexpr int NPL = F16 ? 1 : 2;          // planes per operand
-  constexpr int STAGES = F16 ? AT_STAGES_F16 : AT_STAGES;
+  constexpr int STAGES = F16 ? at_stages_f16(OCC) : AT_STAGES;
   constexpr int Q_BYTES = NPL * 2 * AT_TILE, KV_STAGE = NPL * 2 * AT_TILE, P_BYTES = NPL * 2 * AT_TILE;
   const int seq = blockIdx.z, head = blockIdx.y;
   const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
@@ -361,11 +363,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
 // ---- host --------------------------------------------------------------------------------------------
 
+template <int SPLIT, int F16, int OCC> static void at_attr() {
+  CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<SPLIT, F16, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16 ? at_smem_f16(OCC) : AT_SMEM));
+}
 void attention_tc_init() {      // per device
-  CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-  CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-  CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_F16));
-  CBX_CHECK(cudaFuncSetAttribute(attn_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_F16));
+  at_attr<1, 0, 1>(); at_attr<2, 0, 1>(); at_attr<1, 1, 1>(); at_attr<2, 1, 1>(); at_attr<1, 1, 2>(); at_attr<2, 1, 2>();
 }
 
 void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
@@ -374,19 +376,27 @@ void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
   p.O = a.O; p.ldo = a.ldo; p.Ohi = a.Ohi; p.Olo = a.Olo; p.O16 = a.O16; p.q_start = a.q_start; p.q_len = a.q_len; p.kv_start = a.kv_start; p.kv_len = a.kv_len;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.q_col = a.q_col; p.k_col = a.k_col; p.v_col = a.v_col;
-  // CBX_ATTN_TC=2 selects two softmax threads per query row.  Measured on B200 (B=32 flow stage): 1170 ms vs 1123 ms
-  // for one thread per row -- the kernel is bound by shared-memory operand traffic of the N=64 SS-mode MMAs
-  // (~208 KB per key block), not by softmax latency, so the default stays 1.
+  // CBX_ATTN_TC = softmax threads per query row (1 | 2), CBX_ATTN_OCC = CTAs per SM of the fp16 variant (1 | 2).
+  // bf16x3 operands: the kernel is bound by shared-memory operand traffic of the N=64 SS-mode MMAs, one thread per row is
+  // best (round 1: 1123 ms vs 1170 ms at B=32).  fp16 operands cut the MMA and operand traffic 3x and leave the softmax
+  // (64 ex2 per row and key block on one warp per scheduler) exposed: see DESIGN.md for the measured variants.
   static const int variant = getenv("CBX_ATTN_TC") ? atoi(getenv("CBX_ATTN_TC")) : 1;
+  static const int occ = getenv("CBX_ATTN_OCC") ? atoi(getenv("CBX_ATTN_OCC")) : 2;
   ctx.launches++;
+  if (ctx.timer && ctx.timer->cls == K_FLASH) ctx.timer->work += a.work;
   if (ctx.timer) ctx.timer->begin(K_FLASH, ctx.stream);
   dim3 grid((a.max_q_len + AT_BM - 1) / AT_BM, a.n_heads, a.n_seq);
   if (a.f16) {       // single fp16 plane per operand (a.tm_hi maps it; a.tm_lo is not read)
-    if (variant == 1) attn_tc_kernel<1, 1><<<grid, 192, AT_SMEM_F16, ctx.stream>>>(*a.tm_hi, *a.tm_hi, p);
-    else attn_tc_kernel<2, 1><<<grid, 320, AT_SMEM_F16, ctx.stream>>>(*a.tm_hi, *a.tm_hi, p);
+    if (occ == 2) {
+      if (variant == 1) attn_tc_kernel<1, 1, 2><<<grid, 192, at_smem_f16(2), ctx.stream>>>(*a.tm_hi, *a.tm_hi, p);
+      else attn_tc_kernel<2, 1, 2><<<grid, 320, at_smem_f16(2), ctx.stream>>>(*a.tm_hi, *a.tm_hi, p);
+    } else {
+      if (variant == 1) attn_tc_kernel<1, 1, 1><<<grid, 192, at_smem_f16(1), ctx.stream>>>(*a.tm_hi, *a.tm_hi, p);
+      else attn_tc_kernel<2, 1, 1><<<grid, 320, at_smem_f16(1), ctx.stream>>>(*a.tm_hi, *a.tm_hi, p);
+    }
   } else {
-    if (variant == 1) attn_tc_kernel<1, 0><<<grid, 192, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
-    else attn_tc_kernel<2, 0><<<grid, 320, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
+    if (variant == 1) attn_tc_kernel<1, 0, 1><<<grid, 192, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
+    else attn_tc_kernel<2, 0, 1><<<grid, 320, AT_SMEM, ctx.stream>>>(*a.tm_hi, *a.tm_lo, p);
   }
   if (ctx.timer) ctx.timer->end(K_FLASH, ctx.stream);
   CBX_CHECK(cudaGetLastError());

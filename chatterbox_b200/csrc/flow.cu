@@ -25,17 +25,18 @@ static GemmDev lin_args(const float* A, int lda, int c_in, int M, const Weight& 
   return g;
 }
 
-static void pack_lin(cbx_handle* h, Weight& W, const std::string& name, bool bias = true) {
+static void pack_lin(cbx_handle* h, Weight& W, const std::string& name, bool bias = true, bool half_copy = false) {
   const HostTensor& w = host_tensor(h, name + ".weight");
   const float* b = (bias && has_tensor(h, name + ".bias")) ? host_tensor(h, name + ".bias").data.data() : nullptr;
-  pack_linear(W, w.data.data(), b, (int)w.shape[0], (int)w.shape[1]);
+  pack_linear(W, w.data.data(), b, (int)w.shape[0], (int)w.shape[1], half_copy);
 }
 static void pack_conv(cbx_handle* h, Weight& W, const std::string& name) {
   const HostTensor& w = host_tensor(h, name + ".weight");
   const float* b = has_tensor(h, name + ".bias") ? host_tensor(h, name + ".bias").data.data() : nullptr;
   pack_conv_taps(W, w.data.data(), b, (int)w.shape[0], (int)w.shape[1], (int)w.shape[2]);
 }
-static void pack_cat3(cbx_handle* h, Weight& W, const std::string& a, const std::string& b, const std::string& c, bool bias) {
+static void pack_cat3(cbx_handle* h, Weight& W, const std::string& a, const std::string& b, const std::string& c, bool bias,
+                      bool half_copy = false) {
   const HostTensor &wa = host_tensor(h, a + ".weight"), &wb = host_tensor(h, b + ".weight"), &wc = host_tensor(h, c + ".weight");
   std::vector<float> w;
   w.insert(w.end(), wa.data.begin(), wa.data.end());
@@ -46,7 +47,7 @@ static void pack_cat3(cbx_handle* h, Weight& W, const std::string& a, const std:
     for (const std::string& n : {a, b, c}) { const auto& t = host_tensor(h, n + ".bias").data; bb.insert(bb.end(), t.begin(), t.end()); }
   }
   const int N = (int)(wa.shape[0] + wb.shape[0] + wc.shape[0]);
-  pack_linear(W, w.data(), bias ? bb.data() : nullptr, N, (int)wa.shape[1]);
+  pack_linear(W, w.data(), bias ? bb.data() : nullptr, N, (int)wa.shape[1], half_copy);
 }
 
 static void build_enc_layer(cbx_handle* h, EncLayer& L, const std::string& p) {
@@ -68,10 +69,11 @@ static void build_resnet(cbx_handle* h, CfmResnet& r, const std::string& p) {
   r.ln2_w = upload_tensor(h, p + "block2.block.2.weight"); r.ln2_b = upload_tensor(h, p + "block2.block.2.bias");
 }
 static void build_tfmr(cbx_handle* h, CfmTfmr& t, const std::string& p) {
-  pack_cat3(h, t.qkv, p + "attn1.to_q", p + "attn1.to_k", p + "attn1.to_v", false);
-  pack_lin(h, t.out, p + "attn1.to_out.0");
-  pack_lin(h, t.ff1, p + "ff.net.0.proj");
-  pack_lin(h, t.ff2, p + "ff.net.2");
+  // fp16 copies: operands of the single-plane fp16-activation format of the block GEMMs (Engine.set_cfm_activation_precision)
+  pack_cat3(h, t.qkv, p + "attn1.to_q", p + "attn1.to_k", p + "attn1.to_v", false, true);
+  pack_lin(h, t.out, p + "attn1.to_out.0", true, true);
+  pack_lin(h, t.ff1, p + "ff.net.0.proj", true, true);
+  pack_lin(h, t.ff2, p + "ff.net.2", true, true);
   t.ln1_w = upload_tensor(h, p + "norm1.weight"); t.ln1_b = upload_tensor(h, p + "norm1.bias");
   t.ln3_w = upload_tensor(h, p + "norm3.weight"); t.ln3_b = upload_tensor(h, p + "norm3.bias");
 }
@@ -247,7 +249,8 @@ void flow_encode(cbx_handle* h, Ctx& ctx, const int* tokens, const cbx_layout& L
 }
 
 // ---- CFM estimator ---------------------------------------------------------------------------------
-struct EstBufs { float *h1, *h2, *hn, *qkv, *att, *ff; __nv_bfloat16 *qkv_hi, *qkv_lo; CUtensorMap tm_hi, tm_lo; bool tc; bool f16; bool a16; };
+struct EstBufs { float *h1, *h2, *hn, *qkv, *att, *ff; __nv_bfloat16 *qkv_hi, *qkv_lo; CUtensorMap tm_hi, tm_lo; bool tc; bool f16; bool a16;
+                 double attn_work; };
 
 static void cfm_resnet(Ctx& ctx, CfmResnet& r, const float* in, int lda, int cin, float* out, int ldo, const float* tvec,
                        const cbx_layout& L, EstBufs& b) {
@@ -290,7 +293,7 @@ static void cfm_tfmr(Ctx& ctx, CfmTfmr& t, float* x, int ldx, const cbx_layout& 
     if (b.a16) a.O16 = at16; else { a.Ohi = at_hi; a.Olo = at_lo; }
     a.f16 = b.f16 ? 1 : 0;
     a.n_seq = L.n_seq; a.n_heads = 8; a.q_start = L.start; a.q_len = L.len; a.kv_start = L.start; a.kv_len = L.len;
-    a.max_q_len = L.max_len; a.scale = 0.125f;
+    a.max_q_len = L.max_len; a.scale = 0.125f; a.work = b.attn_work;
     attention_tc(ctx, a);
     GemmDev go = gemm_args_linear(nullptr, 512, rows, t.out, x, ldx);
     feed(go, at_hi, at_lo, at16, 512);
@@ -395,6 +398,8 @@ void cfm_solve(cbx_handle* h, Ctx& ctx, const float* mu, const float* spk, const
   b.h1 = ctx.ws.get<float>((size_t)rows3 * 256); b.h2 = ctx.ws.get<float>((size_t)rows3 * 256);
   b.hn = ctx.ws.get<float>((size_t)rows3 * 256); b.qkv = ctx.ws.get<float>((size_t)rows3 * 1536);
   b.att = ctx.ws.get<float>((size_t)rows3 * 512); b.ff = ctx.ws.get<float>((size_t)rows3 * 1024);
+  b.attn_work = 0.0;
+  if (L3.h_len) for (int i = 0; i < L3.n_seq; ++i) b.attn_work += 4.0 * 64.0 * 8.0 * (double)L3.h_len[i] * (double)L3.h_len[i];
   b.tc = (ctx.attn_impl == 0 && ctx.gemm_impl == 0);
   b.f16 = b.tc && ctx.attn_f16 != 0;
   b.a16 = b.f16 && ctx.cfm_act_f16 != 0;      // fp16 activations ride on the fp16 attention variant

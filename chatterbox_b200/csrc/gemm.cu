@@ -9,6 +9,7 @@
 //
 // Algorithmic HBM bytes per launch (roofline): N*K*2 (weights) + M*K_in*4 (activations) + M*N*4 (output).
 #include "ops.h"
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -466,7 +467,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     // ===================== MMA issuer (one elected thread) ============================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
-      constexpr uint32_t idesc_a16 = idesc & ~(7u << 7);     // a_format = F16 (0), b_format stays BF16: A fp16 x W bf16
+      constexpr uint32_t idesc_a16 = idesc & ~(7u << 7) & ~(7u << 10);   // a_format = b_format = F16 (0): A fp16 x W fp16 copy
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -686,12 +687,26 @@ static void upload_packed(Weight& W, const std::vector<uint16_t>& host, const fl
   make_tmaps_for(W);
 }
 
-void pack_linear(Weight& W, const float* w, const float* bias, int N, int K) {
+void pack_linear(Weight& W, const float* w, const float* bias, int N, int K, bool half_copy) {
   W.N = N; W.K = K; W.Npad = (N + 63) / 64 * 64; W.Kpad = (K + 63) / 64 * 64;
   std::vector<uint16_t> h((size_t)W.Npad * W.Kpad, 0);
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) h[(size_t)n * W.Kpad + k] = f2bf16_host(w[(size_t)n * K + k]);
   upload_packed(W, h, bias);
+  if (half_copy) {       // the bf16-rounded values again, as fp16
+    std::vector<__half> hh((size_t)W.Npad * W.Kpad, __float2half_rn(0.f));
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) {
+        uint32_t u = (uint32_t)h[(size_t)n * W.Kpad + k] << 16;
+        float f; memcpy(&f, &u, 4);
+        hh[(size_t)n * W.Kpad + k] = __float2half_rn(f);
+      }
+    CBX_CHECK(cudaMalloc(&W.w16, hh.size() * 2));
+    CBX_CHECK(cudaMemcpy(W.w16, hh.data(), hh.size() * 2, cudaMemcpyHostToDevice));
+    Weight tmp = W; tmp.w = reinterpret_cast<__nv_bfloat16*>(W.w16);     // 2-byte elements: same map geometry
+    make_tmaps_for(tmp);
+    for (int i = 0; i < 3; ++i) W.tmap16[i] = tmp.tmap[i];
+  }
 }
 // torch Conv1d weight [N][cin][taps] -> [N][tap][ctap], ctap = cin rounded up to 64
 void pack_conv_taps(Weight& W, const float* w, const float* bias, int N, int cin, int taps) {
@@ -717,7 +732,8 @@ void pack_conv_window(Weight& W, const float* w, const float* bias, int N, int c
 void free_weight(Weight& W) {
   if (W.w) cudaFree(W.w);
   if (W.bias) cudaFree(W.bias);
-  W.w = nullptr; W.bias = nullptr;
+  if (W.w16) cudaFree(W.w16);
+  W.w = nullptr; W.bias = nullptr; W.w16 = nullptr;
 }
 
 GemmDev gemm_args_linear(const float* A, int lda, int M, const Weight& W, float* C, int ldc) {
@@ -762,6 +778,7 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
   CUtensorMap tmA, tmA2;
   if (g.A16) {
     CBX_REQUIRE(g.ntaps == 1 && !g.has_seq && (g.lda16 % 8) == 0, "fp16 plane operand needs a plain Linear");
+    CBX_REQUIRE(W.w16 != nullptr, "fp16 activations need the fp16 copy of the weight (pack_linear half_copy)");
     g.a_tma = 3;
     make_plane_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(g.A16), g.M, g.k_total, 128, g.lda16);   // 2-byte elements
     tmA2 = tmA;
@@ -795,7 +812,7 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
     ctx.timer->bytes += b;
   }
   if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
-  gemm_tc_kernel<BN, DUAL><<<grid, TC_THREADS, TcCfg<BN, DUAL>::SMEM, ctx.stream>>>(W.tmap[tmap_idx], tmA, tmA2, g);
+  gemm_tc_kernel<BN, DUAL><<<grid, TC_THREADS, TcCfg<BN, DUAL>::SMEM, ctx.stream>>>(g.A16 ? W.tmap16[tmap_idx] : W.tmap[tmap_idx], tmA, tmA2, g);
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
 }
 

@@ -16,6 +16,8 @@ struct Weight {
   int N = 0, K = 0;          // logical sizes
   int Npad = 0, Kpad = 0;    // N padded to 64, K padded to 64
   CUtensorMap tmap[3];       // TMA maps with box {64 (K), 64|128|256 (N)}, SWIZZLE_128B
+  __half* w16 = nullptr;     // optional fp16 copy of the same values (exact for |w| in [2^-14, 65504]): operand of the
+  CUtensorMap tmap16[3];     // single-plane fp16-activation GEMMs -- tcgen05 kind::f16 wants A and B in ONE 16-bit format
 };
 
 // Geometry of a packed variable-length batch.  Every sequence starts at a multiple of kTileM rows, so
@@ -137,7 +139,7 @@ struct Ctx {
 // ---- weights ------------------------------------------------------------------------------------
 // host fp32 [N][K] (row-major) -> device packed bf16 + TMA maps.  taps/cin describe conv weights given
 // as [N][cin][taps] (torch Conv1d layout); they are re-ordered to [N][tap][cin_pad].
-void pack_linear(Weight& W, const float* host_w, const float* host_bias, int N, int K);
+void pack_linear(Weight& W, const float* host_w, const float* host_bias, int N, int K, bool half_copy = false);
 void pack_conv_taps(Weight& W, const float* host_w, const float* host_bias, int N, int cin, int taps);    // k = tap*ctap + c
 void pack_conv_window(Weight& W, const float* host_w, const float* host_bias, int N, int cin, int taps);  // k = tap*cin + c
 void free_weight(Weight& W);
@@ -175,6 +177,7 @@ struct AttnTcArgs {
   int n_seq, n_heads;
   const int* q_start; const int* q_len; const int* kv_start; const int* kv_len;
   int max_q_len; float scale;
+  double work = 0.0;        // algorithmic flops of this launch (4 * 64 * heads * sum len^2), for the event timer only
 };
 void attention_tc(Ctx& ctx, const AttnTcArgs& a);
 void attention_tc_init();

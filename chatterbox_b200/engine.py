@@ -181,7 +181,8 @@ class Engine:
         device pointers (and with them the cached decode graphs and the KV pool allocation)."""
         if key not in self._t3_bufs:
             self._t3_bufs.clear()            # one shape at a time: the KV pool can be tens of GB
-            self._t3_bufs[key] = make()
+            with torch.inference_mode(False):    # persistent buffers outlive the caller's inference_mode block
+                self._t3_bufs[key] = make()
         return self._t3_bufs[key]
 
     @staticmethod
@@ -364,7 +365,11 @@ class Engine:
             steps_done += k
             self.stats["decode_steps"] += k
             self.stats["paged_launches"] += k * self.t3_layers
-            ev, buf = self._pinned.pop() if self._pinned else (torch.cuda.Event(), torch.zeros(1, dtype=torch.int32).pin_memory())
+            if self._pinned:
+                ev, buf = self._pinned.pop()
+            else:
+                with torch.inference_mode(False):
+                    ev, buf = torch.cuda.Event(), torch.zeros(1, dtype=torch.int32).pin_memory()
             buf.copy_(st_t["n_act"], non_blocking=True)
             ev.record()
             pending.append((ev, buf))

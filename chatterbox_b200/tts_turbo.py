@@ -7,7 +7,7 @@ import torch
 from .engine import Engine
 from .t3 import T3
 from .s3gen import S3Gen, S3GEN_SR, SPEECH_VOCAB_SIZE
-from .tts import Conditionals, punc_norm, synthesize_batch
+from .tts import Conditionals, punc_norm, synthesize_batch, apply_watermark
 
 S3GEN_SIL = 4299            # reference models/s3gen/const.py:2
 TURBO_SPEECH_VOCAB = 6563   # tts_turbo.py:155
@@ -56,14 +56,16 @@ class ChatterboxTurboTTS:
 
     @torch.inference_mode()
     def generate(self, text, repetition_penalty=1.2, min_p=0.0, top_p=0.95, audio_prompt_path=None, exaggeration=0.0,
-                 cfg_weight=0.0, temperature=0.8, top_k=1000, norm_loudness=True, rng="torch_cpu", kv_dtype="bf16"):
-        """reference tts_turbo.py:272-321 (CFG / min_p / exaggeration are ignored there too; watermarking is a CPU
-        post-process outside the hot path)."""
+                 cfg_weight=0.0, temperature=0.8, top_k=1000, norm_loudness=True, rng="torch_cpu", kv_dtype=None,
+                 watermark=True):
+        """reference tts_turbo.py:272-321 (CFG / min_p / exaggeration are ignored there too).  The output is watermarked
+        on the host like the reference's (tts_turbo.py:319) unless watermark=False."""
         assert audio_prompt_path is None, "prepare_conditionals is outside the hot path; set .conds"
         assert self.tokenizer is not None, "no tokenizer loaded; pass token ids to generate_tokens()"
         ids = self.tokenizer(punc_norm(text), return_tensors="pt", padding=True, truncation=True).input_ids
-        return self.generate_tokens(ids, repetition_penalty=repetition_penalty, top_p=top_p, temperature=temperature,
-                                    top_k=top_k, rng=rng, kv_dtype=kv_dtype)
+        wav = self.generate_tokens(ids, repetition_penalty=repetition_penalty, top_p=top_p, temperature=temperature,
+                                   top_k=top_k, rng=rng, kv_dtype=kv_dtype)
+        return apply_watermark(wav, self.sr, watermark)
 
     @torch.inference_mode()
     def generate_batch(self, text_tokens, max_gen_len=1000, repetition_penalty=1.2, top_p=0.95, temperature=0.8,
@@ -103,11 +105,13 @@ class ChatterboxTurboTTS:
 
     @torch.inference_mode()
     def generate_tokens(self, text_tokens, repetition_penalty=1.2, top_p=0.95, temperature=0.8, top_k=1000,
-                        max_gen_len=1000, rng="torch_cpu", kv_dtype="bf16", return_intermediates=False):
+                        max_gen_len=1000, rng="torch_cpu", kv_dtype=None, return_intermediates=False):
         """generate() from tokenizer ids (1, n).  rng='torch_cpu' draws every random tensor from torch's global CPU
         generator in the reference's order (multinomial per token -> meanflow noise s3gen.py:316 -> randn_like(mu)
         flow_matching.py:216 -> SineGen phases -> SineGen noise); rng='device' uses the engine's counter RNG."""
         assert self.conds is not None, "Please set .conds (Conditionals)"
+        if kv_dtype is None:
+            kv_dtype = "fp32" if rng == "torch_cpu" else "bf16"
         tt = torch.atleast_2d(text_tokens).to(torch.long).cpu()
         q = None
         if rng == "torch_cpu":

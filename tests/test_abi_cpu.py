@@ -159,3 +159,51 @@ def test_synthesize_batch_chunking_and_order():
     for call in eng.hift_calls:
         assert len(call) == 1 or sum(call) <= 100
     assert sorted(sum(eng.hift_calls, [])) == sorted(2 * n for n in lens if n > 0)
+
+
+def test_decode_capacity_buckets():
+    """Launch capacity of a decode step: never below the live count, exact GEMV shapes up to 8 rows, then powers of two up
+    to one 128-row tile, then whole tiles (few distinct values -> few cached CUDA graphs)."""
+    from chatterbox_b200.engine import Engine
+    for rp in (1, 2):
+        seen = set()
+        for n in range(1, 600):
+            c = Engine.decode_capacity(n, rp)
+            assert c >= n or c * rp <= 8 and c >= min(n, 8 // rp), (n, rp, c)
+            seen.add(c)
+            if n * rp > 128:
+                assert (c * rp) % 128 == 0 and c * rp - n * rp < 128
+        assert len(seen) <= 16
+    assert [Engine.decode_capacity(n, 2) for n in (1, 2, 3, 4, 5, 33, 64, 65, 256)] == [1, 2, 4, 4, 8, 64, 64, 128, 256]
+
+
+def test_multilingual_text_front_end(tmp_path):
+    """mtl_tts.py:70-107 sentence enders, models/tokenizers/tokenizer.py:256-312 language prefix, mtl_tts.py:339-341 token
+    clean-up (no `< 6561` filter: an out-of-range id is an error like in the reference), watermark failure mode."""
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from chatterbox_b200.tts import (mtl_punc_norm, punc_norm, MTLTokenizer, ChatterboxMultilingualTTS, ChatterboxTTS,
+                                     apply_watermark)
+    assert mtl_punc_norm("你好。") == "你好。" and punc_norm("你好。") == "你好。."
+    assert mtl_punc_norm("hello") == "Hello." and mtl_punc_norm("quoi？") == "Quoi？"
+    vocab = {"[START]": 0, "[STOP]": 1, "[UNK]": 2, "[SPACE]": 3, "[fr]": 4, "a": 5, "b": 6, "e": 7, "́": 8}
+    tok = Tokenizer(models.WordLevel(vocab, unk_token="[UNK]"))
+    from tokenizers import Regex
+    tok.pre_tokenizer = pre_tokenizers.Split(Regex(r"\[[A-Za-z]+\]|."), behavior="isolated")
+    f = tmp_path / "grapheme_mtl_merged_expanded_v1.json"
+    tok.save(str(f))
+    mt = MTLTokenizer(f)
+    assert mt.text_to_tokens("A bÉ", language_id="fr").tolist() == [[4, 5, 3, 6, 7, 8]]      # lower-case, NFKD, prefix, [SPACE]
+    with pytest.raises(NotImplementedError):
+        mt.encode("x", language_id="zh")
+    x = torch.tensor([6561, 5, 6563, 7, 6562, 9])
+    assert ChatterboxTTS.clean_speech_tokens(x).tolist() == [5, 7]
+    with pytest.raises(IndexError):
+        ChatterboxMultilingualTTS.clean_speech_tokens(x)
+    assert ChatterboxMultilingualTTS.clean_speech_tokens(torch.tensor([5, 7, 6562, 6563])).tolist() == [5, 7]
+    wav = torch.zeros(1, 100)
+    assert apply_watermark(wav, 24000, enabled=False) is wav
+    try:
+        import perth  # noqa: F401
+    except ImportError:
+        with pytest.raises(RuntimeError):
+            apply_watermark(wav, 24000)

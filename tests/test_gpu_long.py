@@ -144,7 +144,9 @@ def test_eos_retirement_does_not_disturb_neighbours(golden_dir):
         else:
             assert out[b].tolist() == free[b].tolist()
             assert sampled[b, :steps].tolist() == free[b].tolist(), (b, sampled[b, :steps].tolist(), free[b].tolist())
-    assert int(st["n_act"].item()) == 0
+    # the three EOS utterances left the active list on the device; the four that ran to their budget are flagged done in
+    # the last step and would be dropped by the next step's compaction
+    assert int(st["n_act"].item()) == B - len(eos_at) and int(st["done"].sum().item()) == B
 
 
 # ---------------------------------------------------------------------------------------------------------- flow
