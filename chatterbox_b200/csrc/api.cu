@@ -1,5 +1,6 @@
 // C ABI of libcbx (include/cbx.h): handle lifetime, weight staging, exception -> status-code fence.
 #include "engine.h"
+#include <cuda_fp16.h>
 #include <cstdlib>
 
 using namespace cbx;
@@ -405,6 +406,39 @@ int cbx_test_gemm_splitk(cbx_handle* h, const float* A, const float* w_host, int
   memset(&rn, 0, sizeof(rn));
   rn.x = C; rn.ldx = N; rn.part = part; rn.nsplit = splitk; rn.split_stride = (long)M * N; rn.ldp = N; rn.dim = N;
   resid_norm(c, rn, M);
+  CBX_CHECK(cudaStreamSynchronize(c.stream));
+  free_weight(W);
+  h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+
+__global__ void f32_to_f16_kernel(const float* x, __half* y, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2half_rn(x[i]);
+}
+__global__ void f16_to_f32_kernel(const __half* x, float* y, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __half2float(x[i]);
+}
+/* C[M][N] = act(A x W^T + bias) (+ res) through the fp16-plane operand format of the CFM transformer blocks (A rounded to
+ * one fp16 plane, fp16 copy of W): picks the weight-resident persistent kernel for K = 256 / 512.  out_half = 1: the result
+ * goes through an fp16 plane (as the qkv / ff1 projections write it) before it is widened into C. */
+int cbx_test_gemm_f16(cbx_handle* h, const float* A, const float* w_host, const float* bias_host, const float* res, int M, int N,
+                      int K, int act, int out_half, float* C, void* ws, size_t ws_bytes, cbx_stream stream) {
+  if (!h) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Weight W;
+  pack_linear(W, w_host, bias_host, N, K, true);
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  __half* a16 = c.ws.get<__half>((size_t)M * K);
+  __half* c16 = c.ws.get<__half>((size_t)M * N);
+  f32_to_f16_kernel<<<(unsigned)(((long)M * K + 255) / 256), 256, 0, c.stream>>>(A, a16, (long)M * K);
+  GemmDev g = gemm_args_linear(nullptr, K, M, W, out_half ? nullptr : C, N);
+  g.A16 = a16; g.lda16 = K; g.act = act;
+  if (out_half) { g.Chi = reinterpret_cast<__nv_bfloat16*>(c16); g.Clo = g.Chi; g.ldcb = N; g.c_half = 1; }
+  else if (res) { g.res = res; g.ldr = N; }
+  gemm(c, g, W);
+  if (out_half) f16_to_f32_kernel<<<(unsigned)(((long)M * N + 255) / 256), 256, 0, c.stream>>>(c16, C, (long)M * N);
   CBX_CHECK(cudaStreamSynchronize(c.stream));
   free_weight(W);
   h->launches += c.launches;

@@ -11,6 +11,7 @@
 //                           read exactly once, 16-byte coalesced loads, flash-decoding split over CTAs).
 //  * rope_store_kernel      llama3 RoPE on q,k (in place) + append k,v to the paged cache.
 #include "ops.h"
+#include <cuda_fp8.h>
 #include <cstdlib>
 #include <string>
 
@@ -332,6 +333,24 @@ template <> struct KvPiece<float> {
   }
 };
 
+template <> struct KvPiece<__nv_fp8_e4m3> {     // opt-in fp8 KV cache: 16 values per 16-byte piece
+  static constexpr int N = 16;
+  static __device__ __forceinline__ void decode(const uint4& u, float* x) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w[i] & 0xFFFFu), __NV_E4M3);
+      const __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w[i] >> 16), __NV_E4M3);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+      x[4 * i] = a.x; x[4 * i + 1] = a.y; x[4 * i + 2] = b.x; x[4 * i + 3] = b.y;
+    }
+  }
+};
+// value as it will read back from a cache of element type T
+template <typename T> __device__ __forceinline__ float kv_round(float v) { return (float)(T)v; }
+template <> __device__ __forceinline__ float kv_round<float>(float v) { return v; }
+
 struct PagedDev {
   const float* qkv; int ldqkv;        // [slots][3*H*64] (q rotated in place by rope_store)
   const void* pages; int n_pages, n_layers, n_heads, page_tokens, page_shift, layer;   // page_tokens = 1 << page_shift
@@ -478,6 +497,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 template <typename T> struct BulkCfg;
 template <> struct BulkCfg<__nv_bfloat16> { static constexpr int NST = 8; };
 template <> struct BulkCfg<float> { static constexpr int NST = 4; };
+template <> struct BulkCfg<__nv_fp8_e4m3> { static constexpr int NST = 16; };
 constexpr int PB_TOK = 32;                    // tokens per page (required by this kernel)
 constexpr int PB_THREADS = 160;               // 4 consumer warps + 1 producer warp
 constexpr int PB_OCC = 3;                     // persistent CTAs per SM
@@ -583,8 +603,7 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
             q[i] = __fadd_rn(__fmul_rn(xq[e], cc[e]), __fmul_rn(sgn * yq[e], ss[e])) * p.scale;
             float kr = __fadd_rn(__fmul_rn(xk[e], cc[e]), __fmul_rn(sgn * yk[e], ss[e]));
             float vr = xv[e];
-            if (sizeof(T) == 2) { kr = __bfloat162float(__float2bfloat16_rn(kr)); vr = __bfloat162float(__float2bfloat16_rn(vr)); }
-            kn[i] = kr; vn[i] = vr;
+            kn[i] = kv_round<T>(kr); vn[i] = kv_round<T>(vr);
           }
         }
       } else {
@@ -716,6 +735,7 @@ __global__ void paged_combine_kernel(const float* scratch, float* out, int ldo, 
 void paged_attention_init() {     // per device, before any stream capture
   CBX_CHECK(cudaFuncSetAttribute(paged_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes<__nv_bfloat16>()));
   CBX_CHECK(cudaFuncSetAttribute(paged_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes<float>()));
+  CBX_CHECK(cudaFuncSetAttribute(paged_bulk_kernel<__nv_fp8_e4m3>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes<__nv_fp8_e4m3>()));
 }
 
 void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* slot_row,
@@ -737,6 +757,7 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
   static const bool force_ldg = getenv("CBX_PAGED") && std::string(getenv("CBX_PAGED")) == "ldg";
   const bool bulk = kv.page_tokens == PB_TOK && !(force_ldg && !p.fuse_rope) && !(opts && opts->impl == 1);
   CBX_REQUIRE(bulk || !p.fuse_rope, "fused RoPE + KV append needs the bulk-copy kernel (32-token pages)");
+  CBX_REQUIRE(bulk || kv.kv_fp32 != 2, "the fp8 KV cache needs the bulk-copy kernel");
   dim3 grid(n_slots, kv.n_heads, nsplit);
   ctx.launches++;
   if (ctx.timer) ctx.timer->begin(K_PAGED, ctx.stream);
@@ -745,10 +766,11 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
     if (!n_sm) { int dev = 0; CBX_CHECK(cudaGetDevice(&dev)); CBX_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
     const int n_items = n_slots * kv.n_heads * nsplit;
     const int g = n_items < PB_OCC * n_sm ? n_items : PB_OCC * n_sm;
-    if (kv.kv_fp32) paged_bulk_kernel<float><<<g, PB_THREADS, pb_smem_bytes<float>(), ctx.stream>>>(p, n_items);
+    if (kv.kv_fp32 == 1) paged_bulk_kernel<float><<<g, PB_THREADS, pb_smem_bytes<float>(), ctx.stream>>>(p, n_items);
+    else if (kv.kv_fp32 == 2) paged_bulk_kernel<__nv_fp8_e4m3><<<g, PB_THREADS, pb_smem_bytes<__nv_fp8_e4m3>(), ctx.stream>>>(p, n_items);
     else paged_bulk_kernel<__nv_bfloat16><<<g, PB_THREADS, pb_smem_bytes<__nv_bfloat16>(), ctx.stream>>>(p, n_items);
   } else {
-    if (kv.kv_fp32) paged_decode_kernel<float><<<grid, 128, 0, ctx.stream>>>(p);
+    if (kv.kv_fp32 == 1) paged_decode_kernel<float><<<grid, 128, 0, ctx.stream>>>(p);
     else paged_decode_kernel<__nv_bfloat16><<<grid, 128, 0, ctx.stream>>>(p);
   }
   if (ctx.timer) ctx.timer->end(K_PAGED, ctx.stream);
@@ -796,10 +818,15 @@ void rope_and_store_kv(Ctx& ctx, float* qkv, int ldqkv, const PagedKV& kv, int l
                        const int* tok_pos, int pos_is_per_row, int n_tok, const float* cos_t, const float* sin_t) {
   if (ctx.dry || n_tok == 0) return;
   ctx.launches++;
-  if (kv.kv_fp32)
+  if (kv.kv_fp32 == 1)
     rope_store_kernel<float><<<n_tok, 256, 0, ctx.stream>>>(qkv, ldqkv, kv.pages, kv.n_pages, kv.n_heads, kv.page_tokens,
                                                            layer, kv.page_table, kv.max_pages_per_row, tok_row, tok_pos,
                                                            pos_is_per_row, cos_t, sin_t);
+  else if (kv.kv_fp32 == 2)
+    rope_store_kernel<__nv_fp8_e4m3><<<n_tok, 256, 0, ctx.stream>>>(qkv, ldqkv, kv.pages, kv.n_pages, kv.n_heads,
+                                                                   kv.page_tokens, layer, kv.page_table,
+                                                                   kv.max_pages_per_row, tok_row, tok_pos,
+                                                                   pos_is_per_row, cos_t, sin_t);
   else
     rope_store_kernel<__nv_bfloat16><<<n_tok, 256, 0, ctx.stream>>>(qkv, ldqkv, kv.pages, kv.n_pages, kv.n_heads,
                                                                    kv.page_tokens, layer, kv.page_table,

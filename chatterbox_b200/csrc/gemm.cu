@@ -501,6 +501,167 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
 }
 
 // ================================================================================================
+// gemm_wres_kernel: persistent, WEIGHT-RESIDENT tcgen05 GEMM for the CFM transformer-block projections (K <= 512):
+//     C[M, N] = epilogue( A16[M, K] (one fp16 plane, TMA) x W16[N, K]^T (fp16 copy of the weight) )
+// Why: with K = 256 a 128 x 128 output tile moves 128 KB of operands through L2 -> shared memory for 1024 cycles of MMA;
+// at ~42 B/clk per SM of L2 read bandwidth that alone caps the one-tile-per-CTA kernel at a third of the tensor peak, and
+// the TMEM allocation, barrier set-up and epilogue of every tile sit on top.  Here a CTA loads its BN x K weight panel ONCE
+// (128 KB), then walks the row tiles: A streams through a 4-stage ring (16 KB per K block), the accumulator is double
+// buffered in TMEM (2 x BN columns) so the epilogue of tile i runs under the MMAs of tile i+1, and the epilogue stores each
+// thread's 32-column row segment straight from registers (whole 32-byte sectors, no shared-memory transpose).
+//   warp 0: TMA producer   warp 1: MMA issuer (+ TMEM owner)   warps 2-9: epilogue (lane quarter = warp % 4, column half = (warp-2)/4)
+// Algorithmic HBM bytes per launch: M*K*2 (A) + N*K*2 (W, once) + outputs (+ residual).
+// ================================================================================================
+constexpr int WR_THREADS = 320, WR_STAGES = 4, WR_W_BYTES = 131072, WR_A_STAGE = 16384;
+constexpr int WR_SMEM = WR_W_BYTES + WR_STAGES * WR_A_STAGE + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
+
+__host__ __device__ constexpr uint32_t umma_idesc_f16f16(int M, int N) {       // fp16 x fp16 -> f32, K-major A and B
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(WR_THREADS, 1)
+gemm_wres_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA, const GemmDev g,
+                 const int n_mtiles, const int n_panels) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem;                                   // [KB][BN rows x 128 B]  (SWIZZLE_128B)
+  uint8_t* sA = smem + WR_W_BYTES;                      // [WR_STAGES][128 rows x 128 B]
+  float* sBias = reinterpret_cast<float*>(sA + WR_STAGES * WR_A_STAGE);   // [BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + 1024);
+  uint64_t* w_full = bars;                  // 1
+  uint64_t* a_full = bars + 1;              // [WR_STAGES]
+  uint64_t* a_empty = a_full + WR_STAGES;   // [WR_STAGES]
+  uint64_t* acc_full = a_empty + WR_STAGES; // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = g.Kpad / TC_BK;
+  const int panel = blockIdx.x % n_panels;
+  const int n0 = panel * BN;
+  const int mt0 = blockIdx.x / n_panels, mt_step = gridDim.x / n_panels;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int s = 0; s < WR_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmapW); tma_prefetch_desc(&tmapA); }
+  for (int i = threadIdx.x; i < BN; i += WR_THREADS) sBias[i] = (g.bias && n0 + i < g.Npad) ? g.bias[n0 + i] : 0.f;
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: the weight panel once, then the A tiles of every row tile =============
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, (uint32_t)(KB * BN * 128));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * BN * 128, &tmapW, w_full, kb * TC_BK, n0);
+      uint32_t gi = 0;
+      for (int mt = mt0; mt < n_mtiles; mt += mt_step) {
+        for (int kb = 0; kb < KB; ++kb, ++gi) {
+          const int s = gi % WR_STAGES;
+          mbar_wait(&a_empty[s], ((gi / WR_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&a_full[s], WR_A_STAGE);
+          tma_load_2d(sA + s * WR_A_STAGE, &tmapA, &a_full[s], kb * TC_BK, mt * TC_BM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer ===================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16f16(TC_BM, BN);
+      mbar_wait(w_full, 0);
+      uint32_t gi = 0;
+      int it = 0;
+      for (int mt = mt0; mt < n_mtiles; mt += mt_step, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < KB; ++kb, ++gi) {
+          const int s = gi % WR_STAGES;
+          mbar_wait(&a_full[s], (gi / WR_STAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * WR_A_STAGE);
+          const uint32_t w_addr = smem_u32(sW + kb * BN * 128);
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 16; ++k4)
+            umma_bf16(d, umma_desc_sw128(a_addr + k4 * 32), umma_desc_sw128(w_addr + k4 * 32), idesc, (kb | k4) != 0 ? 1u : 0u);
+          umma_commit(&a_empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global (one 32-column row segment per thread and trip) ====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int it = 0;
+    for (int mt = mt0; mt < n_mtiles; mt += mt_step, ++it) {
+      const int buf = it & 1;
+      const int row = mt * TC_BM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 2; cc += 32) {
+        const int col = half * (BN / 2) + cc;
+        const int n = n0 + col;
+        if (n >= g.n_out) break;
+        float rres[32];
+        if (g.res && row_ok) {
+          const float4* rp = reinterpret_cast<const float4*>(g.res + (long)row * g.ldr + n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 t = rp[j]; rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rres[j] = 0.f;
+        }
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col), r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha + sBias[col + j];
+        if (g.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
+        }
+        if (row_ok) {
+          if (g.Chi) {           // one fp16 plane (c_half)
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(g.Chi) + (long)row * g.ldcb + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
+                                  pack_h2(v[8 * j + 4], v[8 * j + 5]), pack_h2(v[8 * j + 6], v[8 * j + 7]));
+          } else {
+            float4* dst = reinterpret_cast<float4*>(g.C + (long)row * g.ldc + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4((v[4 * j] + rres[4 * j]) * g.out_scale, (v[4 * j + 1] + rres[4 * j + 1]) * g.out_scale,
+                                   (v[4 * j + 2] + rres[4 * j + 2]) * g.out_scale, (v[4 * j + 3] + rres[4 * j + 3]) * g.out_scale);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+// ================================================================================================
 // SIMT reference tiles (debug only)
 // ================================================================================================
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDev g) {
@@ -769,6 +930,8 @@ template <int BN, int DUAL> static void set_tc_attr() {
 }
 void gemm_init() {
   set_tc_attr<64, 0>(); set_tc_attr<64, 1>(); set_tc_attr<128, 0>(); set_tc_attr<128, 1>(); set_tc_attr<256, 0>();
+  CBX_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM));
+  CBX_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM));
 }
 
 template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Weight& W, int tmap_idx) {
@@ -816,6 +979,28 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
 }
 
+// weight-resident persistent kernel: eligible launches (see gemm())
+template <int BN> static void launch_wres(Ctx& ctx, GemmDev g, const Weight& W) {
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; CBX_CHECK(cudaGetDevice(&dev)); CBX_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+  CUtensorMap tmA;
+  make_plane_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(g.A16), g.M, g.k_total, 128, g.lda16);   // 2-byte elements
+  const int n_mtiles = (g.M + TC_BM - 1) / TC_BM;
+  const int n_panels = g.Npad / BN;
+  int groups = n_sm / n_panels;                         // row-tile groups: every CTA of a group owns one weight panel
+  if (groups > n_mtiles) groups = n_mtiles;
+  if (groups < 1) groups = 1;
+  if (ctx.timer && ctx.timer->cls == K_GEMM_TC) {
+    ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
+    double b = (double)g.Npad * g.Kpad * 2.0 + (double)g.M * g.k_total * 2.0 + (double)g.M * g.n_out * (g.Chi ? 2.0 : 4.0);
+    if (g.res) b += (double)g.M * g.n_out * 4.0;
+    ctx.timer->bytes += b;
+  }
+  if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
+  gemm_wres_kernel<BN><<<groups * n_panels, WR_THREADS, WR_SMEM, ctx.stream>>>(W.tmap16[BN == 256 ? 2 : 1], tmA, g, n_mtiles, n_panels);
+  if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
+}
+
 template <int R> static void launch_gemv(Ctx& ctx, const GemmDev& g) {
   if (ctx.timer) ctx.timer->begin(K_GEMV, ctx.stream);
   struct End { Ctx& c; ~End() { if (c.timer) c.timer->end(K_GEMV, c.stream); } } _end{ctx};
@@ -839,6 +1024,16 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     const bool plain = !g.has_seq && g.a_mode == A_TAPS && g.ntaps == 1 && g.stride == 1 && g.pad == 0 &&
                        (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.Chi && !g.Ahi && !g.A16 &&
                        ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+    // fp16-plane Linear with a short reduction (the CFM block projections qkv / ff1 / out): weight-resident persistent kernel
+    static const bool wres_on = !(getenv("CBX_WRES") && atoi(getenv("CBX_WRES")) == 0);
+    const bool wres_epi = !g.swiglu && !g.C2 && !g.accumulate && (g.act == ACT_NONE || g.act == ACT_GELU) && !g.act_vec &&
+                          ((g.Chi && g.c_half && !g.C && !g.res) || (g.C && !g.Chi)) &&
+                          (!g.C || ((g.ldc % 4) == 0 && (g.n_out % 32) == 0 && (!g.res || (g.ldr % 4) == 0))) &&
+                          (!g.Chi || ((g.ldcb % 8) == 0 && (g.n_out % 32) == 0));
+    if (wres_on && g.A16 && W.w16 && !g.has_seq && g.ntaps == 1 && g.splitk <= 1 && wres_epi && g.M >= 4 * TC_BM) {
+      if (g.Kpad == 256 && g.Npad % 256 == 0) { launch_wres<256>(ctx, g, W); CBX_CHECK(cudaGetLastError()); return; }
+      if (g.Kpad == 512 && g.Npad % 128 == 0) { launch_wres<128>(ctx, g, W); CBX_CHECK(cudaGetLastError()); return; }
+    }
     if (plain && g.M <= 8) {
       if (g.M <= 2) launch_gemv<2>(ctx, g);
       else if (g.M <= 4) launch_gemv<4>(ctx, g);

@@ -189,7 +189,7 @@ void attention_generic(Ctx& ctx, const float* Q, const float* K, const float* V,
 struct PagedKV {
   void* pages;            // [n_layers][n_pages][2][n_heads][page_tokens][64] of kv dtype (layer-major)
   int n_pages;
-  int kv_fp32;            // 0 = bf16, 1 = fp32
+  int kv_fp32;            // element type of the cache: 0 = bf16, 1 = fp32, 2 = fp8 e4m3 (opt-in, bulk-copy kernel only)
   int n_layers, n_heads, page_tokens;
   const int* page_table;  // [rows][max_pages_per_row]
   int max_pages_per_row;

@@ -158,16 +158,17 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def set_attention_precision(self, fmt="bf16x3"):
-        """Operand format of the CFM (flow) attention: 'bf16x3' = bf16 hi/lo planes, three MMA terms (default, fp32-faithful);
-        'fp16' = one fp16 plane per operand, one term (tools/attn_precision_study.py: mel RMS 2e-5 vs the 1e-3 bar)."""
+    def set_attention_precision(self, fmt="fp16"):
+        """Operand format of the CFM (flow) attention: 'fp16' = one fp16 plane per operand, one MMA term (default; measured
+        mel RMS 1.1e-5 vs the reference at T = 2040 frames, bar 1e-3); 'bf16x3' = bf16 hi/lo planes, three terms (fp32-faithful,
+        6.7e-6)."""
         assert fmt in ("bf16x3", "fp16")
         self.h.set_option("attn_prec", fmt)
 
-    def set_cfm_activation_precision(self, fmt="bf16x2"):
+    def set_cfm_activation_precision(self, fmt="fp16"):
         """Operand format of the CFM transformer-block GEMM inputs (LayerNorm outputs, attention output, GELU output):
-        'bf16x2' = bf16 hi/lo planes, two MMA terms (default); 'fp16' = one fp16 plane, one term (study: mel RMS 1.4e-4
-        with fp16 attention as well).  The residual stream stays fp32 either way."""
+        'fp16' = one fp16 plane against an fp16 copy of the weights, one MMA term (default; measured mel RMS 1.5e-4 at
+        T = 2040 frames with fp16 attention as well); 'bf16x2' = bf16 hi/lo planes, two terms.  The residual stream stays fp32."""
         assert fmt in ("bf16x2", "fp16")
         self.h.set_option("cfm_act", fmt)
 
@@ -256,7 +257,9 @@ class Engine:
         page_table = first_page[:, None] + np.arange(max_pages, dtype=np.int64)[None, :]
         page_table = np.where(np.arange(max_pages)[None, :] < pages_per_row[:, None], page_table, 0).astype(np.int32)
         n_pages = int(pages_per_row.sum())
-        kvt = torch.float32 if kv_dtype in ("fp32", "f32", torch.float32) else torch.bfloat16
+        kvt = (torch.float32 if kv_dtype in ("fp32", "f32", torch.float32) else
+               torch.float8_e4m3fn if kv_dtype in ("fp8", "e4m3", torch.float8_e4m3fn) else torch.bfloat16)
+        kv_code = {torch.bfloat16: 0, torch.float32: 1, torch.float8_e4m3fn: 2}[kvt]
         L = self.t3_layers
         max_tokens = int(max(max_new))
         # position tables of the checkpoint bound what may be generated (reference: learned tables of 2050 / 4100 rows,
@@ -309,7 +312,7 @@ class Engine:
                  text_flat=t(text_flat), row_text_start=t(row_text_start), row_ntext=t(row_ntext),
                  row_voice=t(row_voice), row_uncond=t(row_uncond))
         qn = q_noise.to(dev, torch.float32).contiguous() if q_noise is not None else None
-        st = T3State(B, R, cfg, _ptr(kv), 1 if kvt == torch.float32 else 0, PAGE_TOKENS, _ptr(st_t["page_table"]), max_pages, n_pages,
+        st = T3State(B, R, cfg, _ptr(kv), kv_code, PAGE_TOKENS, _ptr(st_t["page_table"]), max_pages, n_pages,
                      _ptr(st_t["positions"]), _ptr(st_t["base_pos"]), _ptr(st_t["tokens"]), max_tokens,
                      _ptr(st_t["n_gen"]), _ptr(st_t["max_new"]), _ptr(st_t["done"]), _ptr(st_t["seen"]),
                      _ptr(st_t["x"]), _ptr(st_t["logits"]), LDL, float(cfg_weight), float(repetition_penalty),
@@ -334,7 +337,7 @@ class Engine:
         out = [toks[b, :int(n_gen[b])].to(torch.int64) for b in range(B)]
         # algorithmic traffic of the paged decode attention (bench.py roofline): step i of an utterance reads its
         # s0 + i + 1 cached tokens, K and V, all heads, every layer, both CFG rows
-        elt = 4 if kvt == torch.float32 else 2
+        elt = {torch.bfloat16: 2, torch.float32: 4, torch.float8_e4m3fn: 1}[kvt]
         ng = n_gen.numpy().astype(np.int64)
         ctx_tok = (s0.astype(np.int64) * ng + ng * (ng + 1) // 2).sum()
         self.stats["paged_bytes"] += float(ctx_tok) * rp * 2 * 1024 * elt * L
@@ -377,7 +380,7 @@ class Engine:
             self._pinned.append((ev, buf))
 
     # ------------------------------------------------------------------ flow
-    def flow_mel(self, tokens, ref_dicts, z=None, n_timesteps=None, cfg_rate=0.7, return_mu=False):
+    def flow_mel(self, tokens, ref_dicts, z=None, n_timesteps=None, cfg_rate=0.7, return_mu=False, finalize=True):
         """Batched equivalent of S3Token2Wav.flow_inference (s3gen.py:301-321 -> flow.py:131-198).
         tokens: list of 1-D int tensors; ref_dicts: one dict (shared voice) or a list of dicts with
         prompt_token [1,Np], prompt_feat [1,2Np,80], embedding [1,192].  z: optional list of [80, 2(Np+N)] noise
@@ -391,7 +394,11 @@ class Engine:
         n = np_len + n_gen
         L1 = PackedLayout(n, dev)
         L2 = PackedLayout(2 * n, dev)
-        L3 = L2 if self.meanflow else L2.concat_twice(dev)
+        # streaming chunk (finalize=False, reference flow.py:170-171): the encoder sees every token, the decoder drops the
+        # last pre_lookahead_len * token_mel_ratio = 6 frames (they still depend on tokens that have not arrived yet)
+        cut = 0 if finalize else 6
+        Ld = L2 if finalize else PackedLayout(2 * n - cut, dev, starts=(L2.starts, L2.rows))
+        L3 = Ld if self.meanflow else Ld.concat_twice(dev)
         tok = torch.zeros(L1.rows, dtype=torch.int32)
         cond = torch.zeros(L2.rows, 80, dtype=torch.float32)
         xvec = torch.zeros(B, 192, dtype=torch.float32)
@@ -409,7 +416,7 @@ class Engine:
         spk = torch.zeros(B, 80, dtype=torch.float32, device=dev)
         x = torch.zeros(L2.rows, 80, dtype=torch.float32, device=dev)
         for b in range(B):
-            s2, T = int(L2.starts[b]), int(2 * n[b])
+            s2, T = int(L2.starts[b]), int(2 * n[b]) - cut
             if z is not None:
                 x[s2:s2 + T] = z[b].reshape(80, T).t().to(dev, torch.float32)
             else:
@@ -419,12 +426,12 @@ class Engine:
                     _ptr(ws), ws.numel(), self._stream())
         if return_mu:
             return [mu[int(L2.starts[b]):int(L2.starts[b]) + int(2 * n[b])].clone() for b in range(B)], spk
-        self.h.call("cbx_cfm_solve", _ptr(mu), _ptr(spk), _ptr(cond), _ptr(x), C.byref(L2.c), C.byref(L3.c),
+        self.h.call("cbx_cfm_solve", _ptr(mu), _ptr(spk), _ptr(cond), _ptr(x), C.byref(Ld.c), C.byref(L3.c),
                     int(n_timesteps), float(cfg_rate), 1 if self.meanflow else 0, _ptr(ws), ws.numel(), self._stream())
         out = []
         for b in range(B):
             s2 = int(L2.starts[b])
-            out.append(x[s2 + 2 * np_len[b]:s2 + 2 * n[b]].t().contiguous())      # drop prompt frames (flow.py:196)
+            out.append(x[s2 + 2 * np_len[b]:s2 + 2 * n[b] - cut].t().contiguous())      # drop prompt frames (flow.py:196)
         return out
 
     # ------------------------------------------------------------------ HiFT
@@ -457,7 +464,8 @@ class Engine:
         s = torch.zeros(total, dtype=torch.float32, device=dev)
         wav = torch.zeros(total, dtype=torch.float32, device=dev)
         ws = self.workspace(self.h.lib.cbx_hift_workspace_bytes(self.h.h, C.byref(g)))
-        if source is None:
+        full_cache = source is not None and all(c is not None and c.numel() >= 480 * int(t) for c, t in zip(source, T))
+        if not full_cache:
             pv = None
             if phase_vec is not None:
                 pv = torch.stack([p.reshape(9).to(torch.float32) for p in phase_vec]).to(dev).contiguous()
@@ -474,10 +482,14 @@ class Engine:
                     f0d[int(LT.starts[b]):int(LT.starts[b]) + int(T[b])] = f0[b].reshape(-1).to(dev, torch.float32)
             self.h.call("cbx_hift_source", _ptr(mel), C.byref(g), _ptr(pv), _ptr(nz), int(seed), _ptr(s), _ptr(f0d),
                         C.c_void_p(0), _ptr(ws), ws.numel(), self._stream())
-        else:
+        if source is not None:        # cache_source (hifigan.py:470-472): overwrites the head of the source, full or partial
             for b in range(B):
+                if source[b] is None:
+                    continue
                 o = int(LT.starts[b]) * 480
-                s[o:o + 480 * int(T[b])] = source[b].reshape(-1).to(dev, torch.float32)
+                cs = source[b].reshape(-1).to(dev, torch.float32)
+                m = min(int(cs.numel()), 480 * int(T[b]))
+                s[o:o + m] = cs[:m]
         self.h.call("cbx_hift_decode", _ptr(mel), _ptr(s), C.byref(g), _ptr(wav), 1 if trim_fade else 0, _ptr(ws),
                     ws.numel(), self._stream())
         wavs, srcs = [], []

@@ -28,17 +28,18 @@ class S3Gen:
                        finalize=True, speech_token_lens=None, z=None):
         """reference s3gen.py:301-321 -> mel (1, 80, 2N).  `z` optionally injects the CFM noise [80, 2(Np+N)]."""
         assert ref_dict is not None, "ref_dict required (embed_ref is out of scope)"
-        assert finalize, "streaming (finalize=False) is not implemented"
         toks = torch.atleast_2d(speech_tokens)[0]
-        mel = self.engine.flow_mel([toks], ref_dict, z=None if z is None else [z], n_timesteps=n_cfm_timesteps)[0]
+        # finalize=False (streaming chunk, flow.py:170-171): the mel of the last 3 tokens (6 frames) is withheld
+        mel = self.engine.flow_mel([toks], ref_dict, z=None if z is None else [z], n_timesteps=n_cfm_timesteps,
+                                   finalize=finalize)[0]
         return mel[None]
 
     @torch.inference_mode()
     def hift_inference(self, speech_feat, cache_source=None, phase_vec=None, noise=None, seed=0, trim_fade=False, f0=None):
         """reference s3gen.py:324-327 -> (wav (1, 480T), source (1, 1, 480T))."""
         src = None
-        if cache_source is not None and cache_source.numel() > 0:
-            assert cache_source.shape[-1] == 480 * speech_feat.shape[-1], "only a full-length cache_source is supported"
+        if cache_source is not None and cache_source.numel() > 0:      # full or partial head of the source (hifigan.py:470-472)
+            assert cache_source.shape[-1] <= 480 * speech_feat.shape[-1]
             src = [cache_source]
         wavs, srcs = self.engine.hift([speech_feat[0]], source=src,
                                       phase_vec=None if phase_vec is None else [phase_vec],

@@ -55,9 +55,10 @@ int cbx_version(void);
  *   "time_kernel" = class name                   see cbx_timer_read below
  *   "decode_graph" = "1"|"0"                     every decode step replays a CUDA graph captured once per (state, capacity)
  *                                                (default 1; the call must then be issued on a capturable, non-default stream)
- *   "attn_prec" = "bf16x3"|"fp16"                operand format of the CFM attention: bf16 hi/lo planes, 3 MMA terms (default)
- *                                                or one fp16 plane, 1 term (opt-in)
- *   "cfm_act" = "bf16x2"|"fp16"                  operand format of the CFM transformer-block GEMM inputs (default bf16 hi/lo);
+ *   "attn_prec" = "fp16"|"bf16x3"                operand format of the CFM attention: one fp16 plane, 1 MMA term (default; mel RMS
+ *                                                1.1e-5 vs the reference at T = 2040) or bf16 hi/lo planes, 3 terms (fp32-faithful)
+ *   "cfm_act" = "fp16"|"bf16x2"                  operand format of the CFM transformer-block GEMM inputs: one fp16 plane against an fp16
+ *                                                copy of the weights (default; mel RMS 1.5e-4, bar 1e-3) or bf16 hi/lo planes;
  *                                                "fp16" takes effect together with attn_prec = fp16 */
 int cbx_set_option(cbx_handle* h, const char* key, const char* value);
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
@@ -80,7 +81,7 @@ typedef struct {
   int n_utts, n_rows, cfg;    /* n_rows = n_utts * (cfg ? 2 : 1); rows (2b, 2b+1) = (cond, uncond) */
   /* paged KV cache, layer-major: pages[layer][page][k|v][head][token][64] (one layer's pages are contiguous so that
    * a decode step of that layer stays inside ~1/n_layers of the pool: TLB reach) */
-  void* kv_pages; int kv_dtype; /* 0 = bf16, 1 = fp32 */ int page_tokens;
+  void* kv_pages; int kv_dtype; /* 0 = bf16, 1 = fp32 (parity mode), 2 = fp8 e4m3 (opt-in: halves the KV term of the decode roofline) */ int page_tokens;
   const int* page_table; int max_pages_per_row; /* device [n_rows][max_pages_per_row] */
   int n_pages;             /* pages in the pool (stride between layers) */
   int* positions;          /* device [n_rows] rope position of the token being fed */
@@ -205,6 +206,12 @@ int cbx_test_paged_decode(cbx_handle* h, const float* qkv, void* pages, int kv_d
  * order (N <= 1024).  tile_bn 0 = heuristic. */
 int cbx_test_gemm_splitk(cbx_handle* h, const float* A, const float* w_host, int M, int N, int K, int splitk, int tile_bn,
                          float* C, void* ws, size_t ws_bytes, cbx_stream stream);
+
+/* C[M][N] = act(A x W^T + bias) (+ res) through the fp16-plane operand format of the CFM transformer blocks (A rounded to one
+ * fp16 plane, fp16 copy of W; K = 256 / 512 take the weight-resident persistent kernel).  act: 0 none, 2 gelu.  out_half = 1:
+ * the result passes through an fp16 plane (as the qkv / ff1 projections write it) before it is widened into C. */
+int cbx_test_gemm_f16(cbx_handle* h, const float* A, const float* w_host, const float* bias_host, const float* res, int M,
+                      int N, int K, int act, int out_half, float* C, void* ws, size_t ws_bytes, cbx_stream stream);
 
 #ifdef __cplusplus
 }

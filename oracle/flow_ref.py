@@ -228,12 +228,17 @@ class FlowOracle:
         return h.transpose(1, 2).contiguous(), emb, conds.transpose(1, 2).contiguous(), mask, mel_len1
 
     @torch.inference_mode()
-    def inference(self, token, ref_dict, n_timesteps=None, z=None, noised_mels=None):
+    def inference(self, token, ref_dict, n_timesteps=None, z=None, noised_mels=None, finalize=True):
         """s3gen.py flow_inference :301-321 -> flow.py inference :131-198.  If `z` is None it is drawn
-        with torch.randn_like on the global generator exactly like flow_matching.py:216."""
+        with torch.randn_like on the global generator exactly like flow_matching.py:216.
+        finalize=False (streaming chunk, flow.py:170-171): the last pre_lookahead_len * token_mel_ratio = 6 frames of the
+        encoder output are dropped before the decoder.  The reference leaves `mask` at the untruncated length there (a
+        shape error for any input, flow.py:173-183); this restates the evident intent: every tensor is 6 frames shorter."""
         n_timesteps = n_timesteps or (2 if self.meanflow else 10)
         mu, spks, cond, mask, mel_len1 = self.encode(torch.atleast_2d(token), ref_dict["prompt_token"],
                                                      ref_dict["prompt_feat"], ref_dict["embedding"])
+        if not finalize:
+            mu, cond, mask = mu[..., :-6], cond[..., :-6], mask[..., :-6]
         if z is None:
             z = torch.randn_like(mu)
         if noised_mels is not None:

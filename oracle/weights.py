@@ -82,15 +82,17 @@ def t3_spec(text_vocab=704, n_layers=T3_LAYERS):
     return s
 
 
-def make_t3_weights(seed=0, text_vocab=704, n_layers=T3_LAYERS, head_std=0.06):
+def make_t3_weights(seed=0, text_vocab=704, n_layers=T3_LAYERS, head_std=0.06, bf16=True):
+    """bf16=False keeps the matmul weights as drawn (NOT bf16-representable): the shape of a real fp32 checkpoint, used to
+    measure what rounding the weights to bf16 (north_star: bf16 tensor-core operands) costs against the fp32 reference."""
     sd = OrderedDict()
     for key, shape, kind in t3_spec(text_vocab, n_layers):
         if kind == "w":
-            sd[key] = _randn(seed, key, shape, std=0.7 / math.sqrt(shape[-1]), bf16=True)
+            sd[key] = _randn(seed, key, shape, std=0.7 / math.sqrt(shape[-1]), bf16=bf16)
         elif kind == "w1":
-            sd[key] = _randn(seed, key, shape, std=0.3, bf16=True)
+            sd[key] = _randn(seed, key, shape, std=0.3, bf16=bf16)
         elif kind == "h":
-            w = _randn(seed, key, shape, std=head_std, bf16=True)
+            w = _randn(seed, key, shape, std=head_std, bf16=bf16)
             # ids >= 6561 (SOS/EOS/unused) are dropped by generate() (tts.py:257-262); a trained model almost never
             # emits them, so the synthetic head keeps their logits near zero (utterance length is then set by
             # max_new_tokens, SURVEY.md 8d) -- still bf16-representable (power-of-two scale)

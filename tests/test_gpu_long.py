@@ -45,7 +45,7 @@ def _forced(t3, cond, g, n, kv_dtype):
     return st["logits"][:2, :8194].cpu(), st["sampled"][0, :n].cpu()
 
 
-@pytest.mark.parametrize("kv_dtype,tol", [("fp32", 2e-3), ("bf16", 1e-1)])
+@pytest.mark.parametrize("kv_dtype,tol", [("fp32", 2e-3), ("bf16", 2e-2), ("fp8", 1.0)])
 def test_t3_teacher_forced_logits_at_long_context(golden_dir, kv_dtype, tol):
     """Logits of both CFG rows after 1 / 64 / 256 / 512 / 768 / 900 generated tokens (context 189 .. 1088) against the
     reference backbone fed the same ids.  fp32 KV: fp32-faithful; bf16 KV (bench configuration): the error of rounding
@@ -60,7 +60,7 @@ def test_t3_teacher_forced_logits_at_long_context(golden_dir, kv_dtype, tol):
         assert err < tol, f"{kv_dtype} KV, {n} tokens: max|dlogit|={err}"
 
 
-@pytest.mark.parametrize("kv_dtype,min_rate", [("fp32", 0.998), ("bf16", 0.97)])
+@pytest.mark.parametrize("kv_dtype,min_rate", [("fp32", 0.998), ("bf16", 0.99), ("fp8", 0.80)])
 def test_t3_teacher_forced_argmax_agreement(golden_dir, kv_dtype, min_rate):
     """Over 900 teacher-forced steps the engine's own greedy pick equals the reference's id at (almost) every step;
     a disagreement can only be a near-tie of the top-2 logits."""
@@ -175,8 +175,8 @@ def test_cfm_mel_at_2040_frames(golden_dir):
         try:
             mel = s3.flow_inference(g["tokens"][0], ref_dict=cg, z=z[0]).cpu()
         finally:
-            s3.engine.set_cfm_activation_precision("bf16x2")
-            s3.engine.set_attention_precision("bf16x3")
+            s3.engine.set_cfm_activation_precision("fp16")
+            s3.engine.set_attention_precision("fp16")
         rms = ((mel - g["mel"]) ** 2).mean().sqrt().item()
         mx = (mel - g["mel"]).abs().max().item()
         print(f"[long flow] operands {fmt}: mel RMS {rms:.3e}, max {mx:.3e} (mel std {g['mel'].std():.3f})")

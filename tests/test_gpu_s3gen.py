@@ -44,14 +44,13 @@ def test_cfm_mel_matches_reference(golden_dir):
         assert mel.shape == case["mel"].shape and rms < 1e-3, f"n={case['n']} mel RMS {rms}"
 
 
-@pytest.mark.skipif(os.environ.get("CBX_EXPERIMENTAL") != "1",
-                    reason="fp16 single-term attention: written after the round's GPU budget was spent; first GPU run pending")
 def test_cfm_mel_with_fp16_attention_stays_inside_the_bar(golden_dir):
     """Opt-in operand format of the CFM attention (one fp16 plane, one MMA term instead of three bf16 terms): the CPU study
     tools/attn_precision_study.py predicts a mel RMS of ~2e-5; the bar is the same 1e-3."""
     from oracle import weights as W
     g, fsd, hsd, s3 = _setup(golden_dir)
     s3.engine.set_attention_precision("fp16")
+    s3.engine.set_cfm_activation_precision("bf16x2")
     try:
         for case in g["cases"]:
             _, cg = W.make_conds(seed=1234, n_gen_prompt=case["n_prompt"])
@@ -59,11 +58,9 @@ def test_cfm_mel_with_fp16_attention_stays_inside_the_bar(golden_dir):
             rms = ((mel - case["mel"]) ** 2).mean().sqrt().item()
             assert mel.shape == case["mel"].shape and rms < 1e-3, f"n={case['n']} mel RMS {rms} (fp16 attention)"
     finally:
-        s3.engine.set_attention_precision("bf16x3")
+        s3.engine.set_cfm_activation_precision("fp16")
 
 
-@pytest.mark.skipif(os.environ.get("CBX_EXPERIMENTAL") != "1",
-                    reason="fp16 single-plane block activations: written after the round's GPU budget was spent")
 def test_cfm_mel_with_fp16_block_activations_stays_inside_the_bar(golden_dir):
     """Opt-in: every GEMM input inside the CFM transformer blocks as ONE fp16 plane (A fp16 x W bf16, one MMA term) on top
     of the fp16 attention; residual stream fp32.  CPU study: mel RMS ~1.4e-4; same 1e-3 bar."""
@@ -78,8 +75,8 @@ def test_cfm_mel_with_fp16_block_activations_stays_inside_the_bar(golden_dir):
             rms = ((mel - case["mel"]) ** 2).mean().sqrt().item()
             assert mel.shape == case["mel"].shape and rms < 1e-3, f"n={case['n']} mel RMS {rms} (fp16 block activations)"
     finally:
-        s3.engine.set_cfm_activation_precision("bf16x2")
-        s3.engine.set_attention_precision("bf16x3")
+        s3.engine.set_cfm_activation_precision("fp16")
+        s3.engine.set_attention_precision("fp16")
 
 
 def test_cfm_batch_equals_single(golden_dir):
