@@ -66,6 +66,8 @@ int cbx_create(int device, cbx_handle** out) {
   if (e && std::string(e) == "simt") h->attn_impl = 1;
   e = getenv("CBX_DECODE_GRAPH");
   if (e) h->decode_graph = atoi(e);
+  e = getenv("CBX_DECODE_PDL");
+  if (e) h->decode_pdl = atoi(e);
   try {        // per-device kernel attributes, before any launch or stream capture
     gemm_init(); attention_tc_init(); paged_attention_init(); t3_sample_init();
   } catch (const std::exception& ex) {
@@ -116,6 +118,7 @@ int cbx_set_option(cbx_handle* h, const char* key, const char* value) {
   if (k == "gemm") h->gemm_impl = (v == "simt") ? 1 : 0;
   else if (k == "attn") h->attn_impl = (v == "simt") ? 1 : 0;
   else if (k == "decode_graph") h->decode_graph = (v == "1" || v == "on") ? 1 : 0;
+  else if (k == "decode_pdl") h->decode_pdl = (v == "1" || v == "on") ? 1 : 0;
   else if (k == "attn_prec") h->attn_f16 = (v == "fp16") ? 1 : 0;     // CFM attention operand format (default bf16x3)
   else if (k == "cfm_act") h->cfm_act_f16 = (v == "fp16") ? 1 : 0;   // CFM transformer-block GEMM inputs (default bf16x2)
   else if (k == "time_kernel") {
@@ -442,6 +445,17 @@ int cbx_test_gemm_f16(cbx_handle* h, const float* A, const float* w_host, const 
   CBX_CHECK(cudaStreamSynchronize(c.stream));
   free_weight(W);
   h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+
+/* hardware probe: D[128][64] = A[shift .. shift+127][64] . W[64][64]^T with A (bf16 [160][64], device) staged ONCE in shared
+ * memory and addressed through a row-shifted SWIZZLE_128B descriptor; mode 1 also sets the descriptor's base-offset field */
+int cbx_test_umma_rowshift(cbx_handle* h, const void* A_bf16, const void* W_bf16, int shift, int mode, float* C, cbx_stream stream) {
+  if (!h) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  Ctx c = make_ctx(h, nullptr, 0, stream);
+  umma_rowshift_probe(c, static_cast<const __nv_bfloat16*>(A_bf16), static_cast<const __nv_bfloat16*>(W_bf16), shift, mode, C);
+  CBX_CHECK(cudaStreamSynchronize(c.stream));
   CBX_GUARD_END(h)
 }
 

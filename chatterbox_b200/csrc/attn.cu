@@ -520,6 +520,8 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.n_heads;
   const int per_slot = H * p.nsplit;
+  pdl_wait();                                             // (decode step) the QKV projection has completed
+  pdl_launch_dependents();
   const int n_live = p.n_live ? *p.n_live : 0x7fffffff;
   const long slab_e = (long)PB_TOK * 64;                  // elements per slab
   const long page_stride = 2L * H * slab_e;
@@ -714,6 +716,8 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
 __global__ void paged_combine_kernel(const float* scratch, float* out, int ldo, int H, int nsplit,
                                      __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, const int* n_live) {
   const int slot = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
   if (n_live && slot >= *n_live) return;
   const float* sp = scratch + ((long)slot * H + head) * nsplit * 66;
   float mt = -INFINITY;
@@ -766,9 +770,9 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
     if (!n_sm) { int dev = 0; CBX_CHECK(cudaGetDevice(&dev)); CBX_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
     const int n_items = n_slots * kv.n_heads * nsplit;
     const int g = n_items < PB_OCC * n_sm ? n_items : PB_OCC * n_sm;
-    if (kv.kv_fp32 == 1) paged_bulk_kernel<float><<<g, PB_THREADS, pb_smem_bytes<float>(), ctx.stream>>>(p, n_items);
-    else if (kv.kv_fp32 == 2) paged_bulk_kernel<__nv_fp8_e4m3><<<g, PB_THREADS, pb_smem_bytes<__nv_fp8_e4m3>(), ctx.stream>>>(p, n_items);
-    else paged_bulk_kernel<__nv_bfloat16><<<g, PB_THREADS, pb_smem_bytes<__nv_bfloat16>(), ctx.stream>>>(p, n_items);
+    if (kv.kv_fp32 == 1) launch_kernel(ctx, paged_bulk_kernel<float>, dim3(g), dim3(PB_THREADS), (size_t)pb_smem_bytes<float>(), p, n_items);
+    else if (kv.kv_fp32 == 2) launch_kernel(ctx, paged_bulk_kernel<__nv_fp8_e4m3>, dim3(g), dim3(PB_THREADS), (size_t)pb_smem_bytes<__nv_fp8_e4m3>(), p, n_items);
+    else launch_kernel(ctx, paged_bulk_kernel<__nv_bfloat16>, dim3(g), dim3(PB_THREADS), (size_t)pb_smem_bytes<__nv_bfloat16>(), p, n_items);
   } else {
     if (kv.kv_fp32 == 1) paged_decode_kernel<float><<<grid, 128, 0, ctx.stream>>>(p);
     else paged_decode_kernel<__nv_bfloat16><<<grid, 128, 0, ctx.stream>>>(p);
@@ -776,7 +780,8 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
   if (ctx.timer) ctx.timer->end(K_PAGED, ctx.stream);
   if (nsplit > 1) {
     ctx.launches++;
-    paged_combine_kernel<<<dim3(n_slots, kv.n_heads), 64, 0, ctx.stream>>>(scratch, out, ldo, kv.n_heads, nsplit, out_hi, out_lo, p.n_live);
+    launch_kernel(ctx, paged_combine_kernel, dim3(n_slots, kv.n_heads), dim3(64), 0, (const float*)scratch, out, ldo, kv.n_heads, nsplit,
+                  out_hi, out_lo, p.n_live);
   }
   CBX_CHECK(cudaGetLastError());
 }

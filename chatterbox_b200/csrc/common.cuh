@@ -121,6 +121,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still draining; griddepcontrol.wait blocks until that predecessor has completed and its writes are visible
+// (a no-op for ordinary launches).  Every kernel of the decode step waits before its first global access and releases
+// its own dependents right after, so launch latency and CTA ramp-up of kernel N+1 overlap the tail of kernel N.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------------
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp, .sync.aligned

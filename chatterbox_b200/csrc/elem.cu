@@ -275,6 +275,8 @@ __global__ void __launch_bounds__(1024) t3_sample_kernel(T3SampleDev p) {
   float* skey = sh + 64;                        // [SV_PAD] sort keys (top-k / top-p only)
   int* sidx = reinterpret_cast<int*>(skey + SV_PAD);   // [SV_PAD]
   const int j = blockIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
   if (p.n_act && j >= *p.n_act) return;         // retired slot (device-side compaction, t3_compact_kernel)
   const int utt = p.act_utt[j];
   if (p.done[utt]) return;
@@ -441,7 +443,7 @@ void t3_sample(Ctx& ctx, const T3SampleDev& p, int n_act) {
   if (ctx.dry || n_act == 0) return;
   const int smem = T3_SAMPLE_SMEM;
   ctx.launches++;
-  t3_sample_kernel<<<n_act, 1024, smem, ctx.stream>>>(p);
+  launch_kernel(ctx, t3_sample_kernel, dim3(n_act), dim3(1024), (size_t)smem, p);
   CBX_CHECK(cudaGetLastError());
 }
 
@@ -455,6 +457,8 @@ __global__ void __launch_bounds__(1024) t3_compact_kernel(int* act_utt, int* n_a
                                                           const int* done, int rows_per) {
   __shared__ int wsum[32];
   __shared__ int s_base;
+  pdl_wait();
+  pdl_launch_dependents();
   const int n = *n_act;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_base = 0;
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(1024) t3_compact_kernel(int* act_utt, int* n_a
 void t3_compact(Ctx& ctx, int* act_utt, int* n_act, int* src_slot, int* slot_row, int* m_live, const int* done, int rows_per) {
   if (ctx.dry) return;
   ctx.launches++;
-  t3_compact_kernel<<<1, 1024, 0, ctx.stream>>>(act_utt, n_act, src_slot, slot_row, m_live, done, rows_per);
+  launch_kernel(ctx, t3_compact_kernel, dim3(1), dim3(1024), 0, act_utt, n_act, src_slot, slot_row, m_live, done, rows_per);
   CBX_CHECK(cudaGetLastError());
 }
 
@@ -500,6 +504,8 @@ void t3_compact(Ctx& ctx, int* act_utt, int* n_act, int* src_slot, int* slot_row
 __global__ void __launch_bounds__(256) resid_norm_kernel(const ResidNormDev p) {
   __shared__ float sh[32];
   const int r = blockIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
   if (p.m_live && r >= *p.m_live) return;
   const int i = threadIdx.x * 4;
   const bool on = i < p.dim;
@@ -556,7 +562,7 @@ void resid_norm(Ctx& ctx, const ResidNormDev& p, int rows) {
   if (ctx.dry || rows == 0) return;
   CBX_REQUIRE(p.dim <= 1024 && p.dim % 4 == 0, "resid_norm handles rows of <= 1024 floats");
   ctx.launches++;
-  resid_norm_kernel<<<rows, 256, 0, ctx.stream>>>(p);
+  launch_kernel(ctx, resid_norm_kernel, dim3(rows), dim3(256), 0, p);
   CBX_CHECK(cudaGetLastError());
 }
 

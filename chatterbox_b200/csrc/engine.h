@@ -80,6 +80,7 @@ struct cbx_handle {
   // "decode_graph" option (default on): a decode step is captured once per (state, capacity, workspace) into a CUDA
   // graph and replayed for every step; the executables are cached on the handle.
   int decode_graph = 1;
+  int decode_pdl = 1;        // "decode_pdl": kernels of a decode step are launched with programmatic stream serialization
   std::map<uint64_t, cbx::DecodeGraph> decode_graphs;
   std::vector<void*> owned;                      // device allocations to free
 };

@@ -145,6 +145,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;             // N tiles fastest: CTAs sharing an A tile run together (L2 reuse)
   const int m0 = blockIdx.y * TC_BM;
+  pdl_wait();                                 // (decode step) the producer of A / m_live has completed
+  pdl_launch_dependents();
   if (g.m_live && m0 >= *g.m_live) return;    // device-side retirement: the row tile holds no live decode row
   // split-K: blockIdx.z owns K blocks [kb0, kb0 + KB) and writes its partial sums to C + z * split_stride (plain
   // stores in a fixed order: the reduction happens in the consumer kernel, deterministically)
@@ -712,6 +714,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDev g) {
 // ================================================================================================
 template <int R, int NB>
 __global__ void __launch_bounds__(128) gemv_kernel(const GemmDev g) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb0 = blockIdx.x * NB;
   float acc[R][NB];
@@ -975,7 +979,8 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
     ctx.timer->bytes += b;
   }
   if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
-  gemm_tc_kernel<BN, DUAL><<<grid, TC_THREADS, TcCfg<BN, DUAL>::SMEM, ctx.stream>>>(g.A16 ? W.tmap16[tmap_idx] : W.tmap[tmap_idx], tmA, tmA2, g);
+  launch_kernel(ctx, gemm_tc_kernel<BN, DUAL>, grid, dim3(TC_THREADS), (size_t)TcCfg<BN, DUAL>::SMEM,
+                g.A16 ? W.tmap16[tmap_idx] : W.tmap[tmap_idx], tmA, tmA2, g);
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
 }
 
@@ -1005,9 +1010,9 @@ template <int R> static void launch_gemv(Ctx& ctx, const GemmDev& g) {
   if (ctx.timer) ctx.timer->begin(K_GEMV, ctx.stream);
   struct End { Ctx& c; ~End() { if (c.timer) c.timer->end(K_GEMV, c.stream); } } _end{ctx};
   if (g.Npad <= 2048) {
-    gemv_kernel<R, 2><<<(g.Npad + 1) / 2, 128, 0, ctx.stream>>>(g);
+    launch_kernel(ctx, gemv_kernel<R, 2>, dim3((g.Npad + 1) / 2), dim3(128), 0, g);
   } else {
-    gemv_kernel<R, 4><<<(g.Npad + 3) / 4, 128, 0, ctx.stream>>>(g);
+    launch_kernel(ctx, gemv_kernel<R, 4>, dim3((g.Npad + 3) / 4), dim3(128), 0, g);
   }
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include <map>
+#include <cstring>
 #include <vector>
 #include <string>
 
@@ -134,7 +135,23 @@ struct Ctx {
   int attn_f16 = 0;       // CFM attention operands: 0 = bf16 hi/lo planes, 3 MMA terms (default), 1 = one fp16 plane, 1 term
   int cfm_act_f16 = 0;    // CFM transformer-block GEMM inputs: 0 = bf16 hi/lo planes, 2 terms (default), 1 = one fp16 plane
   long launches = 0;      // kernels launched through this context
+  bool pdl = false;       // launch with programmatic stream serialization (decode step; kernels call pdl_wait())
 };
+
+// kernel launch through cudaLaunchKernelEx so that the PDL attribute can ride along (ctx.pdl)
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(Ctx& ctx, void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx.stream;
+  cudaLaunchAttribute at[1];
+  if (ctx.pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  CBX_CHECK(cudaLaunchKernelEx(&cfg, k, static_cast<KArgs>(args)...));
+}
 
 // ---- weights ------------------------------------------------------------------------------------
 // host fp32 [N][K] (row-major) -> device packed bf16 + TMA maps.  taps/cin describe conv weights given
@@ -146,6 +163,7 @@ void free_weight(Weight& W);
 void make_tmaps_for(Weight& W);   // (re)build the TMA maps of a weight whose .w/.Npad/.Kpad are set
 
 // ---- GEMM ---------------------------------------------------------------------------------------
+void umma_rowshift_probe(Ctx& ctx, const __nv_bfloat16* A, const __nv_bfloat16* W, int shift, int mode, float* C);   // probe.cu
 void gemm_init();   // per device: dynamic shared memory opt-in of every tcgen05 instantiation
 GemmDev gemm_args_linear(const float* A, int lda, int M, const Weight& W, float* C, int ldc);
 void gemm(Ctx& ctx, GemmDev g, const Weight& W);

@@ -352,6 +352,8 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
   const int S = cap * rows_per;
   const size_t mark = ctx.ws.mark();
   const DecodeTiles tl = decode_tiles(S);
+  const bool pdl_saved = ctx.pdl;
+  ctx.pdl = h->decode_pdl != 0;     // every kernel of the step waits (griddepcontrol.wait) before its first global access
   const int max_split = 8;
   float* xn = ctx.ws.get<float>((size_t)S * 1024);
   float* qkv = ctx.ws.get<float>((size_t)S * 3072);
@@ -435,6 +437,7 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
   GemmDev gh = gemm_args_linear(xn, 1024, S, m.head, st.logits, st.ldl);
   feed(gh, xn, xn_hi, xn_lo, 1024);
   gemm(ctx, gh, m.head);
+  ctx.pdl = pdl_saved;
   ctx.ws.reset(mark);
 }
 
@@ -462,7 +465,7 @@ void t3_decode(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap, int n_s
   uint64_t key = fnv1a(&st, sizeof(st));
   const void* wsb = ctx.ws.base; const size_t wsc = ctx.ws.cap;
   key = fnv1a(&cap, sizeof(cap), key); key = fnv1a(&wsb, sizeof(wsb), key); key = fnv1a(&wsc, sizeof(wsc), key);
-  key = fnv1a(&ctx.gemm_impl, sizeof(int), key);
+  key = fnv1a(&ctx.gemm_impl, sizeof(int), key); key = fnv1a(&h->decode_pdl, sizeof(int), key);
   auto it = h->decode_graphs.find(key);
   if (it == h->decode_graphs.end()) {
     if (h->decode_graphs.size() >= 48) {          // bound the cache: drop everything (states of finished batches)

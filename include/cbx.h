@@ -213,6 +213,10 @@ int cbx_test_gemm_splitk(cbx_handle* h, const float* A, const float* w_host, int
 int cbx_test_gemm_f16(cbx_handle* h, const float* A, const float* w_host, const float* bias_host, const float* res, int M,
                       int N, int K, int act, int out_half, float* C, void* ws, size_t ws_bytes, cbx_stream stream);
 
+/* hardware probe: D[128][64] = A[shift .. shift+127][0..63] . W[64][64]^T, A (bf16 [160][64]) staged once in shared memory and
+ * read through a row-shifted SWIZZLE_128B UMMA descriptor (mode 1: with the descriptor's base-offset field set) */
+int cbx_test_umma_rowshift(cbx_handle* h, const void* A_bf16, const void* W_bf16, int shift, int mode, float* C, cbx_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
