@@ -29,7 +29,7 @@ class T3State(C.Structure):
                 ("min_p", C.c_float), ("top_p", C.c_float),
                 ("q_noise", C.c_void_p), ("seed", C.c_ulonglong), ("sampler", C.c_int), ("top_k", C.c_int),
                 ("act_utt", C.c_void_p), ("n_act", C.c_void_p), ("src_slot", C.c_void_p), ("slot_row", C.c_void_p),
-                ("m_live", C.c_void_p), ("force_tokens", C.c_void_p), ("sampled_out", C.c_void_p)]
+                ("m_live", C.c_void_p), ("force_tokens", C.c_void_p), ("sampled_out", C.c_void_p), ("act_fp16", C.c_int)]
 
 
 class HiftGeom(C.Structure):

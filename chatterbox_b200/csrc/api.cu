@@ -69,7 +69,7 @@ int cbx_create(int device, cbx_handle** out) {
   e = getenv("CBX_DECODE_PDL");
   if (e) h->decode_pdl = atoi(e);
   try {        // per-device kernel attributes, before any launch or stream capture
-    gemm_init(); attention_tc_init(); paged_attention_init(); t3_sample_init();
+    gemm_init(); attention_tc_init(); paged_attention_init(); t3_sample_init(); hift_conv_init();
   } catch (const std::exception& ex) {
     delete h;
     return CBX_ERR_CUDA;

@@ -365,6 +365,7 @@ struct PagedDev {
   // (llama3 RoPE tables cos_t / sin_t [pos][32]), appends k / v to the cache and attends to them from registers
   int fuse_rope; const float* cos_t; const float* sin_t;
   const int* n_live;                  // optional device scalar: slots >= *n_live are retired (CTA exits)
+  __half* out16;                      // when set: the output as one fp16 plane
 };
 
 template <typename T>
@@ -702,7 +703,8 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
       if (p.nsplit == 1) {
         const float ov = lt > 0.f ? ot / lt : 0.f;
         const long oidx = (long)slot * p.ldo + head * 64 + d;
-        if (p.out_hi) { __nv_bfloat16 hh, ll; split_bf16(ov, hh, ll); p.out_hi[oidx] = hh; p.out_lo[oidx] = ll; }
+        if (p.out16) p.out16[oidx] = __float2half_rn(ov);
+        else if (p.out_hi) { __nv_bfloat16 hh, ll; split_bf16(ov, hh, ll); p.out_hi[oidx] = hh; p.out_lo[oidx] = ll; }
         else p.out[oidx] = ov;
       } else {
         float* sp = p.scratch + (((long)slot * H + head) * p.nsplit + split) * 66;
@@ -714,7 +716,7 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
 }
 
 __global__ void paged_combine_kernel(const float* scratch, float* out, int ldo, int H, int nsplit,
-                                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, const int* n_live) {
+                                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, const int* n_live, __half* out16) {
   const int slot = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
   pdl_wait();
   pdl_launch_dependents();
@@ -732,7 +734,8 @@ __global__ void paged_combine_kernel(const float* scratch, float* out, int ldo, 
   }
   const float ov = lt > 0.f ? ot / lt : 0.f;
   const long oi = (long)slot * ldo + head * 64 + d;
-  if (out_hi) { __nv_bfloat16 hh, ll; split_bf16(ov, hh, ll); out_hi[oi] = hh; out_lo[oi] = ll; }
+  if (out16) out16[oi] = __float2half_rn(ov);
+  else if (out_hi) { __nv_bfloat16 hh, ll; split_bf16(ov, hh, ll); out_hi[oi] = hh; out_lo[oi] = ll; }
   else out[oi] = ov;
 }
 
@@ -757,6 +760,8 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
   p.scale = 0.125f;
   p.fuse_rope = opts ? opts->fuse_rope : 0; p.cos_t = opts ? opts->cos_t : nullptr; p.sin_t = opts ? opts->sin_t : nullptr;
   p.n_live = opts ? opts->n_live : nullptr;
+  p.out16 = opts ? opts->out16 : nullptr;
+  CBX_REQUIRE(!p.out16 || (kv.page_tokens == PB_TOK && !(opts && opts->impl == 1)), "fp16 output needs the bulk-copy kernel");
   // default: the bulk-copy (TMA engine) kernel; CBX_PAGED=ldg keeps the round-1 __ldg kernel for A/B runs
   static const bool force_ldg = getenv("CBX_PAGED") && std::string(getenv("CBX_PAGED")) == "ldg";
   const bool bulk = kv.page_tokens == PB_TOK && !(force_ldg && !p.fuse_rope) && !(opts && opts->impl == 1);
@@ -781,7 +786,7 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
   if (nsplit > 1) {
     ctx.launches++;
     launch_kernel(ctx, paged_combine_kernel, dim3(n_slots, kv.n_heads), dim3(64), 0, (const float*)scratch, out, ldo, kv.n_heads, nsplit,
-                  out_hi, out_lo, p.n_live);
+                  out_hi, out_lo, p.n_live, p.out16);
   }
   CBX_CHECK(cudaGetLastError());
 }

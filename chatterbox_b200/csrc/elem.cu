@@ -543,7 +543,10 @@ __global__ void __launch_bounds__(256) resid_norm_kernel(const ResidNormDev p) {
     }
   }
   if (!on) return;
-  if (p.yhi) {
+  if (p.y16) {
+    const __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+    *reinterpret_cast<uint2*>(p.y16 + (long)r * p.ldy + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  } else if (p.yhi) {
     uint32_t h0, l0, h1, l1;
     {
       __nv_bfloat16 a, b, c, d;

@@ -105,6 +105,13 @@ void hift_source_run(cbx_handle* h, Ctx& ctx, const float* mel, const cbx_hift_g
 void hift_decode_run(cbx_handle* h, Ctx& ctx, const float* mel, const float* s, const cbx_hift_geom& g, float* wav,
                      int trim_fade);
 
+// staged-tile ResBlock convolutions (hift_conv.cu)
+void hift_conv_init();
+void snake_planes(Ctx& ctx, const float* x, int C, const float* alpha, __nv_bfloat16* hi, __nv_bfloat16* lo, const cbx_layout& L);
+void hift_conv(Ctx& ctx, const Weight& W, int C, int k, int dil, const cbx_layout& L, const __nv_bfloat16* in_hi,
+               const __nv_bfloat16* in_lo, int mode, const float* alpha, const float* res, float* out, int accumulate,
+               float scale, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo);
+
 // helpers shared by the model files
 const HostTensor& host_tensor(cbx_handle* h, const std::string& name);
 bool has_tensor(cbx_handle* h, const std::string& name);

@@ -316,7 +316,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
             const float v0 = st[rr * 33 + 2 * lane] * g.alpha + b0, v1 = st[rr * 33 + 2 * lane + 1] * g.alpha + b1;
             float v = act_apply_slow(ACT_SILU, v0, 0.f) * v1;
             if (!rv) v = 0.f;
-            if (g.Chi) {
+            if (g.Chi && g.c_half) {        // one fp16 plane
+              reinterpret_cast<__half*>(g.Chi)[(long)(m0 + q * 32 + rr) * g.ldcb + nout] = __float2half_rn(v);
+            } else if (g.Chi) {
               __nv_bfloat16 hh, ll;
               split_bf16(v, hh, ll);
               g.Chi[(long)(m0 + q * 32 + rr) * g.ldcb + nout] = hh;
@@ -1021,6 +1023,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
   if (g.a_mode == A_TAPS) CBX_REQUIRE(g.ctap % 64 == 0, "TAPS mode needs 64-channel chunks");
   if (ctx.dry) return;
   CBX_REQUIRE(!g.c_half || (ctx.gemm_impl == 0 && g.Chi && !g.C && !g.C2 && !g.res && g.M > 8), "fp16 plane output needs the tcgen05 planes-only epilogue");
+  CBX_REQUIRE(!g.A16 || W.w16 != nullptr, "fp16 activations need the fp16 copy of the weight");
   ctx.launches++;
   if (ctx.gemm_impl == 1) {
     dim3 grid((g.M + 63) / 64, (g.Npad + 63) / 64);

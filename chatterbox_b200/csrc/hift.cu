@@ -5,6 +5,7 @@
 // activations are fused into the epilogue of the conv that produces their input.
 #include "engine.h"
 #include <cmath>
+#include <cstdlib>
 
 namespace cbx {
 
@@ -122,11 +123,32 @@ void hift_source_run(cbx_handle* h, Ctx& ctx, const float* mel, const cbx_hift_g
               reinterpret_cast<const long*>(g.sample_start), LT.n_seq, LT.max_len, seed);
 }
 
-struct RbBufs { float *xt, *t1, *xr; };
+struct RbBufs { float *xt, *t1, *xr; __nv_bfloat16 *p_hi, *p_lo, *t_hi, *t_lo; bool planes; };
+
+// ResBlock.forward (hifigan.py:154-161) on the shared-memory-staged conv kernel (hift_conv.cu): every conv input travels
+// as bf16 hi/lo planes written by its producer's epilogue; Snake, bias, residual, 1/3 scaling and the stage sum are all
+// epilogue work.  in: x (read only).  out: dst (+)= resblock(x) * out_scale
+static void run_resblock_planes(Ctx& ctx, HiftResBlock& rb, const float* x, int C, const cbx_layout& L, float* dst,
+                                float out_scale, int accumulate, RbBufs& b) {
+  const int dil[3] = {1, 3, 5};
+  const int k = rb.k;
+  snake_planes(ctx, x, C, rb.a1[0].p, b.p_hi, b.p_lo, L);                                   // snake(x; a1_0)
+  for (int j = 0; j < 3; ++j) {
+    // conv1_j (dilated) + Snake(a2_j) -> planes t
+    hift_conv(ctx, rb.c1[j], C, k, dil[j], L, b.p_hi, b.p_lo, 0, rb.a2[j].p, nullptr, nullptr, 0, 1.f, b.t_hi, b.t_lo);
+    const float* res = (j == 0) ? x : b.xr;
+    if (j < 2) {    // conv2_j + residual -> xr (fp32) and the next branch's snake(xr; a1_{j+1}) as planes
+      hift_conv(ctx, rb.c2[j], C, k, 1, L, b.t_hi, b.t_lo, 1, rb.a1[j + 1].p, res, b.xr, 0, 1.f, b.p_hi, b.p_lo);
+    } else {        // last branch: into the stage sum
+      hift_conv(ctx, rb.c2[j], C, k, 1, L, b.t_hi, b.t_lo, 2, nullptr, res, dst, accumulate, out_scale, nullptr, nullptr);
+    }
+  }
+}
 
 // ResBlock.forward (hifigan.py:154-161).  in: x (read only).  out: dst (+)= (resblock(x)) * out_scale
 static void run_resblock(Ctx& ctx, HiftResBlock& rb, const float* x, int C, const cbx_layout& L, float* dst,
                          float out_scale, int accumulate, RbBufs& b) {
+  if (b.planes) { run_resblock_planes(ctx, rb, x, C, L, dst, out_scale, accumulate, b); return; }
   const int dil[3] = {1, 3, 5};
   const int k = rb.k;
   ew_act(ctx, x, C, b.xt, C, L.rows, C, ACT_SNAKE, 0.f, rb.a1[0].p);
@@ -174,6 +196,11 @@ void hift_decode_run(cbx_handle* h, Ctx& ctx, const float* mel, const float* s, 
     float* si = ctx.ws.get<float>(nout);
     float* xs = ctx.ws.get<float>(nout);
     RbBufs b; b.xt = ctx.ws.get<float>(nout); b.t1 = ctx.ws.get<float>(nout); b.xr = ctx.ws.get<float>(nout);
+    // the planes of the staged-conv path live in the same two buffers (hi + lo = 4 bytes per element)
+    static const bool legacy = getenv("CBX_HIFT") && std::string(getenv("CBX_HIFT")) == "legacy";
+    b.planes = !legacy && ctx.gemm_impl == 0;
+    b.p_hi = reinterpret_cast<__nv_bfloat16*>(b.xt); b.p_lo = b.p_hi + (size_t)Lout.rows * C;
+    b.t_hi = reinterpret_cast<__nv_bfloat16*>(b.t1); b.t_lo = b.t_hi + (size_t)Lout.rows * C;
     ew_act(ctx, x, Cin, xl, Cin, Lin.rows, Cin, ACT_LRELU, 0.1f, nullptr);                          // :418
     // ups[i]: polyphase ConvTranspose -> rows q*u + phi (shifted by one row at the last stage for the reflection pad)
     const int shift = (i == 2) ? 1 : 0;

@@ -1,6 +1,7 @@
 // Declarations of the small kernels in elem.cu (model-specific glue that is not a GEMM or attention).
 #pragma once
 #include "ops.h"
+#include <cuda_fp16.h>
 
 namespace cbx {
 
@@ -48,6 +49,7 @@ struct ResidNormDev {
   const float* w; const float* b;        // norm weight (null: residual update only) and LayerNorm bias
   int layernorm; float eps;
   __nv_bfloat16* yhi; __nv_bfloat16* ylo; float* y; int ldy;   // bf16 hi/lo planes, or fp32 when yhi == null
+  __half* y16;                           // one fp16 plane instead (fp16-activation decode mode)
   int dim;
   const int* m_live;                     // optional device scalar: rows >= *m_live exit
 };

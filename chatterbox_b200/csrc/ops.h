@@ -217,6 +217,7 @@ struct PagedOpts {
   const float* cos_t = nullptr; const float* sin_t = nullptr;   // [pos][32] RoPE tables
   const int* n_live = nullptr;        // device scalar: slots >= *n_live exit (device-side retirement)
   int impl = 0;                       // 1 = round-1 __ldg kernel (tests / A-B runs)
+  __half* out16 = nullptr;            // write the output as one fp16 plane [slots][ldo] (fp16-activation decode mode)
 };
 void paged_attention_init();
 void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* slot_row,

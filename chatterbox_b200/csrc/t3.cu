@@ -36,10 +36,10 @@ static void t3_finalize_gpt(cbx_handle* h) {
   for (int i = 0; i < L; ++i) {
     const std::string p = "t3.tfmr.h." + std::to_string(i) + ".";
     T3Layer& ly = m.layers[i];
-    pack_linear(ly.qkv, transposed(host_tensor(h, p + "attn.c_attn.weight")).data(), host_tensor(h, p + "attn.c_attn.bias").data.data(), 3072, 1024);
-    pack_linear(ly.o, transposed(host_tensor(h, p + "attn.c_proj.weight")).data(), host_tensor(h, p + "attn.c_proj.bias").data.data(), 1024, 1024);
-    pack_linear(ly.gu, transposed(host_tensor(h, p + "mlp.c_fc.weight")).data(), host_tensor(h, p + "mlp.c_fc.bias").data.data(), 4096, 1024);
-    pack_linear(ly.down, transposed(host_tensor(h, p + "mlp.c_proj.weight")).data(), host_tensor(h, p + "mlp.c_proj.bias").data.data(), 1024, 4096);
+    pack_linear(ly.qkv, transposed(host_tensor(h, p + "attn.c_attn.weight")).data(), host_tensor(h, p + "attn.c_attn.bias").data.data(), 3072, 1024, true);
+    pack_linear(ly.o, transposed(host_tensor(h, p + "attn.c_proj.weight")).data(), host_tensor(h, p + "attn.c_proj.bias").data.data(), 1024, 1024, true);
+    pack_linear(ly.gu, transposed(host_tensor(h, p + "mlp.c_fc.weight")).data(), host_tensor(h, p + "mlp.c_fc.bias").data.data(), 4096, 1024, true);
+    pack_linear(ly.down, transposed(host_tensor(h, p + "mlp.c_proj.weight")).data(), host_tensor(h, p + "mlp.c_proj.bias").data.data(), 1024, 4096, true);
     ly.ln1 = upload_tensor(h, p + "ln_1.weight"); ly.ln1_b = upload_tensor(h, p + "ln_1.bias");
     ly.ln2 = upload_tensor(h, p + "ln_2.weight"); ly.ln2_b = upload_tensor(h, p + "ln_2.bias");
   }
@@ -56,7 +56,7 @@ static void t3_finalize_gpt(cbx_handle* h) {
   m.max_pos = (int)host_tensor(h, "t3.tfmr.wpe.weight").shape[0];
   CBX_REQUIRE((int)host_tensor(h, "t3.rope_cos").shape[0] >= m.max_pos, "rope identity table shorter than wpe");
   pack_linear(m.head, host_tensor(h, "t3.speech_head.weight").data.data(), host_tensor(h, "t3.speech_head.bias").data.data(),
-              m.vocab, 1024);
+              m.vocab, 1024, true);
   pack_linear(m.spkr, host_tensor(h, "t3.cond_enc.spkr_enc.weight").data.data(),
               host_tensor(h, "t3.cond_enc.spkr_enc.bias").data.data(), 1024, 256);
   m.ready = true;
@@ -76,8 +76,8 @@ void t3_finalize(cbx_handle* h) {
     T3Layer& ly = m.layers[i];
     auto qkv = concat_rows({&host_tensor(h, p + "self_attn.q_proj.weight"), &host_tensor(h, p + "self_attn.k_proj.weight"),
                             &host_tensor(h, p + "self_attn.v_proj.weight")});
-    pack_linear(ly.qkv, qkv.data(), nullptr, 3072, 1024);
-    pack_linear(ly.o, host_tensor(h, p + "self_attn.o_proj.weight").data.data(), nullptr, 1024, 1024);
+    pack_linear(ly.qkv, qkv.data(), nullptr, 3072, 1024, true);    // + fp16 copy: operand of the fp16-activation decode mode
+    pack_linear(ly.o, host_tensor(h, p + "self_attn.o_proj.weight").data.data(), nullptr, 1024, 1024, true);
     const auto& g = host_tensor(h, p + "mlp.gate_proj.weight").data;
     const auto& u = host_tensor(h, p + "mlp.up_proj.weight").data;
     std::vector<float> gu((size_t)8192 * 1024);
@@ -85,8 +85,8 @@ void t3_finalize(cbx_handle* h) {
       memcpy(&gu[(size_t)(2 * j) * 1024], &g[(size_t)j * 1024], 4096);
       memcpy(&gu[(size_t)(2 * j + 1) * 1024], &u[(size_t)j * 1024], 4096);
     }
-    pack_linear(ly.gu, gu.data(), nullptr, 8192, 1024);
-    pack_linear(ly.down, host_tensor(h, p + "mlp.down_proj.weight").data.data(), nullptr, 1024, 4096);
+    pack_linear(ly.gu, gu.data(), nullptr, 8192, 1024, true);
+    pack_linear(ly.down, host_tensor(h, p + "mlp.down_proj.weight").data.data(), nullptr, 1024, 4096, true);
     ly.ln1 = upload_tensor(h, p + "input_layernorm.weight");
     ly.ln2 = upload_tensor(h, p + "post_attention_layernorm.weight");
   }
@@ -99,7 +99,7 @@ void t3_finalize(cbx_handle* h) {
   m.rope_cos = upload_tensor(h, "t3.rope_cos");
   m.rope_sin = upload_tensor(h, "t3.rope_sin");
   m.max_pos = (int)host_tensor(h, "t3.rope_cos").shape[0];
-  pack_linear(m.head, host_tensor(h, "t3.speech_head.weight").data.data(), nullptr, 8194, 1024);
+  pack_linear(m.head, host_tensor(h, "t3.speech_head.weight").data.data(), nullptr, 8194, 1024, true);
   // conditioning encoder
   pack_linear(m.spkr, host_tensor(h, "t3.cond_enc.spkr_enc.weight").data.data(),
               host_tensor(h, "t3.cond_enc.spkr_enc.bias").data.data(), 1024, 256);
@@ -379,7 +379,14 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
   // Tensor-core batches (S > 8): every GEMM operand travels as bf16 hi/lo planes written by its producer (resid_norm,
   // paged attention, SwiGLU epilogue) and is loaded by TMA.  Small batches keep fp32 activations for the GEMV kernels.
   const bool planes = (S > 8 && ctx.gemm_impl == 0);
+  // st.act_fp16 (throughput mode, together with a bf16 / fp8 KV cache): the same dataflow with ONE fp16 plane per activation
+  // against the fp16 copy of the weights -- half the MMAs and half the activation bytes; its error (2^-12 relative per
+  // element) is of the order of the bf16 rounding of K / V that mode already accepts.  fp32-faithful hi/lo planes otherwise.
+  const bool f16 = planes && st.act_fp16 != 0;
   const int* m_live = planes ? st.m_live : nullptr;
+  __half* xn16 = reinterpret_cast<__half*>(xn);
+  __half* at16 = reinterpret_cast<__half*>(att);
+  __half* ac16 = reinterpret_cast<__half*>(act);
   __nv_bfloat16* xn_hi = reinterpret_cast<__nv_bfloat16*>(xn);   __nv_bfloat16* xn_lo = xn_hi + (size_t)S * 1024;
   __nv_bfloat16* at_hi = reinterpret_cast<__nv_bfloat16*>(att);  __nv_bfloat16* at_lo = at_hi + (size_t)S * 1024;
   __nv_bfloat16* ac_hi = reinterpret_cast<__nv_bfloat16*>(act);  __nv_bfloat16* ac_lo = ac_hi + (size_t)S * 4096;
@@ -394,12 +401,13 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
     memset(&rn, 0, sizeof(rn));
     rn.x = x; rn.ldx = 1024; rn.part = prt; rn.nsplit = ns; rn.split_stride = (long)S * 1024; rn.ldp = 1024; rn.bias = bias;
     rn.w = w.p; rn.b = b.p; rn.layernorm = m.gpt ? 1 : 0; rn.eps = 1e-5f;
-    if (planes) { rn.yhi = xn_hi; rn.ylo = xn_lo; } else rn.y = xn;
+    if (f16) rn.y16 = xn16; else if (planes) { rn.yhi = xn_hi; rn.ylo = xn_lo; } else rn.y = xn;
     rn.ldy = 1024; rn.dim = 1024; rn.m_live = st.m_live;
     resid_norm(ctx, rn, S);
   };
   auto feed = [&](GemmDev& g, const float* a32, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld) {
-    if (planes) { g.A = nullptr; g.Ahi = hi; g.Alo = lo; g.ldab = ld; } else g.A = a32;
+    if (f16) { g.A = nullptr; g.A16 = reinterpret_cast<const __half*>(hi); g.lda16 = ld; }
+    else if (planes) { g.A = nullptr; g.Ahi = hi; g.Alo = lo; g.ldab = ld; } else g.A = a32;
     g.m_live = m_live;
   };
   const float* pend = nullptr; int pend_ns = 0; const float* pend_bias = nullptr;   // projection output not yet added to x
@@ -410,8 +418,9 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
     feed(gq, xn, xn_hi, xn_lo, 1024);
     gq.tile_bn = tl.qkv_bn; gq.tile_dual = tl.qkv_dual;
     gemm(ctx, gq, ly.qkv);
+    po.out16 = f16 ? at16 : nullptr;
     paged_decode_attention(ctx, qkv, 3072, kv, l, st.slot_row, S, st.positions, planes ? nullptr : att, 1024, scratch, nsplit,
-                           planes ? at_hi : nullptr, planes ? at_lo : nullptr, &po);
+                           (planes && !f16) ? at_hi : nullptr, (planes && !f16) ? at_lo : nullptr, &po);
     GemmDev go = gemm_args_linear(att, 1024, S, ly.o, part, 1024);
     feed(go, att, at_hi, at_lo, 1024);
     const float* o_bias = m.gpt ? ly.o.bias : nullptr;
@@ -422,7 +431,7 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
     GemmDev gg = gemm_args_linear(xn, 1024, S, ly.gu, act, 4096);
     feed(gg, xn, xn_hi, xn_lo, 1024);
     if (m.gpt) gg.act = ACT_GELU_TANH; else gg.swiglu = 1;
-    if (planes) { gg.C = nullptr; gg.Chi = ac_hi; gg.Clo = ac_lo; gg.ldcb = 4096; }
+    if (planes) { gg.C = nullptr; gg.Chi = ac_hi; gg.Clo = ac_lo; gg.ldcb = 4096; gg.c_half = f16 ? 1 : 0; }
     gg.tile_bn = tl.gu_bn; gg.tile_dual = tl.gu_dual;
     gemm(ctx, gg, ly.gu);
     GemmDev gd = gemm_args_linear(act, 4096, S, ly.down, part, 1024);

@@ -221,7 +221,7 @@ class Engine:
 
     def t3_generate(self, text_tokens, cond, voice_ids=None, max_new_tokens=1000, cfg_weight=0.5, temperature=0.8,
                     top_p=1.0, min_p=0.05, repetition_penalty=1.2, q_noise=None, seed=0, kv_dtype="bf16",
-                    max_sync_steps=None, return_state=False, top_k=0, force_tokens=None):
+                    max_sync_steps=None, return_state=False, top_k=0, force_tokens=None, act_dtype=None):
         """Batched equivalent of T3.inference (t3.py:225-390) or, with a Turbo checkpoint loaded, of
         T3.inference_turbo (t3.py:392-468: no CFG, processors temperature -> top_k -> top_p -> repetition penalty,
         min_p unused; max_new_tokens counts the token sampled from the prefill, i.e. max_gen_len + 1).
@@ -260,6 +260,11 @@ class Engine:
         kvt = (torch.float32 if kv_dtype in ("fp32", "f32", torch.float32) else
                torch.float8_e4m3fn if kv_dtype in ("fp8", "e4m3", torch.float8_e4m3fn) else torch.bfloat16)
         kv_code = {torch.bfloat16: 0, torch.float32: 1, torch.float8_e4m3fn: 2}[kvt]
+        # decode-step operand format: fp32-faithful bf16 hi/lo planes with the fp32 (parity) cache, one fp16 plane in the
+        # throughput configurations (bf16 / fp8 cache) unless asked otherwise
+        if act_dtype is None:
+            act_dtype = "bf16x2" if kvt == torch.float32 else "fp16"
+        assert act_dtype in ("bf16x2", "fp16")
         L = self.t3_layers
         max_tokens = int(max(max_new))
         # position tables of the checkpoint bound what may be generated (reference: learned tables of 2050 / 4100 rows,
@@ -318,7 +323,8 @@ class Engine:
                      _ptr(st_t["x"]), _ptr(st_t["logits"]), LDL, float(cfg_weight), float(repetition_penalty),
                      float(temperature), float(min_p), float(top_p), _ptr(qn), int(seed), 1 if turbo else 0, int(top_k),
                      _ptr(st_t["act_utt"]), _ptr(st_t["n_act"]), _ptr(st_t["src_slot"]), _ptr(st_t["slot_row"]),
-                     _ptr(st_t["m_live"]), _ptr(forced), _ptr(st_t["sampled"]) if forced is not None else C.c_void_p(0))
+                     _ptr(st_t["m_live"]), _ptr(forced), _ptr(st_t["sampled"]) if forced is not None else C.c_void_p(0),
+                     1 if act_dtype == "fp16" else 0)
         ws = self.workspace(self.h.lib.cbx_t3_workspace_bytes(self.h.h, n_tok, R))
         cond = cond.to(dev, torch.float32).contiguous()
         self.h.call("cbx_t3_prefill", C.byref(st), n_tok, _ptr(d["tok_row"]), _ptr(d["tok_pos"]), _ptr(d["row_start"]),
@@ -438,7 +444,9 @@ class Engine:
     def _hift_geom(self, T):
         dev = self.device
         T = np.asarray(T, dtype=np.int32)
-        LT = PackedLayout(T, dev, alloc=T + 1)          # +1: room for the 120T+1-th row of the last stage
+        # +4 frames: room for the 120T+1-th row of the last stage, and a zero gap of >= 32 rows at the 8T level between two
+        # sequences -- the staged-tile ResBlock convolutions (hift_conv.cu) read their dilated halo (up to 25 rows) from it
+        LT = PackedLayout(T, dev, alloc=T + 4)
         L8 = LT.scaled(8, 8 * T, dev)
         L40 = LT.scaled(40, 40 * T, dev)
         L120 = LT.scaled(120, 120 * T + 1, dev)

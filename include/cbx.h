@@ -111,6 +111,10 @@ typedef struct {
    * the id the sampler picked itself goes to sampled_out[u][i] (optional) */
   const int* force_tokens;
   int* sampled_out;
+  /* operand format of the decode-step projections: 0 = activations as bf16 hi/lo planes (fp32-faithful: bit-exact greedy
+   * ids with an fp32 KV cache), 1 = one fp16 plane against the fp16 copy of the weights (throughput mode: half the tensor
+   * work; error of the order of the bf16 KV rounding it is meant to be combined with) */
+  int act_fp16;
 } cbx_t3_state;
 
 /* replaces T3.prepare_conditioning + T3CondEnc.forward + Perceiver.forward

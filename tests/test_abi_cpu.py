@@ -86,7 +86,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     from chatterbox_b200._lib import T3State, Layout, HiftGeom
     fields = ["n_utts", "kv_pages", "page_table", "n_pages", "positions", "tokens", "max_new", "seen", "logits", "ldl",
               "cfg_weight", "top_p", "q_noise", "seed", "sampler", "top_k", "act_utt", "n_act", "src_slot", "slot_row", "m_live",
-              "force_tokens", "sampled_out"]
+              "force_tokens", "sampled_out", "act_fp16"]
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "cbx.h"', 'int main(void) {',
            'printf("%zu %zu %zu\\n", sizeof(cbx_t3_state), sizeof(cbx_layout), sizeof(cbx_hift_geom));']
     src += [f'printf("%zu\\n", offsetof(cbx_t3_state, {f}));' for f in fields]

@@ -31,7 +31,7 @@ def _t3(golden_dir):
     return _cache["t3"]
 
 
-def _forced(t3, cond, g, n, kv_dtype):
+def _forced(t3, cond, g, n, kv_dtype, act_dtype=None):
     """Teacher-forced run over the reference's first n ids; returns (logits of both CFG rows after n tokens, the ids the
     engine's own greedy pick would have been)."""
     eng = t3.engine
@@ -39,37 +39,39 @@ def _forced(t3, cond, g, n, kv_dtype):
     ids = g["tokens"][0]
     out, st = eng.t3_generate([g["text_tokens"][0]], cnd, max_new_tokens=n, cfg_weight=0.5, temperature=0.8, top_p=1.0,
                               min_p=1.0, repetition_penalty=1.2, kv_dtype=kv_dtype, return_state=True,
-                              force_tokens=[ids[:n]])
+                              force_tokens=[ids[:n]], act_dtype=act_dtype)
     torch.cuda.synchronize()
     assert out[0].tolist() == ids[:n].tolist()                  # the forced ids were recorded as the utterance's tokens
     return st["logits"][:2, :8194].cpu(), st["sampled"][0, :n].cpu()
 
 
-@pytest.mark.parametrize("kv_dtype,tol", [("fp32", 2e-3), ("bf16", 2e-2), ("fp8", 1.0)])
-def test_t3_teacher_forced_logits_at_long_context(golden_dir, kv_dtype, tol):
+@pytest.mark.parametrize("kv_dtype,act_dtype,tol", [("fp32", "bf16x2", 2e-3), ("bf16", "bf16x2", 2e-2), ("bf16", "fp16", 6e-2),
+                                                    ("fp8", "fp16", 1.0)])
+def test_t3_teacher_forced_logits_at_long_context(golden_dir, kv_dtype, act_dtype, tol):
     """Logits of both CFG rows after 1 / 64 / 256 / 512 / 768 / 900 generated tokens (context 189 .. 1088) against the
-    reference backbone fed the same ids.  fp32 KV: fp32-faithful; bf16 KV (bench configuration): the error of rounding
-    K/V to 8 mantissa bits, bounded."""
+    reference backbone fed the same ids.  fp32 KV + hi/lo activation planes: fp32-faithful; bf16 KV: the error of rounding
+    K/V to 8 mantissa bits; bf16 KV + one fp16 activation plane = the BENCH configuration; fp8 KV: opt-in."""
     g, sd, c3, t3, cond = _t3(golden_dir)
     worst = 0.0
     for n, ref in sorted(g["taps"].items()):
-        logits, _ = _forced(t3, cond, g, n, kv_dtype)
+        logits, _ = _forced(t3, cond, g, n, kv_dtype, act_dtype)
         err = (logits - ref).abs().max().item()
         worst = max(worst, err)
-        print(f"[long t3 {kv_dtype}] after {n} tokens (context {g['s0'] + n}): max|dlogit| = {err:.3e} (|logit| max {ref.abs().max():.2f})")
-        assert err < tol, f"{kv_dtype} KV, {n} tokens: max|dlogit|={err}"
+        print(f"[long t3 kv {kv_dtype} act {act_dtype}] after {n} tokens (context {g['s0'] + n}): max|dlogit| = {err:.3e} (|logit| max {ref.abs().max():.2f})")
+        assert err < tol, f"{kv_dtype} KV / {act_dtype} activations, {n} tokens: max|dlogit|={err}"
 
 
-@pytest.mark.parametrize("kv_dtype,min_rate", [("fp32", 0.998), ("bf16", 0.99), ("fp8", 0.80)])
-def test_t3_teacher_forced_argmax_agreement(golden_dir, kv_dtype, min_rate):
+@pytest.mark.parametrize("kv_dtype,act_dtype,min_rate", [("fp32", "bf16x2", 0.998), ("bf16", "bf16x2", 0.99), ("bf16", "fp16", 0.98),
+                                                         ("fp8", "fp16", 0.80)])
+def test_t3_teacher_forced_argmax_agreement(golden_dir, kv_dtype, act_dtype, min_rate):
     """Over 900 teacher-forced steps the engine's own greedy pick equals the reference's id at (almost) every step;
     a disagreement can only be a near-tie of the top-2 logits."""
     g, sd, c3, t3, cond = _t3(golden_dir)
     n = g["tokens"].shape[1]
-    _, sampled = _forced(t3, cond, g, n, kv_dtype)
+    _, sampled = _forced(t3, cond, g, n, kv_dtype, act_dtype)
     agree = (sampled == g["tokens"][0].to(torch.int32)).float().mean().item()
-    print(f"[long t3 {kv_dtype}] teacher-forced argmax agreement over {n} steps: {agree:.4f}")
-    assert agree >= min_rate, f"{kv_dtype} KV: agreement {agree}"
+    print(f"[long t3 kv {kv_dtype} act {act_dtype}] teacher-forced argmax agreement over {n} steps: {agree:.4f}")
+    assert agree >= min_rate, f"{kv_dtype} KV / {act_dtype}: agreement {agree}"
 
 
 def test_t3_free_running_900_steps_fp32_kv(golden_dir):
