@@ -533,28 +533,45 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
   }
   __syncthreads();
   if (warp == 4) {
-    // ===================== producer: bulk copies of every item's pages (split, split + nsplit, ...) ==========
-    if (lane == 0) {
-      uint32_t gi = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int slot = it / per_slot;
-        if (slot >= n_live) break;                        // items are slot-major: nothing live beyond this one
-        const int rem = it - slot * per_slot;
-        const int head = rem / p.nsplit, split = rem - head * p.nsplit;
-        const int row = p.slot_row[slot];
-        const int npg = (p.positions[row] + PB_TOK) / PB_TOK;
-        const int* pt = p.page_table + (long)row * p.max_pages;
-        const T* base = layer_base + (long)head * slab_e;
-        for (int pj = split; pj < npg; pj += p.nsplit, ++gi) {
-          const int s = gi % NST;
-          mbar_wait(&empty[s], ((gi / NST) & 1) ^ 1);
-          const T* kp = base + (long)pt[pj] * page_stride;
-          uint8_t* st = pb_smem + s * STAGE;
-          mbar_arrive_expect_tx(&full[s], STAGE);
-          bulk_g2s(st, kp, SLAB, &full[s]);
-          bulk_g2s(st + SLAB, kp + (long)H * slab_e, SLAB, &full[s]);
+    // ===================== producer warp: bulk copies of every item's pages (split, split + nsplit, ...) =========
+    // All 32 lanes fetch metadata (the page ids of the next 32 pages in one coalesced load, the next item's row / position
+    // while the current item streams); lane 0 alone talks to the barriers and the copy engine, so no page-table load sits
+    // on its critical path between two bulk copies.
+    uint32_t gi = 0;
+    int it = blockIdx.x;
+    int slot = it < n_items ? it / per_slot : n_live;
+    int row = 0, pos = 0;
+    if (slot < n_live) { row = p.slot_row[slot]; pos = p.positions[row]; }
+    while (it < n_items && slot < n_live) {
+      const int rem = it - slot * per_slot;
+      const int head = rem / p.nsplit, split = rem - head * p.nsplit;
+      const int npg = (pos + PB_TOK) / PB_TOK;
+      const int* pt = p.page_table + (long)row * p.max_pages;
+      const T* base = layer_base + (long)head * slab_e;
+      // next item's metadata: issued now, needed after this item's pages
+      const int it_n = it + gridDim.x;
+      const int slot_n = it_n < n_items ? it_n / per_slot : n_live;
+      int row_n = 0, pos_n = 0;
+      if (slot_n < n_live) { row_n = p.slot_row[slot_n]; pos_n = p.positions[row_n]; }
+      int i = 0;
+      for (int pj0 = split; pj0 < npg; pj0 += 32 * p.nsplit) {
+        const int pj_l = pj0 + lane * p.nsplit;
+        const int pg_l = pj_l < npg ? pt[pj_l] : 0;
+        const int cnt = min(32, (npg - pj0 + p.nsplit - 1) / p.nsplit);
+        for (int u = 0; u < cnt; ++u, ++i, ++gi) {
+          const int page = __shfl_sync(0xffffffffu, pg_l, u);
+          if (lane == 0) {
+            const int s = gi % NST;
+            mbar_wait(&empty[s], ((gi / NST) & 1) ^ 1);
+            const T* kp = base + (long)page * page_stride;
+            uint8_t* st = pb_smem + s * STAGE;
+            mbar_arrive_expect_tx(&full[s], STAGE);
+            bulk_g2s(st, kp, SLAB, &full[s]);
+            bulk_g2s(st + SLAB, kp + (long)H * slab_e, SLAB, &full[s]);
+          }
         }
       }
+      it = it_n; slot = slot_n; row = row_n; pos = pos_n;
     }
     return;
   }
@@ -650,8 +667,10 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
       }
       float sc = 0.f;
       if (tok < S) {
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};                 // four independent chains instead of one of 16 dependent FMAs
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) sc = fmaf(q[j], kx[j], sc);
+        for (int j = 0; j < DPL; ++j) s4[j & 3] = fmaf(q[j], kx[j], s4[j & 3]);
+        sc = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
       sc += __shfl_xor_sync(0xffffffffu, sc, 1);
       sc += __shfl_xor_sync(0xffffffffu, sc, 2);

@@ -716,22 +716,72 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDev g) {
 // ================================================================================================
 template <int R, int NB>
 __global__ void __launch_bounds__(128) gemv_kernel(const GemmDev g) {
-  pdl_wait();
-  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb0 = blockIdx.x * NB;
+  const int K = g.Kpad;
+  // The weights do not depend on the previous kernel: the first K slice of every column is already in flight while that
+  // kernel drains (PDL) -- for the 1024-wide projections that is the CTA's whole weight traffic.
+  const int kf = warp * 256 + lane * 8;
+  uint4 wf[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int n = nb0 + j;
+    wf[j] = (n < g.Npad && kf < K) ? __ldg(reinterpret_cast<const uint4*>(g.Wp + (long)n * K + kf)) : make_uint4(0, 0, 0, 0);
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  // optional fused row norm of the raw residual stream (dim = k_total <= 1024): statistics once per CTA
+  __shared__ float s_stat[R][2];
+  if (g.norm_w) {
+    for (int r = warp; r < R; r += 4) {
+      float s1 = 0.f, s2 = 0.f;
+      if (r < g.M) {
+        for (int k = lane * 4; k < g.k_total; k += 128) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(g.A + (long)r * g.lda + k));
+          s1 += (a.x + a.y) + (a.z + a.w);
+          s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+        }
+      }
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane == 0) {
+        if (g.norm_ln) {
+          const float mean = s1 / g.k_total;
+          float var = 0.f;            // second pass for the variance (matches the two-pass LayerNorm kernels)
+          s_stat[r][0] = mean; s_stat[r][1] = var;
+        } else {
+          s_stat[r][0] = 0.f; s_stat[r][1] = rsqrtf(s2 / g.k_total + g.norm_eps);
+        }
+      }
+    }
+    __syncthreads();
+    if (g.norm_ln) {
+      for (int r = warp; r < R; r += 4) {
+        float v = 0.f;
+        const float mean = s_stat[r][0];
+        if (r < g.M) {
+          for (int k = lane * 4; k < g.k_total; k += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(g.A + (long)r * g.lda + k));
+            const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+            v += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+          }
+        }
+        v = warp_sum(v);
+        if (lane == 0) s_stat[r][1] = rsqrtf(v / g.k_total + g.norm_eps);
+      }
+      __syncthreads();
+    }
+  }
   float acc[R][NB];
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int j = 0; j < NB; ++j) acc[r][j] = 0.0f;
-  const int K = g.Kpad;
-  for (int k = warp * 256 + lane * 8; k < K; k += 1024) {
+  for (int k = kf; k < K; k += 1024) {
     uint4 w[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       int n = nb0 + j;
-      w[j] = (n < g.Npad) ? __ldg(reinterpret_cast<const uint4*>(g.Wp + (long)n * K + k)) : make_uint4(0, 0, 0, 0);
+      w[j] = (k == kf) ? wf[j] : ((n < g.Npad) ? __ldg(reinterpret_cast<const uint4*>(g.Wp + (long)n * K + k)) : make_uint4(0, 0, 0, 0));
     }
     float x[R][8];
 #pragma unroll
@@ -741,6 +791,22 @@ __global__ void __launch_bounds__(128) gemv_kernel(const GemmDev g) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(g.A + (long)r * g.lda + k + 4));
         x[r][0] = a.x; x[r][1] = a.y; x[r][2] = a.z; x[r][3] = a.w;
         x[r][4] = b.x; x[r][5] = b.y; x[r][6] = b.z; x[r][7] = b.w;
+        if (g.norm_w) {
+          const float4 wa = __ldg(reinterpret_cast<const float4*>(g.norm_w + k));
+          const float4 wb = __ldg(reinterpret_cast<const float4*>(g.norm_w + k + 4));
+          const float nw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+          const float mean = s_stat[r][0], inv = s_stat[r][1];
+          if (g.norm_ln) {
+            const float4 ba = __ldg(reinterpret_cast<const float4*>(g.norm_b + k));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(g.norm_b + k + 4));
+            const float nb[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[r][i] = (x[r][i] - mean) * inv * nw[i] + nb[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[r][i] = nw[i] * (x[r][i] * inv);
+          }
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[r][i] = 0.0f;
@@ -1030,7 +1096,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     gemm_simt_kernel<<<grid, 256, 0, ctx.stream>>>(g);
   } else {
     const bool plain = !g.has_seq && g.a_mode == A_TAPS && g.ntaps == 1 && g.stride == 1 && g.pad == 0 &&
-                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.Chi && !g.Ahi && !g.A16 &&
+                       (g.lda % 4 == 0) && (g.k_total % 8 == 0) && !g.C2 && !g.Chi && !g.Ahi && !g.A16 && (!g.norm_w || g.k_total <= 1024) &&
                        ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
     // fp16-plane Linear with a short reduction (the CFM block projections qkv / ff1 / out): weight-resident persistent kernel
     static const bool wres_on = !(getenv("CBX_WRES") && atoi(getenv("CBX_WRES")) == 0);
@@ -1042,6 +1108,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
       if (g.Kpad == 256 && g.Npad % 256 == 0) { launch_wres<256>(ctx, g, W); CBX_CHECK(cudaGetLastError()); return; }
       if (g.Kpad == 512 && g.Npad % 128 == 0) { launch_wres<128>(ctx, g, W); CBX_CHECK(cudaGetLastError()); return; }
     }
+    CBX_REQUIRE(!g.norm_w || (plain && g.M <= 8), "the fused row norm exists in the GEMV kernel only");
     if (plain && g.M <= 8) {
       if (g.M <= 2) launch_gemv<2>(ctx, g);
       else if (g.M <= 4) launch_gemv<4>(ctx, g);

@@ -78,6 +78,9 @@ struct GemmDev {
   const int* m_live;        // optional device scalar: row tiles with m0 >= *m_live exit at once (device-side retirement)
   int tile_bn;              // 0 = heuristic; 64 | 128 | 256 forces the N tile (decode shapes are tuned by measurement)
   int tile_dual;            // with tile_bn: 1 = the two-CTAs-per-SM configuration
+  // GEMV path only (<= 8 rows, B=1 latency): A is the RAW residual stream and the kernel applies the row norm itself
+  // (RMSNorm: norm_w * (x * rsqrt(mean x^2 + eps)); LayerNorm when norm_ln) -- one launch less per projection
+  const float* norm_w; const float* norm_b; int norm_ln; float norm_eps;
 };
 
 struct Arena {  // bump allocator over caller-owned workspace; dry=true only counts

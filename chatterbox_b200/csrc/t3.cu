@@ -396,7 +396,11 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
   t3_compact(ctx, st.act_utt, st.n_act, st.src_slot, st.slot_row, st.m_live, st.done, rows_per);
   t3_sample(ctx, sp, cap);
   // norm feeding a GEMM: x (+= split-K partials of the previous projection) -> norm -> planes / fp32
+  // GEMV path (<= 8 rows): no separate norm launches -- the o / down GEMVs add their result into x in the epilogue and
+  // the qkv / gate-up / head GEMVs normalise the raw residual stream in their prologue
+  const DevVec* fused_w = nullptr; const DevVec* fused_b = nullptr;
   auto norm_in = [&](const float* prt, int ns, const float* bias, const DevVec& w, const DevVec& b) {
+    if (!planes) { fused_w = &w; fused_b = &b; return; }
     ResidNormDev rn;
     memset(&rn, 0, sizeof(rn));
     rn.x = x; rn.ldx = 1024; rn.part = prt; rn.nsplit = ns; rn.split_stride = (long)S * 1024; rn.ldp = 1024; rn.bias = bias;
@@ -407,7 +411,10 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
   };
   auto feed = [&](GemmDev& g, const float* a32, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld) {
     if (f16) { g.A = nullptr; g.A16 = reinterpret_cast<const __half*>(hi); g.lda16 = ld; }
-    else if (planes) { g.A = nullptr; g.Ahi = hi; g.Alo = lo; g.ldab = ld; } else g.A = a32;
+    else if (planes) { g.A = nullptr; g.Ahi = hi; g.Alo = lo; g.ldab = ld; }
+    else if (a32 == xn) {          // the consumer of a norm: raw residual stream + fused row norm
+      g.A = x; g.lda = 1024; g.norm_w = fused_w->p; g.norm_b = fused_b->p; g.norm_ln = m.gpt ? 1 : 0; g.norm_eps = 1e-5f;
+    } else g.A = a32;
     g.m_live = m_live;
   };
   const float* pend = nullptr; int pend_ns = 0; const float* pend_bias = nullptr;   // projection output not yet added to x
@@ -421,11 +428,11 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
     po.out16 = f16 ? at16 : nullptr;
     paged_decode_attention(ctx, qkv, 3072, kv, l, st.slot_row, S, st.positions, planes ? nullptr : att, 1024, scratch, nsplit,
                            (planes && !f16) ? at_hi : nullptr, (planes && !f16) ? at_lo : nullptr, &po);
-    GemmDev go = gemm_args_linear(att, 1024, S, ly.o, part, 1024);
+    GemmDev go = gemm_args_linear(att, 1024, S, ly.o, planes ? part : x, 1024);
     feed(go, att, at_hi, at_lo, 1024);
     const float* o_bias = m.gpt ? ly.o.bias : nullptr;
-    go.bias = nullptr;
-    if (planes) { go.splitk = tl.o_split; go.split_stride = (long)S * 1024; go.tile_bn = tl.o_bn; }
+    if (planes) { go.bias = nullptr; go.splitk = tl.o_split; go.split_stride = (long)S * 1024; go.tile_bn = tl.o_bn; }
+    else { go.res = x; go.ldr = 1024; }            // GEMV: x += o(att) (+ bias) in the epilogue
     gemm(ctx, go, ly.o);
     norm_in(part, planes ? tl.o_split : 1, o_bias, ly.ln2, ly.ln2_b);
     GemmDev gg = gemm_args_linear(xn, 1024, S, ly.gu, act, 4096);
@@ -434,11 +441,11 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
     if (planes) { gg.C = nullptr; gg.Chi = ac_hi; gg.Clo = ac_lo; gg.ldcb = 4096; gg.c_half = f16 ? 1 : 0; }
     gg.tile_bn = tl.gu_bn; gg.tile_dual = tl.gu_dual;
     gemm(ctx, gg, ly.gu);
-    GemmDev gd = gemm_args_linear(act, 4096, S, ly.down, part, 1024);
+    GemmDev gd = gemm_args_linear(act, 4096, S, ly.down, planes ? part : x, 1024);
     feed(gd, act, ac_hi, ac_lo, 4096);
     pend_bias = m.gpt ? ly.down.bias : nullptr;
-    gd.bias = nullptr;
-    if (planes) { gd.splitk = tl.down_split; gd.split_stride = (long)S * 1024; gd.tile_bn = tl.down_bn; }
+    if (planes) { gd.bias = nullptr; gd.splitk = tl.down_split; gd.split_stride = (long)S * 1024; gd.tile_bn = tl.down_bn; }
+    else { gd.res = x; gd.ldr = 1024; }
     gemm(ctx, gd, ly.down);
     pend = part; pend_ns = planes ? tl.down_split : 1;
   }

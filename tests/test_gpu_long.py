@@ -33,13 +33,16 @@ def _t3(golden_dir):
 
 def _forced(t3, cond, g, n, kv_dtype, act_dtype=None):
     """Teacher-forced run over the reference's first n ids; returns (logits of both CFG rows after n tokens, the ids the
-    engine's own greedy pick would have been)."""
+    engine's own greedy pick would have been).  The utterance is run as a batch of 6 identical copies (12 CFG rows): above
+    8 rows the decode step takes the tensor-core path (split-K projections, plane / fp16 operands) that the bench uses;
+    a single utterance would exercise the GEMV kernels instead (covered by tests/test_gpu_t3.py)."""
     eng = t3.engine
     cnd = t3.prepare_conditioning(cond)
     ids = g["tokens"][0]
-    out, st = eng.t3_generate([g["text_tokens"][0]], cnd, max_new_tokens=n, cfg_weight=0.5, temperature=0.8, top_p=1.0,
+    nb = 6
+    out, st = eng.t3_generate([g["text_tokens"][0]] * nb, cnd, max_new_tokens=n, cfg_weight=0.5, temperature=0.8, top_p=1.0,
                               min_p=1.0, repetition_penalty=1.2, kv_dtype=kv_dtype, return_state=True,
-                              force_tokens=[ids[:n]], act_dtype=act_dtype)
+                              force_tokens=[ids[:n]] * nb, act_dtype=act_dtype)
     torch.cuda.synchronize()
     assert out[0].tolist() == ids[:n].tolist()                  # the forced ids were recorded as the utterance's tokens
     return st["logits"][:2, :8194].cpu(), st["sampled"][0, :n].cpu()
