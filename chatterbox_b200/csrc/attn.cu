@@ -366,6 +366,7 @@ struct PagedDev {
   int fuse_rope; const float* cos_t; const float* sin_t;
   const int* n_live;                  // optional device scalar: slots >= *n_live are retired (CTA exits)
   __half* out16;                      // when set: the output as one fp16 plane
+  int dbg_early_release;              // A/B switch (CBX_PB_EARLY=1): release a stage before its loads are known to have returned
 };
 
 template <typename T>
@@ -657,8 +658,17 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
       uint4 kr[NPC], vr[NPC];
 #pragma unroll
       for (int j = 0; j < NPC; ++j) { kr[j] = kp[j]; vr[j] = vp[j]; }
+      // Release the stage only once the shared-memory loads have RETURNED: the arrive takes a value derived from every
+      // load as an (unused) operand, so it cannot issue while one of them is still in flight -- otherwise the producer's
+      // next bulk copy may land in the stage under a pending LDS (seen with the fp32 cache: 8 conflicted LDS.128 per trip).
+      uint32_t dep = 0;
+#pragma unroll
+      for (int j = 0; j < NPC; ++j) dep ^= kr[j].x ^ vr[j].x;
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);              // the stage's bytes are in registers
+      if (lane == 0) {
+        if (p.dbg_early_release) mbar_arrive(&empty[s]);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])), "r"(dep) : "memory");
+      }
 #pragma unroll
       for (int j = 0; j < NPC; ++j) { KvPiece<T>::decode(kr[j], kx + j * KvPiece<T>::N); KvPiece<T>::decode(vr[j], vx + j * KvPiece<T>::N); }
       if (p.fuse_rope && tok == pos) {                    // taken from registers, its cache slot is being written now
@@ -780,6 +790,8 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
   p.fuse_rope = opts ? opts->fuse_rope : 0; p.cos_t = opts ? opts->cos_t : nullptr; p.sin_t = opts ? opts->sin_t : nullptr;
   p.n_live = opts ? opts->n_live : nullptr;
   p.out16 = opts ? opts->out16 : nullptr;
+  static const bool early = getenv("CBX_PB_EARLY") != nullptr;
+  p.dbg_early_release = early ? 1 : 0;
   CBX_REQUIRE(!p.out16 || (kv.page_tokens == PB_TOK && !(opts && opts->impl == 1)), "fp16 output needs the bulk-copy kernel");
   // default: the bulk-copy (TMA engine) kernel; CBX_PAGED=ldg keeps the round-1 __ldg kernel for A/B runs
   static const bool force_ldg = getenv("CBX_PAGED") && std::string(getenv("CBX_PAGED")) == "ldg";
