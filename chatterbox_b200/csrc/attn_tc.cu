@@ -361,6 +361,306 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
+
+// ================================================================================================
+// attn_f16_kernel: the fp16-operand variant, rebuilt around the softmax warps' ISSUE budget.
+// ncu of attn_tc_kernel<1,1,2> (profiles/r2_ncu_attn_tc.txt): tensor pipe idle most of the time, 9.7 issued instructions per
+// (row, key) element, schedulers 47 % busy with 2.6 warps each -- the softmax is the kernel.  Head dim 64 makes that
+// structural: a 128 x 64 key block costs 256 tensor cycles (QK^T + PV, one fp16 term) but 8192 ex2 = 512 MUFU cycles, so the
+// exp pipe is the roof and every other softmax instruction has to fit under it:
+//   * row max with 3-input FMNMX3 (32 instead of 64 instructions per 64 keys)
+//   * scale / subtract, row sum and the O rescale on PACKED fp32 pairs (fma.rn.f32x2 / add.f32x2: FFMA2 / FADD2)
+//   * PTM = 1: P never touches shared memory.  The softmax writes its fp16 row straight back into the TMEM columns of the S
+//     tile it came from (tcgen05.st) and the PV product takes A from TMEM (.ts form of tcgen05.mma): no STS, no proxy
+//     fence, and the PV MMAs read only V (2 KB per K step) from shared memory instead of P + V (6 KB, over the 128 B/clk
+//     the SS form can pull for an N = 64 tile).
+// Same roles and barriers as attn_tc_kernel; S tiles double buffered, S_{j+2} cannot overtake PV_j because one thread
+// issues both in that order and the tensor pipe executes in issue order.
+// ================================================================================================
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// accumulator forms: the destination IS the loop-carried register (a plain "=l" output lands in the dying operand's register
+// and is then moved back: 64 extra MOVs per key block in the first build)
+__device__ __forceinline__ void fma2_acc(uint64_t& acc, uint64_t scale, uint64_t add) { asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc) : "l"(scale), "l"(add)); }
+__device__ __forceinline__ void add2_acc(uint64_t& acc, uint64_t b) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(b)); }
+__device__ __forceinline__ float max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+// D[tmem] (+)= A[tmem] * B[smem desc]   (.ts form: the A operand -- 128 rows x 16 fp16, two per 32-bit column -- comes from TMEM)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__host__ __device__ constexpr int af_stages(int occ, int ptm) { return occ == 2 ? (ptm ? 5 : 4) : (ptm ? 8 : 6); }
+__host__ __device__ constexpr int af_smem(int occ, int ptm) {
+  return AT_Q_BYTES / 2 + af_stages(occ, ptm) * (AT_KV_STAGE / 2) + (ptm ? 0 : AT_P_BYTES / 2) + 1024 + 256;
+}
+
+template <int OCC, int PTM>
+__global__ void __launch_bounds__(192, OCC)
+attn_f16_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcDev p) {
+  constexpr int STAGES = af_stages(OCC, PTM);
+  constexpr int Q_BYTES = 2 * AT_TILE, KV_STAGE = 2 * AT_TILE, P_BYTES = PTM ? 0 : 2 * AT_TILE;
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
+  const int q0 = blockIdx.x * AT_BM;
+  if (q0 >= qlen) return;
+  const int qrow0 = p.q_start[seq] + q0, krow0 = p.kv_start[seq];
+  const int nblk = (kvlen + AT_BN - 1) / AT_BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                                   // 128 rows x 128 B
+  uint8_t* sKV = sQ + Q_BYTES;                          // stages of [K 64 rows][V 64 rows]
+  uint8_t* sP = sKV + STAGES * KV_STAGE;                // PTM = 0 only: 128 rows x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* kv_full = bars + 1;             // [STAGES]
+  uint64_t* kv_empty = kv_full + STAGES;    // [STAGES]
+  uint64_t* s_full = kv_empty + STAGES;     // [2]
+  uint64_t* s_empty = s_full + 2;           // [2]
+  uint64_t* p_full = s_empty + 2;           // 1
+  uint64_t* pv_full = p_full + 1;           // 1
+  uint64_t* pv_empty = pv_full + 1;         // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
+    mbar_init(p_full, 4); mbar_init(pv_full, 1); mbar_init(pv_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tm);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS0 = tmem_base, tS1 = tmem_base + 64, tPV = tmem_base + 128;
+
+  if (warp == 0) {
+    // ===================== TMA producer ===============================================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      const int qc = p.q_col + head * 64;
+      tma_load_2d(sQ, &tm, q_full, qc, qrow0);
+      tma_load_2d(sQ + AT_TILE, &tm, q_full, qc, qrow0 + 64);
+      const int kc = p.k_col + head * 64, vc = p.v_col + head * 64;
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % STAGES;
+        mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
+        uint8_t* st = sKV + s * KV_STAGE;
+        mbar_arrive_expect_tx(&kv_full[s], KV_STAGE);
+        const int r = krow0 + j * AT_BN;
+        tma_load_2d(st, &tm, &kv_full[s], kc, r);
+        tma_load_2d(st + AT_TILE, &tm, &kv_full[s], vc, r);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(AT_BM, AT_BN);                   // A, B K-major
+      constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BM, 64) | (1u << 16);        // B (= V) MN-major
+      const uint32_t q_a = smem_u32(sQ), p_a = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int j) {
+        const int s = j % STAGES;
+        mbar_wait(&kv_full[s], (j / STAGES) & 1);
+        mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t k_a = smem_u32(sKV + s * KV_STAGE);
+        const uint32_t d = (j & 1) ? tS1 : tS0;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          umma_bf16(d, umma_desc_sw128(q_a + k4 * 32), umma_desc_sw128(k_a + k4 * 32), idesc_s, k4 != 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+      };
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) issue_s(j + 1);            // S of the next block overlaps the softmax of this one
+        const int s = j % STAGES;
+        mbar_wait(p_full, j & 1);                    // P_j is in TMEM (or smem)
+        mbar_wait(pv_empty, (j & 1) ^ 1);            // PV accumulator of block j-1 has been read
+        tcgen05_fence_after();
+        const uint32_t v_a = smem_u32(sKV + s * KV_STAGE + AT_TILE);
+        const uint32_t tP = (j & 1) ? tS1 : tS0;     // PTM: P_j sits in the first 32 columns of its S tile
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {             // 16 keys per step: 8 TMEM columns (32 B of a P row), 2048 B along V rows
+          const uint64_t dv = umma_desc_sw128_mn(v_a + k4 * 2048);
+          if (PTM) umma_f16_ts(tPV, tP + k4 * 8, dv, idesc_pv, k4 != 0 ? 1u : 0u);
+          else umma_bf16(tPV, umma_desc_sw128(p_a + k4 * 32), dv, idesc_pv, k4 != 0 ? 1u : 0u);
+        }
+        umma_commit(pv_full);                        // PV_j ready, P free
+        umma_commit(&kv_empty[s]);                   // K/V stage free
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue: one query row per thread ===================
+    const int quarter = warp & 3;                     // TMEM lane quarter of this warp (hardware: warp id % 4)
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    uint64_t o2[32];                                  // 64 output columns as packed pairs
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o2[i] = 0ull;
+    float m = -INFINITY, l = 0.f, c_prev = 1.f;
+    uint8_t* prow = sP + row * 128;
+    const uint64_t sc2 = pk2(p.scale_log2e, p.scale_log2e);
+    auto fold_pv = [&](bool release) {                // O = O * c_prev + PV
+      const uint64_t c2 = pk2(c_prev, c_prev);
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 32) {
+        uint32_t v0[32];
+        tmem_ld_32x32(tPV + lane_off + cc, v0);
+        tmem_ld_wait();
+        if (release && cc == 32) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pv_empty);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          fma2_acc(o2[cc / 2 + i], c2, pk2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1])));
+      }
+    };
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tcgen05_fence_after();
+      uint32_t r[64];
+      const uint32_t ts = ((j & 1) ? tS1 : tS0) + lane_off;
+      tmem_ld_32x32(ts, *reinterpret_cast<uint32_t(*)[32]>(r));
+      tmem_ld_32x32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(r + 32));
+      tmem_ld_wait();
+      if (!PTM) {                                     // PTM: the S tile doubles as the P buffer, released by the PV commit order
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[j & 1]);
+      }
+      if (j * AT_BN + AT_BN > kvlen) {                // only the last key block needs the length mask
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (j * AT_BN + i >= kvlen) r[i] = 0xff800000u;        // -inf
+      }
+      float mxa = m, mxb = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        mxa = max3(mxa, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        mxb = max3(mxb, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+      }
+      const float mx = fmaxf(mxa, mxb);
+      // raw scores are unscaled; the (positive) scale commutes with max, so scale once here
+      const float mxs = mx * p.scale_log2e;
+      const float c = (m == -INFINITY) ? 1.f : fast_exp2(m * p.scale_log2e - mxs);
+      const uint64_t nm2 = pk2(-mxs, -mxs);
+      uint64_t sa = 0ull, sb = 0ull;
+      uint32_t ph[32];                                // P_j as packed fp16 pairs
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        float x0, x1, x2, x3;
+        upk2(fma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, nm2), x0, x1);
+        upk2(fma2(pk2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), sc2, nm2), x2, x3);
+        x0 = fast_exp2(x0); x1 = fast_exp2(x1); x2 = fast_exp2(x2); x3 = fast_exp2(x3);
+        add2_acc(sa, pk2(x0, x1));
+        add2_acc(sb, pk2(x2, x3));
+        ph[i / 2] = pack_half2(x0, x1);
+        ph[i / 2 + 1] = pack_half2(x2, x3);
+      }
+      {
+        float s0, s1, s2, s3;
+        upk2(sa, s0, s1); upk2(sb, s2, s3);
+        l = l * c + ((s0 + s1) + (s2 + s3));
+      }
+      m = mx;
+      // hand P_j to the MMA warp first (its registers die here), then fold the previous block's PV into O
+      if (PTM) {
+        tmem_st_32x32_x32(ts, ph);                    // row `row`, columns 0..31 of the S tile = 64 fp16 keys
+        tmem_st_wait();
+        tcgen05_fence_before();
+      } else {
+        if (j > 0) mbar_wait(pv_full, (j - 1) & 1);   // PV_{j-1} has finished reading the P buffer
+#pragma unroll
+        for (int cq = 0; cq < 8; ++cq)
+          *reinterpret_cast<uint4*>(prow + (((uint32_t)(cq ^ (row & 7))) << 4)) = make_uint4(ph[4 * cq], ph[4 * cq + 1], ph[4 * cq + 2], ph[4 * cq + 3]);
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (PTM) { if (lane == 0) mbar_arrive(&s_empty[j & 1]); }   // bookkeeping only: S_{j+2} is issued after PV_j by the same thread
+      if (j > 0) {                                    // PV_{j-1} was computed relative to the previous max: O = O * c_prev + PV
+        mbar_wait(pv_full, (j - 1) & 1);
+        tcgen05_fence_after();
+        fold_pv(true);
+      }
+      c_prev = c;
+    }
+    // last block's PV
+    mbar_wait(pv_full, (nblk - 1) & 1);
+    tcgen05_fence_after();
+    fold_pv(false);
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) upk2(o2[i], o[2 * i], o[2 * i + 1]);
+    const long off = (long)(qrow0 + row) * p.ldo + head * 64;
+    if (q0 + row < qlen) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      if (p.O16) {
+        uint4* d16 = reinterpret_cast<uint4*>(p.O16 + off);
+#pragma unroll
+        for (int i = 0; i < 64; i += 8)
+          d16[i / 8] = make_uint4(pack_half2(o[i] * inv, o[i + 1] * inv), pack_half2(o[i + 2] * inv, o[i + 3] * inv),
+                                  pack_half2(o[i + 4] * inv, o[i + 5] * inv), pack_half2(o[i + 6] * inv, o[i + 7] * inv));
+      } else if (p.Ohi) {
+        uint4* dh = reinterpret_cast<uint4*>(p.Ohi + off);
+        uint4* dl = reinterpret_cast<uint4*>(p.Olo + off);
+#pragma unroll
+        for (int i = 0; i < 64; i += 8) {
+          uint4 h, lw;
+          split_pair_at(o[i] * inv, o[i + 1] * inv, h.x, lw.x);
+          split_pair_at(o[i + 2] * inv, o[i + 3] * inv, h.y, lw.y);
+          split_pair_at(o[i + 4] * inv, o[i + 5] * inv, h.z, lw.z);
+          split_pair_at(o[i + 6] * inv, o[i + 7] * inv, h.w, lw.w);
+          dh[i / 8] = h; dl[i / 8] = lw;
+        }
+      } else {
+        float* dst = p.O + off;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+      }
+    } else if (p.O16) {          // padding rows of the sequence's last tile stay finite (see attn_tc_kernel)
+      uint4* d16 = reinterpret_cast<uint4*>(p.O16 + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d16[i] = make_uint4(0, 0, 0, 0);
+    } else if (p.Ohi) {
+      uint4* dh = reinterpret_cast<uint4*>(p.Ohi + off);
+      uint4* dl = reinterpret_cast<uint4*>(p.Olo + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dh[i] = make_uint4(0, 0, 0, 0); dl[i] = make_uint4(0, 0, 0, 0); }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
 // ---- host --------------------------------------------------------------------------------------------
 
 template <int SPLIT, int F16, int OCC> static void at_attr() {
@@ -368,6 +668,10 @@ template <int SPLIT, int F16, int OCC> static void at_attr() {
 }
 void attention_tc_init() {      // per device
   at_attr<1, 0, 1>(); at_attr<2, 0, 1>(); at_attr<1, 1, 1>(); at_attr<2, 1, 1>(); at_attr<1, 1, 2>(); at_attr<2, 1, 2>();
+  CBX_CHECK(cudaFuncSetAttribute(attn_f16_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, af_smem(1, 0)));
+  CBX_CHECK(cudaFuncSetAttribute(attn_f16_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, af_smem(1, 1)));
+  CBX_CHECK(cudaFuncSetAttribute(attn_f16_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, af_smem(2, 0)));
+  CBX_CHECK(cudaFuncSetAttribute(attn_f16_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, af_smem(2, 1)));
 }
 
 void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
@@ -386,6 +690,19 @@ void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
   if (ctx.timer && ctx.timer->cls == K_FLASH) ctx.timer->work += a.work;
   if (ctx.timer) ctx.timer->begin(K_FLASH, ctx.stream);
   dim3 grid((a.max_q_len + AT_BM - 1) / AT_BM, a.n_heads, a.n_seq);
+  // CBX_ATTN_F16 = 2 (default): attn_f16_kernel with P in TMEM (.ts PV product); 1: same kernel, P through shared memory;
+  // 0: the round-2 first version (attn_tc_kernel<*, 1, *>)
+  static const int f16_kernel = getenv("CBX_ATTN_F16") ? atoi(getenv("CBX_ATTN_F16")) : 2;
+  if (a.f16 && f16_kernel >= 1 && variant == 1) {
+    const int ptm = f16_kernel >= 2 ? 1 : 0;
+    if (occ == 2) {
+      if (ptm) attn_f16_kernel<2, 1><<<grid, 192, af_smem(2, 1), ctx.stream>>>(*a.tm_hi, p);
+      else attn_f16_kernel<2, 0><<<grid, 192, af_smem(2, 0), ctx.stream>>>(*a.tm_hi, p);
+    } else {
+      if (ptm) attn_f16_kernel<1, 1><<<grid, 192, af_smem(1, 1), ctx.stream>>>(*a.tm_hi, p);
+      else attn_f16_kernel<1, 0><<<grid, 192, af_smem(1, 0), ctx.stream>>>(*a.tm_hi, p);
+    }
+  } else
   if (a.f16) {       // single fp16 plane per operand (a.tm_hi maps it; a.tm_lo is not read)
     if (occ == 2) {
       if (variant == 1) attn_tc_kernel<1, 1, 2><<<grid, 192, at_smem_f16(2), ctx.stream>>>(*a.tm_hi, *a.tm_hi, p);

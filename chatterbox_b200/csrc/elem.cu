@@ -705,24 +705,41 @@ void cfm_euler(Ctx& ctx, float* x, const float* v, const int* tile_seq2, const i
 // ================================================================================================
 // harmonic-plus-noise source (hifigan.py SineGen.forward :200-231 + SourceModuleHnNSF :267-283)
 // Phase: torch.cumsum on CPU accumulates float32 sequentially in fp64 and rounds every output to fp32
-// (ATen cpu_cum_base_kernel, acc_type<float> = double); the '% 1' comes after.  hift_phase_scan_kernel replays that
-// scan exactly: one thread per (sequence, harmonic) walks all 480*T samples.
-__global__ void hift_phase_scan_kernel(const float* f0, float* cumf, const int* startT, const int* lenT,
-                                       const long* startS, int n_seq) {
+// (ATen cpu_cum_base_kernel, acc_type<float> = double); the '% 1' comes after.  The engine replays that scan EXACTLY, but
+// not sample by sample: inside one mel frame the increment d = (double)(f0 * h / 24000) is constant for 480 samples, so
+//     c_k = c_0 + k * d   holds bit for bit whenever no addition of the frame rounds,
+// i.e. when c_0 and d are both multiples of u = ulp(c_0 + 480 d): every partial sum is then a multiple of u below 2^53 u.
+// hift_phase_frames_kernel walks the FRAMES of one (sequence, harmonic) sequentially (a few thousand steps instead of
+// ~10^6 dependent fp64 additions), records c_0 and the exact / inexact flag per frame and falls back to the 480 sequential
+// additions only for a frame that does round (binade crossings, increments with bits below the running sum's ulp);
+// hift_source_kernel then evaluates c_0 + (k+1) d per sample (or replays the frame's additions when flagged).  The round-2
+// sample-by-sample kernel was 33 % of the HiFT stage (profiles/r2_launches_hift.txt) and wrote / re-read 9 floats per sample.
+struct PhaseTab { double* c0; unsigned char* inexact; };   // [frame row][9]
+__device__ __forceinline__ bool frame_adds_exact(double c, double d) {
+  if (d == 0.0) return true;
+  const double cend = c + 480.0 * d;                                   // >= d > 0, normal
+  const int e = ((__double2hiint(cend) >> 20) & 0x7ff) - 1023;         // ilogb(cend); a rounded-up cend only makes u coarser
+  const double u_inv = __hiloint2double((1023 + 52 - e) << 20, 0);     // 1 / ulp(cend)
+  const double a = c * u_inv, b = d * u_inv;
+  return a == rint(a) && b == rint(b);
+}
+__global__ void hift_phase_frames_kernel(const float* f0, PhaseTab tab, const int* startT, const int* lenT, int n_seq) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_seq * 9) return;
   const int s = id / 9, h = id % 9;
-  const long L = (long)lenT[s] * 480;
-  float* out = cumf + startS[s] * 9 + (long)h * L;
   double c = 0.0;
+  const long r0 = startT[s];
   for (int tau = 0; tau < lenT[s]; ++tau) {
-    const float inc = f0[(long)startT[s] + tau] * (float)(h + 1) / 24000.0f;   // F_mat value (fp32)
+    const float inc = f0[r0 + tau] * (float)(h + 1) / 24000.0f;        // F_mat value (fp32)
     const double d = (double)inc;
-    float* o = out + (long)tau * 480;
-    for (int k = 0; k < 480; ++k) { c += d; o[k] = (float)c; }
+    const bool ex = frame_adds_exact(c, d);
+    tab.c0[(r0 + tau) * 9 + h] = c;
+    tab.inexact[(r0 + tau) * 9 + h] = ex ? 0 : 1;
+    if (ex) c = c + 480.0 * d;
+    else for (int k = 0; k < 480; ++k) c += d;
   }
 }
-__global__ void __launch_bounds__(480) hift_source_kernel(const float* f0, const float* cumf, const float* phase_vec,
+__global__ void __launch_bounds__(480) hift_source_kernel(const float* f0, PhaseTab tab, const float* phase_vec,
                                                           const float* noise, const float* lin_w, float lin_b,
                                                           float* s_out, const int* startT, const int* lenT,
                                                           const long* startS, int n_seq, unsigned long long seed) {
@@ -737,7 +754,12 @@ __global__ void __launch_bounds__(480) hift_source_kernel(const float* f0, const
   float acc = lin_b;
 #pragma unroll
   for (int h = 0; h < 9; ++h) {
-    const float cf = cumf[startS[s] * 9 + (long)h * L + n];
+    const long ti = ((long)startT[s] + tau) * 9 + h;
+    const double d = (double)(f * (float)(h + 1) / 24000.0f);
+    double cacc = tab.c0[ti];
+    if (!tab.inexact[ti]) cacc = cacc + (double)(o + 1) * d;              // exact: the product has <= 33 significant bits
+    else for (int k = 0; k <= o; ++k) cacc += d;                          // this frame rounds: replay its additions
+    const float cf = (float)cacc;
     const float frac = cf - floorf(cf);                                     // torch '% 1' on non-negative values
     const float theta = 6.283185307179586f * frac;
     const float ph = phase_vec ? phase_vec[s * 9 + h] : 0.f;
@@ -757,11 +779,15 @@ __global__ void __launch_bounds__(480) hift_source_kernel(const float* f0, const
 }
 void hift_source(Ctx& ctx, const float* f0, float* cumf, const float* phase_vec, const float* noise, const float* lin_w,
                  float lin_b, float* s_out, const int* startT, const int* lenT, const long* startS, int n_seq, int maxT,
-                 unsigned long long seed) {
+                 unsigned long long seed, long n_frame_rows) {
   if (ctx.dry || n_seq == 0) return;
   ctx.launches += 2;
-  hift_phase_scan_kernel<<<(n_seq * 9 + 31) / 32, 32, 0, ctx.stream>>>(f0, cumf, startT, lenT, startS, n_seq);
-  hift_source_kernel<<<dim3(maxT, n_seq), 480, 0, ctx.stream>>>(f0, cumf, phase_vec, noise, lin_w, lin_b, s_out, startT,
+  // the per-frame table lives in the caller's `cumf` scratch (sized for 9 floats per SAMPLE: far more than 9 x 9 bytes per frame)
+  PhaseTab tab;
+  tab.c0 = reinterpret_cast<double*>(cumf);
+  tab.inexact = reinterpret_cast<unsigned char*>(tab.c0 + (size_t)n_frame_rows * 9);
+  hift_phase_frames_kernel<<<(n_seq * 9 + 31) / 32, 32, 0, ctx.stream>>>(f0, tab, startT, lenT, n_seq);
+  hift_source_kernel<<<dim3(maxT, n_seq), 480, 0, ctx.stream>>>(f0, tab, phase_vec, noise, lin_w, lin_b, s_out, startT,
                                                                lenT, startS, n_seq, seed);
   CBX_CHECK(cudaGetLastError());
 }

@@ -126,6 +126,158 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+
+// ---- register-direct epilogue ---------------------------------------------------------------------------------------
+// One thread = one output row; a tcgen05.ld brings 32 consecutive accumulator columns of that row into registers and the
+// whole epilogue (bias, activation, residual, SwiGLU, plane split) runs on them with 32 independent chains, then leaves
+// as 16 / 32-byte vector stores (whole sectors per thread: a 32-column fp32 segment is one 128-byte line).  No shared-memory
+// transpose, no rolled per-row loops: the transposing epilogue below needed ~5 k dependent instructions per warp and, on
+// decode-sized GEMMs (<= 4 row tiles, one wave), WAS the kernel (ncu r2_ncu_gemm_tc_decode_before.txt: 14 cycles per issued
+// instruction, 70 k of 77 k cycles).
+__device__ __forceinline__ void stg256(float* p, const float* v) {      // 32-byte aligned
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ldg256(const float* p, float* v) {      // 32-byte aligned
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
+               "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2x(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// NV values of one row -> fp32 / fp16 plane / bf16 hi+lo planes at element offset `off` of the row (vector stores when the
+// whole group is in range and aligned, guarded scalar stores for the ragged last group of a matrix)
+template <int NV>
+__device__ __forceinline__ void store_row_f32(float* dst, const float* v, int nvalid, bool wide) {
+  if (nvalid >= NV) {
+    if (wide) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 8) stg256(dst + j, v + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) if (j < nvalid) dst[j] = v[j];
+  }
+}
+template <int NV>
+__device__ __forceinline__ void store_row_f16(__half* dst, const float* v, int nvalid) {
+  if (nvalid >= NV) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 8)
+      *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_h2x(v[j], v[j + 1]), pack_h2x(v[j + 2], v[j + 3]), pack_h2x(v[j + 4], v[j + 5]), pack_h2x(v[j + 6], v[j + 7]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) if (j < nvalid) dst[j] = __float2half_rn(v[j]);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void store_row_hilo(__nv_bfloat16* dh, __nv_bfloat16* dl, const float* v, int nvalid) {
+  if (nvalid >= NV) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 8) {
+      uint4 h, l;
+      split_pair(v[j], v[j + 1], h.x, l.x); split_pair(v[j + 2], v[j + 3], h.y, l.y);
+      split_pair(v[j + 4], v[j + 5], h.z, l.z); split_pair(v[j + 6], v[j + 7], h.w, l.w);
+      *reinterpret_cast<uint4*>(dh + j) = h; *reinterpret_cast<uint4*>(dl + j) = l;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) if (j < nvalid) { __nv_bfloat16 hh, ll; split_bf16(v[j], hh, ll); dh[j] = hh; dl[j] = ll; }
+  }
+}
+
+// epilogue of one warp's quarter (32 rows) x column half of the tile; Cz = C + split offset
+template <int BN>
+__device__ __forceinline__ void epilogue_direct(const GemmDev& g, float* Cz, uint32_t tmem_base, int m0, int n0, int q, int half,
+                                                int lane, bool row_valid) {
+  const int row = m0 + q * 32 + lane;
+  const bool row_ok = row < g.M;
+  const bool wide_c = (g.epi_direct & 2) != 0, wide_r = (g.epi_direct & 4) != 0;
+#pragma unroll 1
+  for (int cc = 0; cc < BN / 2; cc += 32) {
+    const int col = half * (BN / 2) + cc;
+    const int n = n0 + col;
+    if (n >= g.n_out) break;                     // warp-uniform
+    const int nvalid = g.n_out - n;              // >= 32 except in the ragged last chunk
+    float rres[32];
+    const bool has_res = g.res != nullptr;
+    if (has_res && row_ok && nvalid >= 32) {
+      const float* rp = g.res + (long)row * g.ldr + n;
+      if (wide_r) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) ldg256(rp + j, rres + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) { const float4 t = *reinterpret_cast<const float4*>(rp + j); rres[j] = t.x; rres[j + 1] = t.y; rres[j + 2] = t.z; rres[j + 3] = t.w; }
+      }
+    } else if (has_res && row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rres[j] = j < nvalid ? g.res[(long)row * g.ldr + n + j] : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rres[j] = 0.f;
+    }
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+    tmem_ld_wait();
+    float v[32];
+    if (g.bias) {                                // Npad-padded: the whole 32-column group is readable
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
+        v[j] = fmaf(__uint_as_float(r[j]), g.alpha, b.x); v[j + 1] = fmaf(__uint_as_float(r[j + 1]), g.alpha, b.y);
+        v[j + 2] = fmaf(__uint_as_float(r[j + 2]), g.alpha, b.z); v[j + 3] = fmaf(__uint_as_float(r[j + 3]), g.alpha, b.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha;
+    }
+    if (g.swiglu) {
+      // columns (2j, 2j+1) = (gate_j, up_j) -> out[j] = silu(gate) * up: 16 outputs at column n/2
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { const float v0 = v[2 * j]; o[j] = row_valid ? (v0 / (1.0f + expf(-v0))) * v[2 * j + 1] : 0.f; }
+      if (row_ok) {
+        const int no = n >> 1, nv = nvalid >> 1;
+        if (g.Chi && g.c_half) store_row_f16<16>(reinterpret_cast<__half*>(g.Chi) + (long)row * g.ldcb + no, o, nv);
+        else if (g.Chi) store_row_hilo<16>(g.Chi + (long)row * g.ldcb + no, g.Clo + (long)row * g.ldcb + no, o, nv);
+        else store_row_f32<16>(g.C + (long)row * g.ldc + no, o, nv, wide_c);
+      }
+      continue;
+    }
+    switch (g.act) {       // warp-uniform; one 32-wide copy of each hot activation
+      case ACT_NONE: break;
+      case ACT_LRELU:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * g.act_p;
+        break;
+      case ACT_SILU:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + expf(-v[j]));
+        break;
+      case ACT_GELU:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
+        break;
+      default:             // ACT_GELU_TANH (transformers NewGELUActivation)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + tanhf(0.79788456080286535588f * (v[j] + 0.044715f * (v[j] * v[j] * v[j]))));
+        break;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { v[j] = (v[j] + rres[j]) * g.out_scale; if (!row_valid) v[j] = 0.f; }
+    if (row_ok) {
+      if (g.Chi && g.c_half) store_row_f16<32>(reinterpret_cast<__half*>(g.Chi) + (long)row * g.ldcb + n, v, nvalid);
+      else if (g.Chi) store_row_hilo<32>(g.Chi + (long)row * g.ldcb + n, g.Clo + (long)row * g.ldcb + n, v, nvalid);
+      else store_row_f32<32>(Cz + (long)row * g.ldc + n, v, nvalid, wide_c);
+    }
+  }
+}
+
 template <int BN, int DUAL>
 __global__ void __launch_bounds__(TC_THREADS, DUAL ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA,
@@ -276,6 +428,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     const int myvalid = (er.valid && row_own < g.M) ? 1 : 0;
     float* st = reinterpret_cast<float*>(smem + warp * (32 * 33 * 4));   // pipeline buffers are idle now
     const int rows_here = min(32, g.M - (m0 + q * 32));
+    if (g.epi_direct) epilogue_direct<BN>(g, Cz, tmem_base, m0, n0, q, half, lane, myvalid != 0);
+    else
 #pragma unroll 1
     for (int cc = 0; cc < BN / 2; cc += 32) {
       const int col = half * (BN / 2) + cc;
@@ -1030,6 +1184,23 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
   if (g.splitk > 1) {
     CBX_REQUIRE(g.C && !g.bias && !g.res && !g.C2 && !g.Chi && !g.accumulate && !g.swiglu && g.act == ACT_NONE && g.alpha == 1.0f &&
                 g.out_scale == 1.0f && g.splitk <= g.Kpad / TC_BK, "split-K writes raw partial sums");
+  }
+  {
+    // register-direct epilogue (see epilogue_direct): every destination vector-aligned, one of the inline activations
+    auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(a - 1)) == 0; };
+    static const bool direct_on = !(getenv("CBX_EPI_DIRECT") && atoi(getenv("CBX_EPI_DIRECT")) == 0);
+    const bool act_ok = !g.act_vec && (g.act == ACT_NONE || g.act == ACT_LRELU || g.act == ACT_SILU || g.act == ACT_GELU || g.act == ACT_GELU_TANH);
+    bool ok = direct_on && act_ok && !g.C2 && !g.accumulate && !(g.Chi && g.C) && (g.Chi || g.C) && !g.dbg;
+    if (g.swiglu) ok = ok && !g.res && g.act == ACT_NONE && (g.n_out % 2) == 0;
+    if (g.C && !g.Chi) ok = ok && (g.ldc % 4) == 0 && al(g.C, 16) && (g.split_stride % 4) == 0;
+    if (g.Chi) ok = ok && (g.ldcb % 8) == 0 && al(g.Chi, 16) && (g.c_half || al(g.Clo, 16));
+    if (g.res) ok = ok && (g.ldr % 4) == 0 && al(g.res, 16);
+    g.epi_direct = 0;
+    if (ok) {
+      g.epi_direct = 1;
+      if (g.C && (g.ldc % 8) == 0 && al(g.C, 32) && (g.split_stride % 8) == 0) g.epi_direct |= 2;       // 32-byte stores
+      if (g.res && (g.ldr % 8) == 0 && al(g.res, 32)) g.epi_direct |= 4;                                 // 32-byte residual loads
+    }
   }
   dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM, g.splitk);
   if (ctx.timer && ctx.timer->cls == K_GEMM_TC) {

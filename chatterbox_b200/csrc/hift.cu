@@ -118,9 +118,10 @@ void hift_source_run(cbx_handle* h, Ctx& ctx, const float* mel, const cbx_hift_g
   }
   f0_head(ctx, cur, 512, m.f0_w.p, m.f0_b, f0, rows);
   if (f0_in) f0 = const_cast<float*>(f0_in);
-  float* cumf = ctx.ws.get<float>((size_t)g.total_samples * 9);
+  // per-frame phase table: 9 x (double c_0 + flag byte) per frame row
+  float* cumf = ctx.ws.get<float>((size_t)rows * 9 * 3 + 64);
   hift_source(ctx, f0, cumf, phase_vec, noise, m.src_w.p, m.src_b, s_out, LT.start, LT.len,
-              reinterpret_cast<const long*>(g.sample_start), LT.n_seq, LT.max_len, seed);
+              reinterpret_cast<const long*>(g.sample_start), LT.n_seq, LT.max_len, seed, rows);
 }
 
 struct RbBufs { float *xt, *t1, *xr; __nv_bfloat16 *p_hi, *p_lo, *t_hi, *t_lo; bool planes; };

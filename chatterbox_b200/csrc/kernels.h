@@ -66,7 +66,7 @@ void cfm_euler(Ctx& ctx, float* x, const float* v, const int* tile_seq2, const i
                const int* start3, int B, float dt, float w, int cfg, long rows2);
 void hift_source(Ctx& ctx, const float* f0, float* cumf, const float* phase_vec, const float* noise, const float* lin_w,
                  float lin_b, float* s_out, const int* startT, const int* lenT, const long* startS, int n_seq, int maxT,
-                 unsigned long long seed);
+                 unsigned long long seed, long n_frame_rows);
 void f0_head(Ctx& ctx, const float* x, int ld, const float* w, float b, float* f0, long rows);
 void hift_stft(Ctx& ctx, const float* s, float* out, const int* startF, const int* lenT, const long* startS, int n_seq,
                int maxT);

@@ -81,6 +81,7 @@ struct GemmDev {
   // GEMV path only (<= 8 rows, B=1 latency): A is the RAW residual stream and the kernel applies the row norm itself
   // (RMSNorm: norm_w * (x * rsqrt(mean x^2 + eps)); LayerNorm when norm_ln) -- one launch less per projection
   const float* norm_w; const float* norm_b; int norm_ln; float norm_eps;
+  int epi_direct;           // set by the launcher: bit 0 = register-direct epilogue, bit 1 = 32-byte C stores, bit 2 = 32-byte residual loads
 };
 
 struct Arena {  // bump allocator over caller-owned workspace; dry=true only counts
