@@ -66,6 +66,7 @@ SYMBOLS = {
     "cbx_test_attention_tc": (_I, [_P, _P, _P, _I, C.POINTER(Layout), _F, _P, _S, _P]),
     "cbx_test_paged_decode": (_I, [_P, _P, _P, _I, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _S, _P]),
     "cbx_test_gemm_splitk": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _S, _P]),
+    "cbx_bench_gemm_f16": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _S, _P]),
     "cbx_test_umma_rowshift": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "cbx_test_gemm_f16": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _S, _P]),
 }

@@ -1,5 +1,6 @@
 // C ABI of libcbx (include/cbx.h): handle lifetime, weight staging, exception -> status-code fence.
 #include "engine.h"
+#include <vector>
 #include <cuda_fp16.h>
 #include <cstdlib>
 
@@ -445,6 +446,61 @@ int cbx_test_gemm_f16(cbx_handle* h, const float* A, const float* w_host, const 
   CBX_CHECK(cudaStreamSynchronize(c.stream));
   free_weight(W);
   h->launches += c.launches;
+  CBX_GUARD_END(h)
+}
+
+/* micro-benchmark of one decode-step projection: C = A16[M][K] x W16[N][K]^T (+ SwiGLU) with `n_weights` distinct copies of
+ * the weight used round-robin (together larger than L2, as in the real step where 1 GB of weights streams per step);
+ * returns the average device time per launch in microseconds (CUDA events around reps * n_weights launches). */
+int cbx_bench_gemm_f16(cbx_handle* h, int M, int N, int K, int splitk, int tile_bn, int tile_dual, int swiglu, int n_weights,
+                       int reps, float* us_out, void* ws, size_t ws_bytes, cbx_stream stream) {
+  if (!h || !us_out) return CBX_ERR_INVALID;
+  CBX_GUARD_BEGIN
+  CBX_REQUIRE(n_weights >= 1 && n_weights <= 64 && reps >= 1, "bench shape");
+  std::vector<float> hw((size_t)N * K);
+  uint32_t x = 12345u;
+  for (auto& v : hw) { x = x * 1664525u + 1013904223u; v = ((float)(x >> 8) / 16777216.0f - 0.5f) * 0.06f; }
+  std::vector<Weight> Ws(n_weights);
+  pack_linear(Ws[0], hw.data(), nullptr, N, K, true);
+  for (int i = 1; i < n_weights; ++i) {
+    Ws[i] = Ws[0];
+    Ws[i].w = nullptr; Ws[i].bias = nullptr;
+    CBX_CHECK(cudaMalloc(&Ws[i].w16, (size_t)Ws[0].Npad * Ws[0].Kpad * 2));
+    CBX_CHECK(cudaMemcpy(Ws[i].w16, Ws[0].w16, (size_t)Ws[0].Npad * Ws[0].Kpad * 2, cudaMemcpyDeviceToDevice));
+    Weight tmp = Ws[i]; tmp.w = reinterpret_cast<__nv_bfloat16*>(Ws[i].w16);
+    make_tmaps_for(tmp);
+    for (int j = 0; j < 3; ++j) Ws[i].tmap16[j] = tmp.tmap[j];
+    Ws[i].bias = Ws[0].bias;
+  }
+  Ctx c = make_ctx(h, ws, ws_bytes, stream);
+  c.timer = nullptr;
+  __half* a16 = c.ws.get<__half>((size_t)M * K);
+  CBX_CHECK(cudaMemsetAsync(a16, 0x2c, (size_t)M * K * 2, c.stream));        // 0x2c2c = 0.0652 in fp16
+  const int n_out = swiglu ? N / 2 : N;
+  float* C = c.ws.get<float>((size_t)(splitk > 1 ? splitk : 1) * M * n_out);
+  __half* c16 = c.ws.get<__half>((size_t)M * n_out);
+  cudaEvent_t e0, e1;
+  CBX_CHECK(cudaEventCreate(&e0)); CBX_CHECK(cudaEventCreate(&e1));
+  auto one = [&](const Weight& W) {
+    GemmDev g = gemm_args_linear(nullptr, K, M, W, C, n_out);
+    g.A16 = a16; g.lda16 = K; g.bias = nullptr;
+    g.tile_bn = tile_bn; g.tile_dual = tile_dual;
+    if (swiglu) { g.swiglu = 1; g.C = nullptr; g.Chi = reinterpret_cast<__nv_bfloat16*>(c16); g.Clo = g.Chi; g.ldcb = n_out; g.c_half = 1; }
+    if (splitk > 1) { g.splitk = splitk; g.split_stride = (long)M * n_out; }
+    gemm(c, g, W);
+  };
+  for (int i = 0; i < n_weights; ++i) one(Ws[i]);                              // warm-up
+  CBX_CHECK(cudaEventRecord(e0, c.stream));
+  for (int r = 0; r < reps; ++r)
+    for (int i = 0; i < n_weights; ++i) one(Ws[i]);
+  CBX_CHECK(cudaEventRecord(e1, c.stream));
+  CBX_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CBX_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  *us_out = ms * 1000.0f / (float)(reps * n_weights);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (int i = 1; i < n_weights; ++i) cudaFree(Ws[i].w16);
+  free_weight(Ws[0]);
   CBX_GUARD_END(h)
 }
 

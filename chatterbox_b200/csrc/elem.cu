@@ -197,6 +197,32 @@ void pack_hilo_cat(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat
   pack_hilo_cat_kernel<<<(unsigned)(((long)Npad * K + 255) / 256), 256, 0, ctx.stream>>>(src, ld, N, K, out, Npad);
   CBX_CHECK(cudaGetLastError());
 }
+// fp32 activations [rows][cols] (ld) of a packed batch -> bf16 hi/lo planes [rows][ldp], ZERO on layout padding rows: the
+// operand of a plane-fed conv GEMM (its taps read the rows before a sequence start, which are the padding rows of the
+// previous sequence).  4 elements per thread (16-byte load, two 8-byte stores); cols % 4 == 0.
+__global__ void pack_planes_seq_kernel(const float* src, int ld, long rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo, int ldp,
+                                       SeqMap seq) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4 = cols >> 2;
+  if (i >= rows * c4) return;
+  const long r = i / c4; const int c = (int)(i - r * c4) << 2;
+  const int s = seq.tile_seq[r / kTileM];
+  const bool valid = (s >= 0) && (r - seq.out_start[s] < seq.out_len[s]);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) v = *reinterpret_cast<const float4*>(src + r * ld + c);
+  __nv_bfloat16 h[4], l[4];
+  split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi + r * ldp + c) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+  *reinterpret_cast<uint2*>(lo + r * ldp + c) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+}
+void pack_planes_seq(Ctx& ctx, const float* src, int ld, long rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo, int ldp,
+                     const SeqMap& seq) {
+  if (ctx.dry || rows == 0) return;
+  CBX_REQUIRE((cols % 4) == 0 && (ld % 4) == 0 && (ldp % 4) == 0, "pack_planes_seq: 4-element groups");
+  ctx.launches++;
+  pack_planes_seq_kernel<<<(unsigned)((rows * (cols >> 2) + 255) / 256), 256, 0, ctx.stream>>>(src, ld, rows, cols, hi, lo, ldp, seq);
+  CBX_CHECK(cudaGetLastError());
+}
 void pack_hilo(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat16* hi, __nv_bfloat16* lo, int Npad, int Kpad) {
   if (ctx.dry) return;
   ctx.launches++;

@@ -4,6 +4,7 @@
 // Everything runs on packed channel-last buffers [rows, C] (see cbx_layout); convs are implicit GEMMs.
 #include "engine.h"
 #include <cmath>
+#include <cstdlib>
 
 namespace cbx {
 
@@ -250,11 +251,33 @@ void flow_encode(cbx_handle* h, Ctx& ctx, const int* tokens, const cbx_layout& L
 
 // ---- CFM estimator ---------------------------------------------------------------------------------
 struct EstBufs { float *h1, *h2, *hn, *qkv, *att, *ff; __nv_bfloat16 *qkv_hi, *qkv_lo; CUtensorMap tm_hi, tm_lo; bool tc; bool f16; bool a16;
-                 double attn_work; };
+                 double attn_work;
+                 // plane-fed convs (b.cp): conv input [rows][<=512] and the LayerNorm+Mish output [rows][256] as bf16 hi/lo planes
+                 bool cp; __nv_bfloat16 *in_hi, *in_lo, *h_hi, *h_lo; };
+
+// stride-1 conv as a plane-fed GEMM: the input travels as bf16 hi/lo planes (zero on layout padding rows), every tap is the same
+// TMA box shifted by one row -- no fp32 tile, no converter warps in the main loop; same split, same products as the converter path
+static GemmDev conv_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ldp, const Weight& W, int c_in, int ntaps, int pad,
+                           const cbx_layout& L, float* C, int ldc) {
+  GemmDev g = conv_args(nullptr, ldp, W, c_in, ntaps, 1, pad, 1, L, L, C, ldc);
+  g.Ahi = hi; g.Alo = lo; g.ldab = ldp;
+  return g;
+}
 
 static void cfm_resnet(Ctx& ctx, CfmResnet& r, const float* in, int lda, int cin, float* out, int ldo, const float* tvec,
                        const cbx_layout& L, EstBufs& b) {
   SeqMap sm = seqmap(L, L);
+  if (b.cp) {
+    pack_planes_seq(ctx, in, lda, L.rows, cin, b.in_hi, b.in_lo, 512, sm);
+    gemm(ctx, conv_planes(b.in_hi, b.in_lo, 512, r.conv1, cin, 3, 2, L, b.h1, 256), r.conv1);
+    layernorm(ctx, b.h1, 256, r.ln1_w.p, r.ln1_b.p, nullptr, 256, L.rows, 256, 1e-5f, ACT_MISH, 1.f, tvec, 0, &sm, b.h_hi, b.h_lo);
+    gemm(ctx, conv_planes(b.h_hi, b.h_lo, 256, r.conv2, 256, 3, 2, L, b.h1, 256), r.conv2);
+    layernorm(ctx, b.h1, 256, r.ln2_w.p, r.ln2_b.p, b.h2, 256, L.rows, 256, 1e-5f, ACT_MISH, 1.f, nullptr, 0, &sm);
+    GemmDev g = conv_planes(b.in_hi, b.in_lo, 512, r.res, cin, 1, 0, L, out, ldo);
+    g.res = b.h2; g.ldr = 256;
+    gemm(ctx, g, r.res);
+    return;
+  }
   gemm(ctx, conv_args(in, lda, r.conv1, cin, 3, 1, 2, 1, L, L, b.h1, 256), r.conv1);
   layernorm(ctx, b.h1, 256, r.ln1_w.p, r.ln1_b.p, b.h2, 256, L.rows, 256, 1e-5f, ACT_MISH, 1.f, tvec, 0, &sm);
   gemm(ctx, conv_args(b.h2, 256, r.conv2, 256, 3, 1, 2, 1, L, L, b.h1, 256), r.conv2);
@@ -401,6 +424,15 @@ void cfm_solve(cbx_handle* h, Ctx& ctx, const float* mu, const float* spk, const
   b.attn_work = 0.0;
   if (L3.h_len) for (int i = 0; i < L3.n_seq; ++i) b.attn_work += 4.0 * 64.0 * 8.0 * (double)L3.h_len[i] * (double)L3.h_len[i];
   b.tc = (ctx.attn_impl == 0 && ctx.gemm_impl == 0);
+  static const bool conv_planes_on = !(getenv("CBX_CONV_PLANES") && atoi(getenv("CBX_CONV_PLANES")) == 0);
+  b.cp = b.tc && conv_planes_on && L3.h_start && L3.h_len;
+  // the plane path has no per-row tap mask: it needs >= 2 (zero) padding rows between consecutive sequences of the layout
+  if (b.cp) for (int i = 0; i + 1 < L3.n_seq; ++i) if (L3.h_start[i + 1] - (L3.h_start[i] + L3.h_len[i]) < 2) { b.cp = false; break; }
+  b.in_hi = b.in_lo = b.h_hi = b.h_lo = nullptr;
+  if (b.cp) {
+    b.in_hi = ctx.ws.get<__nv_bfloat16>((size_t)rows3 * 512); b.in_lo = ctx.ws.get<__nv_bfloat16>((size_t)rows3 * 512);
+    b.h_hi = ctx.ws.get<__nv_bfloat16>((size_t)rows3 * 256); b.h_lo = ctx.ws.get<__nv_bfloat16>((size_t)rows3 * 256);
+  }
   b.f16 = b.tc && ctx.attn_f16 != 0;
   b.a16 = b.f16 && ctx.cfm_act_f16 != 0;      // fp16 activations ride on the fp16 attention variant
   b.qkv_hi = reinterpret_cast<__nv_bfloat16*>(b.qkv);                 // the planes reuse the fp32 qkv buffer
@@ -415,7 +447,15 @@ void cfm_solve(cbx_handle* h, Ctx& ctx, const float* mu, const float* spk, const
     float* skip = xcat + 256;
     cfm_resnet(ctx, m.down.res, xin, 320, 320, skip, 512, tv(0), L3, b);
     for (int j = 0; j < 4; ++j) cfm_tfmr(ctx, m.down.t[j], skip, 512, L3, b);
-    gemm(ctx, conv_args(skip, 512, m.down_conv, 256, 3, 1, 2, 1, L3, L3, bufX, 256), m.down_conv);
+    auto causal_conv = [&](const float* src, int lds, Weight& W, float* dst) {      // CausalConv1d k3 (decoder.py:26-34)
+      if (b.cp) {
+        pack_planes_seq(ctx, src, lds, rows3, 256, b.in_hi, b.in_lo, 512, sm3);
+        gemm(ctx, conv_planes(b.in_hi, b.in_lo, 512, W, 256, 3, 2, L3, dst, 256), W);
+      } else {
+        gemm(ctx, conv_args(src, lds, W, 256, 3, 1, 2, 1, L3, L3, dst, 256), W);
+      }
+    };
+    causal_conv(skip, 512, m.down_conv, bufX);
     // 12 mid blocks (decoder.py:299-312); the last one writes into xcat[:, 0:256]
     float* cur = bufX; float* nxt = bufY;
     for (int i = 0; i < 12; ++i) {
@@ -428,11 +468,16 @@ void cfm_solve(cbx_handle* h, Ctx& ctx, const float* mu, const float* spk, const
     // up block on cat[x, skip] (decoder.py:314-330)
     cfm_resnet(ctx, m.up.res, xcat, 512, 512, bufX, 256, tv(13), L3, b);
     for (int j = 0; j < 4; ++j) cfm_tfmr(ctx, m.up.t[j], bufX, 256, L3, b);
-    gemm(ctx, conv_args(bufX, 256, m.up_conv2, 256, 3, 1, 2, 1, L3, L3, bufY, 256), m.up_conv2);
+    causal_conv(bufX, 256, m.up_conv2, bufY);
     // final block + projection (decoder.py:331-333)
-    gemm(ctx, conv_args(bufY, 256, m.final_conv, 256, 3, 1, 2, 1, L3, L3, b.h1, 256), m.final_conv);
-    layernorm(ctx, b.h1, 256, m.final_ln_w.p, m.final_ln_b.p, b.h2, 256, (int)rows3, 256, 1e-5f, ACT_MISH, 1.f, nullptr, 0, &sm3);
-    gemm(ctx, conv_args(b.h2, 256, m.final_proj, 256, 1, 0, 0, 1, L3, L3, v, 80), m.final_proj);
+    causal_conv(bufY, 256, m.final_conv, b.h1);
+    if (b.cp) {
+      layernorm(ctx, b.h1, 256, m.final_ln_w.p, m.final_ln_b.p, nullptr, 256, (int)rows3, 256, 1e-5f, ACT_MISH, 1.f, nullptr, 0, &sm3, b.h_hi, b.h_lo);
+      gemm(ctx, conv_planes(b.h_hi, b.h_lo, 256, m.final_proj, 256, 1, 0, L3, v, 80), m.final_proj);
+    } else {
+      layernorm(ctx, b.h1, 256, m.final_ln_w.p, m.final_ln_b.p, b.h2, 256, (int)rows3, 256, 1e-5f, ACT_MISH, 1.f, nullptr, 0, &sm3);
+      gemm(ctx, conv_args(b.h2, 256, m.final_proj, 256, 1, 0, 0, 1, L3, L3, v, 80), m.final_proj);
+    }
     cfm_euler(ctx, x, v, L2.tile_seq, L2.start, L2.len, L3.start, B, tspan[k + 1] - tspan[k], cfg_rate, cfg, rows2);
   }
 }

@@ -609,11 +609,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         uint8_t* a_st = smem + s * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&tma_full[s], g.a_tma == 3 ? (16384 + Cfg::W_BYTES) : g.a_tma ? (Cfg::A_BYTES + Cfg::W_BYTES) : Cfg::W_BYTES);
         tma_load_2d(a_st + Cfg::A_BYTES, &tmapW, &tma_full[s], (kb0 + kb) * TC_BK, n0);
-        if (g.a_tma == 3) {
-          tma_load_2d(a_st, &tmapA, &tma_full[s], (kb0 + kb) * TC_BK, m0);             // the fp16 plane
-        } else if (g.a_tma == 2) {
-          tma_load_2d(a_st, &tmapA, &tma_full[s], (kb0 + kb) * TC_BK, m0);             // hi plane, SWIZZLE_128B
-          tma_load_2d(a_st + 16384, &tmapA2, &tma_full[s], (kb0 + kb) * TC_BK, m0);    // lo plane
+        if (g.a_tma >= 2) {
+          // plane operands: (channel block, input row of this tap) -- for a plain Linear that is (k, m0); for a stride-1 conv
+          // the same tile shifted by tap * dil rows.  Rows of other sequences never enter: the producers of conv planes write
+          // zeros on layout padding rows and every sequence is followed by >= pad of them (engine.py layouts).
+          const int k0 = (kb0 + kb) * TC_BK;
+          const int tap = k0 / g.ctap, c = k0 - tap * g.ctap;
+          const int arow = (int)(in_row0 + (long)tap * g.dil);
+          tma_load_2d(a_st, &tmapA, &tma_full[s], c, arow);                              // hi plane (or the fp16 plane), SWIZZLE_128B
+          if (g.a_tma == 2) tma_load_2d(a_st + 16384, &tmapA2, &tma_full[s], c, arow);   // lo plane
         } else if (g.a_tma) {
           const int k0 = (kb0 + kb) * TC_BK;
           const int tap = k0 / g.ctap, c = k0 - tap * g.ctap;
@@ -809,6 +813,139 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constan
           }
         }
       }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+
+// ================================================================================================
+// gemm_stream_kernel: persistent tcgen05 GEMM for the decode-step projections (M <= a few row tiles, K = 1024 / 4096):
+//     C[M, N] = epilogue( A16[M, K] (one fp16 plane, TMA) x W16[N, K]^T (fp16 copy of the weight, TMA) )
+// Why a second kernel: at 512 rows a projection is 2-9 GFLOP against 2-17 MB of weights -- a few microseconds of tensor or
+// HBM time -- and the one-tile-per-CTA kernel spends several times that on everything else: two shallow stages (its shared
+// memory is laid out for the fp32 A tile of the converter path), a cold pipeline per tile, TMEM allocation and barrier set-up
+// per tile, an epilogue that starts only after the last MMA.  Here each CTA owns a list of (row tile, column tile, K split)
+// items and keeps ONE pipeline running across them: 6 stages of (A 16 KB + W BN x 128 B) always in flight -- the loads of
+// the next item start while the current one is still in its MMAs -- the accumulator is double buffered in TMEM so the
+// register-direct epilogue (epilogue_direct) of item i runs under the main loop of item i+1, and all set-up happens once.
+// Items are ordered row-tile-fastest: the CTAs that share a weight tile run at the same time and it crosses HBM once.
+//   warp 0: TMA producer   warp 1: MMA issuer (+ TMEM owner)   warps 2-9: epilogue
+// Algorithmic HBM bytes per launch: M*K*2 (A) + N*K*2 (W, once) + outputs.
+// ================================================================================================
+template <int BN> struct StreamCfg {
+  static constexpr int STAGES = BN == 64 ? 8 : (BN == 128 ? 6 : 4);
+  static constexpr int STAGE_BYTES = 16384 + BN * 128;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(WR_THREADS, 1)
+gemm_stream_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA, const GemmDev g,
+                   const int n_ntiles) {
+  using Cfg = StreamCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                    // [STAGES]
+  uint64_t* empty = bars + STAGES;          // [STAGES]
+  uint64_t* acc_full = empty + STAGES;      // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmapW); tma_prefetch_desc(&tmapA); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                 // (decode step) the producer of A / m_live has completed
+  pdl_launch_dependents();
+  // work list: live row tiles x column tiles x K splits, row tile fastest
+  const int m_rows = g.m_live ? min(*g.m_live, g.M) : g.M;
+  const int n_mt = (m_rows + TC_BM - 1) / TC_BM;
+  const int splitk = g.splitk > 1 ? g.splitk : 1;
+  const int n_items = n_mt * n_ntiles * splitk;
+  const int KBt = g.Kpad / TC_BK;
+  auto item = [&](int it, int& m0, int& n0, int& kb0, int& KB, int& ks) {
+    const int mt = it % n_mt;
+    const int rest = it / n_mt;
+    const int nt = rest % n_ntiles;
+    ks = rest / n_ntiles;
+    m0 = mt * TC_BM; n0 = nt * BN;
+    kb0 = (int)((long)ks * KBt / splitk);
+    KB = (int)((long)(ks + 1) * KBt / splitk) - kb0;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =================================================================
+    if (lane == 0) {
+      uint32_t gi = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        int m0, n0, kb0, KB, ks;
+        item(it, m0, n0, kb0, KB, ks);
+        for (int kb = 0; kb < KB; ++kb, ++gi) {
+          const int s = gi % STAGES;
+          mbar_wait(&empty[s], ((gi / STAGES) & 1) ^ 1);
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          tma_load_2d(st, &tmapA, &full[s], (kb0 + kb) * TC_BK, m0);
+          tma_load_2d(st + 16384, &tmapW, &full[s], (kb0 + kb) * TC_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer ===================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16f16(TC_BM, BN);
+      uint32_t gi = 0;
+      int i = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
+        int m0, n0, kb0, KB, ks;
+        item(it, m0, n0, kb0, KB, ks);
+        const int buf = i & 1;
+        mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < KB; ++kb, ++gi) {
+          const int s = gi % STAGES;
+          mbar_wait(&full[s], (gi / STAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t w_addr = a_addr + 16384;
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 16; ++k4)
+            umma_bf16(d, umma_desc_sw128(a_addr + k4 * 32), umma_desc_sw128(w_addr + k4 * 32), idesc, (kb | k4) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =========================================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int i = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++i) {
+      int m0, n0, kb0, KB, ks;
+      item(it, m0, n0, kb0, KB, ks);
+      const int buf = i & 1;
+      mbar_wait(&acc_full[buf], (i >> 1) & 1);
+      tcgen05_fence_after();
+      float* Cz = g.C ? g.C + (long)ks * g.split_stride : nullptr;
+      epilogue_direct<BN>(g, Cz, tmem_base + (uint32_t)(buf * BN), m0, n0, q, half, lane, m0 + q * 32 + lane < g.M);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -1158,6 +1295,27 @@ void gemm_init() {
   set_tc_attr<64, 0>(); set_tc_attr<64, 1>(); set_tc_attr<128, 0>(); set_tc_attr<128, 1>(); set_tc_attr<256, 0>();
   CBX_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM));
   CBX_CHECK(cudaFuncSetAttribute(gemm_wres_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM));
+  CBX_CHECK(cudaFuncSetAttribute(gemm_stream_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<64>::SMEM));
+  CBX_CHECK(cudaFuncSetAttribute(gemm_stream_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<128>::SMEM));
+  CBX_CHECK(cudaFuncSetAttribute(gemm_stream_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<256>::SMEM));
+}
+
+// register-direct epilogue (see epilogue_direct): every destination vector-aligned, one of the inline activations
+static void set_epi_direct(GemmDev& g) {
+  auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(a - 1)) == 0; };
+  static const bool direct_on = !(getenv("CBX_EPI_DIRECT") && atoi(getenv("CBX_EPI_DIRECT")) == 0);
+  const bool act_ok = !g.act_vec && (g.act == ACT_NONE || g.act == ACT_LRELU || g.act == ACT_SILU || g.act == ACT_GELU || g.act == ACT_GELU_TANH);
+  bool ok = direct_on && act_ok && !g.C2 && !g.accumulate && !(g.Chi && g.C) && (g.Chi || g.C) && !g.dbg;
+  if (g.swiglu) ok = ok && !g.res && g.act == ACT_NONE && (g.n_out % 2) == 0;
+  if (g.C && !g.Chi) ok = ok && (g.ldc % 4) == 0 && al(g.C, 16) && (g.split_stride % 4) == 0;
+  if (g.Chi) ok = ok && (g.ldcb % 8) == 0 && al(g.Chi, 16) && (g.c_half || al(g.Clo, 16));
+  if (g.res) ok = ok && (g.ldr % 4) == 0 && al(g.res, 16);
+  g.epi_direct = 0;
+  if (ok) {
+    g.epi_direct = 1;
+    if (g.C && (g.ldc % 8) == 0 && al(g.C, 32) && (g.split_stride % 8) == 0) g.epi_direct |= 2;       // 32-byte stores
+    if (g.res && (g.ldr % 8) == 0 && al(g.res, 32)) g.epi_direct |= 4;                                 // 32-byte residual loads
+  }
 }
 
 template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Weight& W, int tmap_idx) {
@@ -1172,10 +1330,12 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
     make_plane_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(g.A16), g.M, g.k_total, 128, g.lda16);   // 2-byte elements
     tmA2 = tmA;
   } else if (g.Ahi) {
-    CBX_REQUIRE(g.ntaps == 1 && !g.has_seq && g.Alo && (g.ldab % 8) == 0, "plane operand needs a plain Linear");
+    CBX_REQUIRE(g.a_mode == A_TAPS && g.stride == 1 && g.Alo && (g.ldab % 8) == 0, "plane operands need a Linear or a stride-1 conv");
     g.a_tma = 2;
-    make_plane_tmap(&tmA, g.Ahi, g.M, g.k_total, 128, g.ldab);
-    make_plane_tmap(&tmA2, g.Alo, g.M, g.k_total, 128, g.ldab);
+    const long a_rows = (g.ntaps > 1 || g.has_seq) ? g.M_in : g.M;
+    const int a_cols = (g.ntaps > 1 || g.has_seq) ? g.c_in : g.k_total;
+    make_plane_tmap(&tmA, g.Ahi, a_rows, a_cols, 128, g.ldab);
+    make_plane_tmap(&tmA2, g.Alo, a_rows, a_cols, 128, g.ldab);
   } else {
     if (g.a_tma) make_a_tmap(&tmA, g); else tmA = W.tmap[tmap_idx];
     tmA2 = tmA;
@@ -1185,23 +1345,7 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
     CBX_REQUIRE(g.C && !g.bias && !g.res && !g.C2 && !g.Chi && !g.accumulate && !g.swiglu && g.act == ACT_NONE && g.alpha == 1.0f &&
                 g.out_scale == 1.0f && g.splitk <= g.Kpad / TC_BK, "split-K writes raw partial sums");
   }
-  {
-    // register-direct epilogue (see epilogue_direct): every destination vector-aligned, one of the inline activations
-    auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(a - 1)) == 0; };
-    static const bool direct_on = !(getenv("CBX_EPI_DIRECT") && atoi(getenv("CBX_EPI_DIRECT")) == 0);
-    const bool act_ok = !g.act_vec && (g.act == ACT_NONE || g.act == ACT_LRELU || g.act == ACT_SILU || g.act == ACT_GELU || g.act == ACT_GELU_TANH);
-    bool ok = direct_on && act_ok && !g.C2 && !g.accumulate && !(g.Chi && g.C) && (g.Chi || g.C) && !g.dbg;
-    if (g.swiglu) ok = ok && !g.res && g.act == ACT_NONE && (g.n_out % 2) == 0;
-    if (g.C && !g.Chi) ok = ok && (g.ldc % 4) == 0 && al(g.C, 16) && (g.split_stride % 4) == 0;
-    if (g.Chi) ok = ok && (g.ldcb % 8) == 0 && al(g.Chi, 16) && (g.c_half || al(g.Clo, 16));
-    if (g.res) ok = ok && (g.ldr % 4) == 0 && al(g.res, 16);
-    g.epi_direct = 0;
-    if (ok) {
-      g.epi_direct = 1;
-      if (g.C && (g.ldc % 8) == 0 && al(g.C, 32) && (g.split_stride % 8) == 0) g.epi_direct |= 2;       // 32-byte stores
-      if (g.res && (g.ldr % 8) == 0 && al(g.res, 32)) g.epi_direct |= 4;                                 // 32-byte residual loads
-    }
-  }
+  set_epi_direct(g);
   dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM, g.splitk);
   if (ctx.timer && ctx.timer->cls == K_GEMM_TC) {
     ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
@@ -1245,6 +1389,30 @@ template <int BN> static void launch_wres(Ctx& ctx, GemmDev g, const Weight& W) 
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
 }
 
+// persistent streaming kernel for the decode-step projections: eligible launches (see gemm())
+template <int BN> static void launch_stream(Ctx& ctx, GemmDev g, const Weight& W) {
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; CBX_CHECK(cudaGetDevice(&dev)); CBX_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+  CUtensorMap tmA;
+  make_plane_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(g.A16), g.M, g.k_total, 128, g.lda16);   // 2-byte elements
+  if (g.splitk < 1) g.splitk = 1;
+  const int n_ntiles = (g.Npad + BN - 1) / BN;
+  const int n_items = ((g.M + TC_BM - 1) / TC_BM) * n_ntiles * g.splitk;
+  if (ctx.timer && ctx.timer->cls == K_GEMM_TC) {
+    ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
+    const double out_elems = (double)g.M * (double)(g.swiglu ? g.n_out / 2 : g.n_out);
+    double b = (double)g.Npad * g.Kpad * 2.0 + (double)g.M * g.k_total * 2.0;
+    if (g.C) b += out_elems * 4.0 * g.splitk;
+    if (g.Chi) b += out_elems * (g.c_half ? 2.0 : 4.0);
+    if (g.res) b += out_elems * 4.0;
+    ctx.timer->bytes += b;
+  }
+  if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
+  launch_kernel(ctx, gemm_stream_kernel<BN>, dim3(n_items < n_sm ? n_items : n_sm), dim3(WR_THREADS), (size_t)StreamCfg<BN>::SMEM,
+                W.tmap16[BN == 64 ? 0 : (BN == 128 ? 1 : 2)], tmA, g, n_ntiles);
+  if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
+}
+
 template <int R> static void launch_gemv(Ctx& ctx, const GemmDev& g) {
   if (ctx.timer) ctx.timer->begin(K_GEMV, ctx.stream);
   struct End { Ctx& c; ~End() { if (c.timer) c.timer->end(K_GEMV, c.stream); } } _end{ctx};
@@ -1278,6 +1446,21 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     if (wres_on && g.A16 && W.w16 && !g.has_seq && g.ntaps == 1 && g.splitk <= 1 && wres_epi && g.M >= 4 * TC_BM) {
       if (g.Kpad == 256 && g.Npad % 256 == 0) { launch_wres<256>(ctx, g, W); CBX_CHECK(cudaGetLastError()); return; }
       if (g.Kpad == 512 && g.Npad % 128 == 0) { launch_wres<128>(ctx, g, W); CBX_CHECK(cudaGetLastError()); return; }
+    }
+    // fp16-plane Linear at decode size (a few row tiles, long reduction): persistent streaming kernel
+    static const int stream_max_m = getenv("CBX_GEMM_STREAM") ? atoi(getenv("CBX_GEMM_STREAM")) : 1024;
+    if (g.A16 && W.w16 && !g.has_seq && g.ntaps == 1 && g.M > 8 && g.M <= stream_max_m && g.Kpad >= 512) {
+      GemmDev gs = g;
+      if (gs.splitk < 1) gs.splitk = 1;
+      set_epi_direct(gs);
+      const bool split_ok = gs.splitk == 1 || (gs.C && !gs.bias && !gs.res && !gs.Chi && !gs.swiglu && gs.act == ACT_NONE && gs.alpha == 1.0f &&
+                                               gs.out_scale == 1.0f && gs.splitk <= gs.Kpad / TC_BK);
+      if (gs.epi_direct && split_ok) {
+        const int bn = (g.tile_bn == 64 || g.tile_bn == 256) && g.Npad % g.tile_bn == 0 ? g.tile_bn : (g.Npad % 128 == 0 ? 128 : 64);
+        if (bn == 64) launch_stream<64>(ctx, gs, W); else if (bn == 128) launch_stream<128>(ctx, gs, W); else launch_stream<256>(ctx, gs, W);
+        CBX_CHECK(cudaGetLastError());
+        return;
+      }
     }
     CBX_REQUIRE(!g.norm_w || (plain && g.M <= 8), "the fused row norm exists in the GEMV kernel only");
     if (plain && g.M <= 8) {

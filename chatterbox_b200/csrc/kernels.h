@@ -35,6 +35,8 @@ void gather_rows(Ctx& ctx, const float* table, int ld, const int* ids, float* ou
                  const float* add_table, int add_ld, const int* add_ids, int id_limit);
 void pack_hilo(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat16* hi, __nv_bfloat16* lo, int Npad, int Kpad);
 void pack_hilo_cat(Ctx& ctx, const float* src, int ld, int N, int K, __nv_bfloat16* out, int Npad);
+void pack_planes_seq(Ctx& ctx, const float* src, int ld, long rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo, int ldp,
+                     const SeqMap& seq);
 void t3_embed(Ctx& ctx, float* out, int n_tok, const int* tok_row, const int* tok_pos, const float* cond,
               const int* row_voice, int len_cond, const int* text_flat, const int* text_start, const int* n_text,
               const int* row_uncond, const float* text_emb, int text_vocab, const float* text_pos,

@@ -399,7 +399,7 @@ class Engine:
         n_gen = np.array([int(t.numel()) for t in tokens], dtype=np.int32)
         n = np_len + n_gen
         L1 = PackedLayout(n, dev)
-        L2 = PackedLayout(2 * n, dev)
+        L2 = PackedLayout(2 * n, dev, alloc=2 * n + 4)     # >= 4 zero rows after every sequence: the halo of the plane-fed causal convs
         # streaming chunk (finalize=False, reference flow.py:170-171): the encoder sees every token, the decoder drops the
         # last pre_lookahead_len * token_mel_ratio = 6 frames (they still depend on tokens that have not arrived yet)
         cut = 0 if finalize else 6

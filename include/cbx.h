@@ -217,6 +217,12 @@ int cbx_test_gemm_splitk(cbx_handle* h, const float* A, const float* w_host, int
 int cbx_test_gemm_f16(cbx_handle* h, const float* A, const float* w_host, const float* bias_host, const float* res, int M,
                       int N, int K, int act, int out_half, float* C, void* ws, size_t ws_bytes, cbx_stream stream);
 
+/* micro-benchmark of one decode-step projection (A fp16 plane [M][K], fp16 weight copy, optional SwiGLU epilogue, split-K partial
+ * sums): `n_weights` distinct weight copies are used round-robin so that the weights stream from HBM as they do in the real
+ * step; *us_out = average device time per launch in microseconds (tools/decode_gemm_bench.py). */
+int cbx_bench_gemm_f16(cbx_handle* h, int M, int N, int K, int splitk, int tile_bn, int tile_dual, int swiglu, int n_weights,
+                       int reps, float* us_out, void* ws, size_t ws_bytes, cbx_stream stream);
+
 /* hardware probe: D[128][64] = A[shift .. shift+127][0..63] . W[64][64]^T, A (bf16 [160][64]) staged once in shared memory and
  * read through a row-shifted SWIZZLE_128B UMMA descriptor (mode 1: with the descriptor's base-offset field set) */
 int cbx_test_umma_rowshift(cbx_handle* h, const void* A_bf16, const void* W_bf16, int shift, int mode, float* C, cbx_stream stream);
