@@ -344,21 +344,22 @@ def run_engine(args, rank, world, local_rank):
     audio_e = allsum(sum(t["audio_s"] for t in tms_e))
     log(f"e2e: {ms_e:.1f} ms for {e2e_steps} steps")
 
-    # ---- 3. profiling passes (outside the timed region): one kernel class per pass, CUDA events per launch
+    # ---- 3. profiling pass (outside the timed region): CUDA events around every launch of every instrumented kernel class
     prof = {}
     if not args.no_profile:
-        for cls in ("gemm_tc", "flash", "paged"):
-            eng.stats.update(paged_bytes=0.0, paged_launches=0, decode_steps=0, decode_row_steps=0)
-            eng.h.set_option("time_kernel", cls)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); e0.record()
-            one_pass(False, {})
-            e1.record(); torch.cuda.synchronize()
-            k_ms, k_n, k_work = eng.h.timer_read()
-            k_bytes = eng.h.timer_read_bytes()
-            prof[cls] = dict(ms=k_ms, n=k_n, work=k_work, bytes=k_bytes, pass_ms=e0.elapsed_time(e1), paged_bytes=eng.stats["paged_bytes"])
-            eng.h.set_option("time_kernel", "none")
-            log(f"profile {cls}: kernel {k_ms:.0f} ms over {k_n} launches, pass {prof[cls]['pass_ms']:.0f} ms")
+        eng.stats.update(paged_bytes=0.0, paged_launches=0, decode_steps=0, decode_row_steps=0)
+        eng.h.set_option("time_kernel", "all")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        one_pass(False, {})
+        e1.record(); torch.cuda.synchronize()
+        pass_ms = e0.elapsed_time(e1)
+        for cls in ("gemm_tc", "wres", "stream", "gemv", "attn_tc", "flash", "paged", "hift_conv"):
+            prof[cls] = eng.h.timer_read_class(cls)
+            prof[cls]["pass_ms"] = pass_ms
+        prof["paged"]["paged_bytes"] = eng.stats["paged_bytes"]
+        eng.h.set_option("time_kernel", "none")
+        log("profile pass %.0f ms: " % pass_ms + ", ".join(f"{k} {v['ms']:.0f} ms / {v['n']}" for k, v in prof.items()))
 
     # ---- 4a. strong scaling: 256 utterances TOTAL, LPT-sharded (BASELINE config 3 split over the box)
     extra = {}
@@ -465,31 +466,40 @@ def run_engine(args, rank, world, local_rank):
         traffic = json.load(open(tp))
     kroof = {}
     if prof:
-        g = prof["gemm_tc"]
-        kroof["gemm_tc_kernel"] = {
-            "what": "tcgen05 GEMM / implicit-GEMM conv family (T3 projections, CFM, encoder, HiFT convs)", "bound": "tensor",
-            "achieved": g["work"] / 1e12 / (g["ms"] / 1e3) if g["ms"] > 0 else 0.0, "peak": tf_peak, "unit": "TFLOP/s",
-            "algorithmic_flops_per_launch": g["work"] / max(1, g["n"]), "launches": g["n"], "avg_launch_ms": g["ms"] / max(1, g["n"]),
-            "share_of_step": g["ms"] / g["pass_ms"],
-            "hbm_view": {"algorithmic_bytes_per_launch": g["bytes"] / max(1, g["n"]), "achieved": g["bytes"] / 1e9 / (g["ms"] / 1e3) if g["ms"] > 0 else 0.0,
-                         "peak": hbm_peak, "unit": "GB/s"},
-            "note": "algorithmic flops = 2*M*N*K; fp32-faithful operands issue 2x (bf16 hi/lo activations) on the tensor pipe"}
-        f = prof["flash"]
-        kroof["attn_tc_kernel"] = {
-            "what": "tcgen05 flash attention of the CFM estimator blocks", "bound": "tensor",
-            "achieved": f["work"] / 1e12 / (f["ms"] / 1e3) if f["ms"] > 0 else 0.0, "peak": tf_peak, "unit": "TFLOP/s",
-            "algorithmic_flops_per_launch": f["work"] / max(1, f["n"]), "launches": f["n"], "avg_launch_ms": f["ms"] / max(1, f["n"]),
-            "share_of_step": f["ms"] / f["pass_ms"],
-            "note": "algorithmic flops = 4*64*heads*sum(T^2) (CFM launches; the encoder's mma.sync launches are in the same timer class)"}
-        p = prof["paged"]
-        kroof["paged_bulk_kernel"] = {
-            "what": "T3 decode attention over the paged KV cache (bulk-copy staged, fused RoPE + append)", "bound": "hbm",
-            "achieved": p["paged_bytes"] / 1e9 / (p["ms"] / 1e3) if p["ms"] > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
-            "algorithmic_bytes_per_launch": p["paged_bytes"] / max(1, p["n"]), "launches": p["n"], "avg_launch_ms": p["ms"] / max(1, p["n"]),
-            "share_of_step": p["ms"] / p["pass_ms"]}
-        for k in kroof:
-            kroof[k]["frac"] = kroof[k]["achieved"] / kroof[k]["peak"]
-            kroof[k]["traffic"] = traffic.get(k)
+        def entry(cls, kernel, what, bound, note=None, bytes_override=None):
+            r = prof[cls]
+            if r["n"] == 0:
+                return
+            sec = r["ms"] / 1e3
+            byt = bytes_override if bytes_override is not None else r["bytes"]
+            e = {"what": what, "bound": bound, "launches": r["n"], "avg_launch_ms": r["ms"] / r["n"], "share_of_step": r["ms"] / r["pass_ms"],
+                 "algorithmic_flops_per_launch": r["work"] / r["n"], "algorithmic_bytes_per_launch": byt / r["n"],
+                 "tflops": r["work"] / 1e12 / sec if sec > 0 else 0.0, "gbytes_per_s": byt / 1e9 / sec if sec > 0 else 0.0}
+            if bound == "hbm":
+                e.update(achieved=e["gbytes_per_s"], peak=hbm_peak, unit="GB/s")
+            else:
+                e.update(achieved=e["tflops"], peak=tf_peak, unit="TFLOP/s")
+            e["frac"] = e["achieved"] / e["peak"]
+            tr = traffic.get(kernel)
+            e["traffic"] = tr["dram_bytes_per_launch"] if tr else None       # dram__bytes_read + write per launch (ncu --set full)
+            if tr:
+                e["traffic_note"] = f"ncu capture {tr['from']} (profiles/), taken at the capture's own launch shape"
+            if note:
+                e["note"] = note
+            kroof[kernel] = e
+        entry("gemm_tc", "gemm_tc_kernel", "tcgen05 GEMM / implicit-GEMM conv, one tile per CTA (CFM convs + ff2, encoder, T3 prefill, HiFT pre/up/post convs)", "tensor",
+              "algorithmic flops = 2*M*N*K; bf16 hi/lo operands issue 2x on the tensor pipe")
+        entry("wres", "gemm_wres_kernel", "weight-resident persistent GEMM of the CFM block projections (K <= 512), TMA-store epilogue", "hbm",
+              "K = 256: 95 FLOP/B, below the ridge (222 FLOP/B): HBM-bound by its activations")
+        entry("stream", "gemm_stream_kernel", "persistent GEMM of the T3 decode-step projections (weights streamed once per step)", "hbm")
+        entry("gemv", "gemv_kernel", "weight-streaming GEMV (<= 8 rows)", "hbm")
+        entry("attn_tc", "attn_otm2_kernel", "tcgen05 flash attention of the CFM estimator blocks (fp16 operands, P and O in TMEM)", "tensor",
+              "algorithmic flops = 4*64*heads*sum(T^2); head dim 64: 8192 ex2 per 128x64 block = 512 MUFU clocks against 256 MMA clocks -> <= ~50 % of the tensor peak")
+        entry("flash", "flash_attn_kernel", "mma.sync flash attention (conformer encoder with rel-pos bias, T3 prefill)", "tensor", "legacy path; time share only")
+        entry("paged", "paged_bulk_kernel", "T3 decode attention over the paged KV cache (bulk-copy staged, fused RoPE + append)", "hbm",
+              bytes_override=prof["paged"]["paged_bytes"])
+        entry("hift_conv", "hift_conv_kernel", "HiFT ResBlock convolutions (persistent, row-shifted UMMA descriptors)", "tensor",
+              "algorithmic flops = 2*rows*C*k*C; bf16 hi/lo operands issue 2x")
         dom = max(kroof, key=lambda k: kroof[k]["share_of_step"])
         roofline = dict(kernel=dom, **{k: v for k, v in kroof[dom].items() if k != "what"})
         roofline["measured_in"] = "separate profiling pass after the timed region (CUDA events per launch on the launching stream)"

@@ -48,6 +48,7 @@ SYMBOLS = {
     "cbx_launch_count": (C.c_longlong, [_P]),
     "cbx_timer_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     "cbx_timer_read_bytes": (_I, [_P, C.POINTER(C.c_double)]),
+    "cbx_timer_read_class": (_I, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cbx_load_tensor": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(C.c_int64)]),
     "cbx_finalize_weights": (_I, [_P, C.c_char_p]),
     "cbx_t3_cond_encode": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _S, _P]),
@@ -118,6 +119,12 @@ class Handle:
         ms, n, w = C.c_double(0), C.c_longlong(0), C.c_double(0)
         self.call("cbx_timer_read", C.byref(ms), C.byref(n), C.byref(w))
         return float(ms.value), int(n.value), float(w.value)
+
+    def timer_read_class(self, cls):
+        """-> dict(ms, n, work, bytes) of one kernel class after set_option('time_kernel', 'all' | cls)."""
+        ms, n, w, b = C.c_double(0), C.c_longlong(0), C.c_double(0), C.c_double(0)
+        self.call("cbx_timer_read_class", cls.encode(), C.byref(ms), C.byref(n), C.byref(w), C.byref(b))
+        return dict(ms=float(ms.value), n=int(n.value), work=float(w.value), bytes=float(b.value))
 
     def timer_read_bytes(self):
         b = C.c_double(0)

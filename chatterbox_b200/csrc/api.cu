@@ -123,8 +123,9 @@ int cbx_set_option(cbx_handle* h, const char* key, const char* value) {
   else if (k == "attn_prec") h->attn_f16 = (v == "fp16") ? 1 : 0;     // CFM attention operand format (default bf16x3)
   else if (k == "cfm_act") h->cfm_act_f16 = (v == "fp16") ? 1 : 0;   // CFM transformer-block GEMM inputs (default bf16x2)
   else if (k == "time_kernel") {
-    h->timer.drain(); h->timer.ms = 0.0; h->timer.n = 0; h->timer.work = 0.0; h->timer.bytes = 0.0;
-    h->timer.cls = v == "gemm_tc" ? K_GEMM_TC : v == "gemv" ? K_GEMV : v == "flash" ? K_FLASH : v == "paged" ? K_PAGED : K_NONE;
+    h->timer.reset();
+    h->timer.cls = v == "gemm_tc" ? K_GEMM_TC : v == "gemv" ? K_GEMV : v == "flash" ? K_FLASH : v == "paged" ? K_PAGED : v == "wres" ? K_WRES :
+                   v == "stream" ? K_STREAM : v == "attn_tc" ? K_ATTN_TC : v == "hift_conv" ? K_HIFT_CONV : v == "all" ? K_ALL : K_NONE;
   }
   else { h->err = "unknown option " + k; return CBX_ERR_INVALID; }
   return CBX_OK;
@@ -135,15 +136,28 @@ long long cbx_launch_count(cbx_handle* h) { return h ? h->launches : 0; }
 int cbx_timer_read(cbx_handle* h, double* ms, long long* launches, double* work) {
   if (!h || !ms || !launches) return CBX_ERR_INVALID;
   h->timer.drain();
-  *ms = h->timer.ms; *launches = h->timer.n;
-  if (work) *work = h->timer.work;
+  *ms = h->timer.ms(); *launches = h->timer.n();
+  if (work) *work = h->timer.work();
   return CBX_OK;
 }
 
 int cbx_timer_read_bytes(cbx_handle* h, double* bytes) {
   if (!h || !bytes) return CBX_ERR_INVALID;
   h->timer.drain();
-  *bytes = h->timer.bytes;
+  *bytes = h->timer.bytes();
+  return CBX_OK;
+}
+
+int cbx_timer_read_class(cbx_handle* h, const char* cls, double* ms, long long* launches, double* work, double* bytes) {
+  if (!h || !cls || !ms || !launches) return CBX_ERR_INVALID;
+  const std::string v = cls;
+  const int c = v == "gemm_tc" ? K_GEMM_TC : v == "gemv" ? K_GEMV : v == "flash" ? K_FLASH : v == "paged" ? K_PAGED : v == "wres" ? K_WRES :
+                v == "stream" ? K_STREAM : v == "attn_tc" ? K_ATTN_TC : v == "hift_conv" ? K_HIFT_CONV : K_NONE;
+  if (c == K_NONE) return CBX_ERR_INVALID;
+  h->timer.drain();
+  *ms = h->timer.ms_c[c]; *launches = h->timer.n_c[c];
+  if (work) *work = h->timer.work_c[c];
+  if (bytes) *bytes = h->timer.bytes_c[c];
   return CBX_OK;
 }
 

@@ -101,12 +101,95 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx,
     else if (yhi) { __nv_bfloat16 h, l; split_bf16(v, h, l); hr[i] = h; lr[i] = l; } else yr[i] = v;
   }
 }
+// Register-resident variant for dim = 128 * CH (256 / 512): the row is read ONCE (one 16-byte load per lane and 128-column
+// chunk), mean and variance come from the registers with the same two-pass arithmetic, and the result leaves as 16-byte
+// (fp32), 8-byte (fp16 plane) or 2 x 8-byte (bf16 hi/lo planes) stores.  Same operation order per element as layernorm_kernel.
+template <int CH>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* x, int ldx, const float* w, const float* b, float* y,
+                                                            int ldy, int rows, float eps, int act, float out_scale,
+                                                            const float* seq_add, int seq_add_ld, int has_seq, SeqMap seq,
+                                                            __nv_bfloat16* yhi, __nv_bfloat16* ylo, __half* y16) {
+  constexpr int dim = CH * 128;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  int s = 0; bool valid = true;
+  if (has_seq) {
+    s = seq.tile_seq[r / kTileM];
+    valid = (s >= 0) && (r - seq.out_start[s] < seq.out_len[s]);
+  }
+  float v[CH][4];
+  if (valid) {
+    const float* xr = x + (long)r * ldx;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { const float4 t = *reinterpret_cast<const float4*>(xr + c * 128 + lane * 4); v[c][0] = t.x; v[c][1] = t.y; v[c][2] = t.z; v[c][3] = t.w; }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sum += v[c][e];
+    const float mean = warp_sum(sum) / dim;
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float d = v[c][e] - mean; var += d * d; }
+    const float inv = rsqrtf(warp_sum(var) / dim + eps);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i0 = c * 128 + lane * 4;
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + i0)), bv = __ldg(reinterpret_cast<const float4*>(b + i0));
+      const float ww[4] = {wv.x, wv.y, wv.z, wv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float t = (v[c][e] - mean) * inv * ww[e] + bb[e];
+        t = act_apply(act, t, 0.f);
+        if (seq_add) t += seq_add[(long)s * seq_add_ld + i0 + e];
+        v[c][e] = t * out_scale;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[c][e] = 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const long o = (long)r * ldy + c * 128 + lane * 4;
+    if (y16) {
+      const __half2 h0 = __floats2half2_rn(v[c][0], v[c][1]), h1 = __floats2half2_rn(v[c][2], v[c][3]);
+      *reinterpret_cast<uint2*>(y16 + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    } else if (yhi) {
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_bf16(v[c][e], h[e], l[e]);
+      *reinterpret_cast<uint2*>(yhi + o) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+      *reinterpret_cast<uint2*>(ylo + o) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+    } else {
+      *reinterpret_cast<float4*>(y + o) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+    }
+  }
+}
+
 void layernorm(Ctx& ctx, const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int dim,
                float eps, int act, float out_scale, const float* seq_add, int seq_add_ld, const SeqMap* seq,
                __nv_bfloat16* yhi, __nv_bfloat16* ylo, __half* y16) {
   if (ctx.dry || rows == 0) return;
   ctx.launches++;
   SeqMap sm; if (seq) sm = *seq;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const void* outp = y16 ? (const void*)y16 : yhi ? (const void*)yhi : (const void*)y;
+  const bool vec_ok = (dim == 256 || dim == 512) && (ldx % 4) == 0 && (ldy % 4) == 0 && al16(x) && al16(w) && al16(b) && al16(outp) &&
+                      (!yhi || al16(ylo));
+  if (vec_ok) {
+    if (dim == 256) layernorm_vec_kernel<2><<<(rows + 7) / 8, 256, 0, ctx.stream>>>(x, ldx, w, b, y, ldy, rows, eps, act, out_scale, seq_add, seq_add_ld,
+                                                                                   seq ? 1 : 0, sm, yhi, ylo, y16);
+    else layernorm_vec_kernel<4><<<(rows + 7) / 8, 256, 0, ctx.stream>>>(x, ldx, w, b, y, ldy, rows, eps, act, out_scale, seq_add, seq_add_ld,
+                                                                         seq ? 1 : 0, sm, yhi, ylo, y16);
+    CBX_CHECK(cudaGetLastError());
+    return;
+  }
   layernorm_kernel<<<(rows + 7) / 8, 256, 0, ctx.stream>>>(x, ldx, w, b, y, ldy, rows, dim, eps, act, out_scale, seq_add,
                                                           seq_add_ld, seq ? 1 : 0, sm, yhi, ylo, y16);
   CBX_CHECK(cudaGetLastError());

@@ -191,10 +191,14 @@ __device__ __forceinline__ void store_row_hilo(__nv_bfloat16* dh, __nv_bfloat16*
 }
 
 // epilogue of one warp's quarter (32 rows) x column half of the tile; Cz = C + split offset
+// stg / tmC (optional, g.epi_direct bit 3): fp32 rows leave through a per-warp 32-row x 128-byte staging tile (SWIZZLE_128B,
+// 1024-byte aligned) and ONE bulk tensor store per 32-column group -- whole 128-byte lines per request; the tensor map
+// clips rows >= M and columns >= n_out.
 template <int BN>
 __device__ __forceinline__ void epilogue_direct(const GemmDev& g, float* Cz, uint32_t tmem_base, int m0, int n0, int q, int half,
-                                                int lane, bool row_valid) {
+                                                int lane, bool row_valid, uint8_t* stg = nullptr, const CUtensorMap* tmC = nullptr) {
   const int row = m0 + q * 32 + lane;
+  const bool tma_out = stg != nullptr && (g.epi_direct & 8) != 0;
   const bool row_ok = row < g.M;
   const bool wide_c = (g.epi_direct & 2) != 0, wide_r = (g.epi_direct & 4) != 0;
 #pragma unroll 1
@@ -270,18 +274,34 @@ __device__ __forceinline__ void epilogue_direct(const GemmDev& g, float* Cz, uin
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) { v[j] = (v[j] + rres[j]) * g.out_scale; if (!row_valid) v[j] = 0.f; }
-    if (row_ok) {
+    if (tma_out) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous group has left the staging tile
+      __syncwarp();
+      const uint32_t srow = smem_u32(stg) + (uint32_t)lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((uint32_t)(j ^ (lane & 7)) << 4)), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                     "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(tmC), "r"(smem_u32(stg)), "r"(n), "r"(m0 + q * 32) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else if (row_ok) {
       if (g.Chi && g.c_half) store_row_f16<32>(reinterpret_cast<__half*>(g.Chi) + (long)row * g.ldcb + n, v, nvalid);
       else if (g.Chi) store_row_hilo<32>(g.Chi + (long)row * g.ldcb + n, g.Clo + (long)row * g.ldcb + n, v, nvalid);
       else store_row_f32<32>(Cz + (long)row * g.ldc + n, v, nvalid, wide_c);
     }
   }
+  if (tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused / released
 }
 
 template <int BN, int DUAL>
 __global__ void __launch_bounds__(TC_THREADS, DUAL ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA,
-               const __grid_constant__ CUtensorMap tmapA2, const GemmDev g) {
+               const __grid_constant__ CUtensorMap tmapA2, const __grid_constant__ CUtensorMap tmapC, const GemmDev g) {
   using Cfg = TcCfg<BN, DUAL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -428,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     const int myvalid = (er.valid && row_own < g.M) ? 1 : 0;
     float* st = reinterpret_cast<float*>(smem + warp * (32 * 33 * 4));   // pipeline buffers are idle now
     const int rows_here = min(32, g.M - (m0 + q * 32));
-    if (g.epi_direct) epilogue_direct<BN>(g, Cz, tmem_base, m0, n0, q, half, lane, myvalid != 0);
+    if (g.epi_direct) epilogue_direct<BN>(g, Cz, tmem_base, m0, n0, q, half, lane, myvalid != 0, smem + warp * 4096, &tmapC);   // pipeline buffers are idle now
     else
 #pragma unroll 1
     for (int cc = 0; cc < BN / 2; cc += 32) {
@@ -674,8 +694,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
 //   warp 0: TMA producer   warp 1: MMA issuer (+ TMEM owner)   warps 2-9: epilogue (lane quarter = warp % 4, column half = (warp-2)/4)
 // Algorithmic HBM bytes per launch: M*K*2 (A) + N*K*2 (W, once) + outputs (+ residual).
 // ================================================================================================
-constexpr int WR_THREADS = 320, WR_STAGES = 4, WR_W_BYTES = 131072, WR_A_STAGE = 16384;
-constexpr int WR_SMEM = WR_W_BYTES + WR_STAGES * WR_A_STAGE + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int WR_THREADS = 320, WR_STAGES = 3, WR_W_BYTES = 131072, WR_A_STAGE = 16384;
+constexpr int WR_STG = 8 * 4096;        // per epilogue warp: one 32-row x 128-byte staging tile of the TMA-store epilogue
+constexpr int WR_SMEM = WR_W_BYTES + WR_STAGES * WR_A_STAGE + WR_STG + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
 
 __host__ __device__ constexpr uint32_t umma_idesc_f16f16(int M, int N) {       // fp16 x fp16 -> f32, K-major A and B
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -687,13 +708,14 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 template <int BN>
 __global__ void __launch_bounds__(WR_THREADS, 1)
-gemm_wres_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA, const GemmDev g,
-                 const int n_mtiles, const int n_panels) {
+gemm_wres_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapA,
+                 const __grid_constant__ CUtensorMap tmapC, const GemmDev g, const int n_mtiles, const int n_panels) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem;                                   // [KB][BN rows x 128 B]  (SWIZZLE_128B)
   uint8_t* sA = smem + WR_W_BYTES;                      // [WR_STAGES][128 rows x 128 B]
-  float* sBias = reinterpret_cast<float*>(sA + WR_STAGES * WR_A_STAGE);   // [BN]
+  uint8_t* sStg = sA + WR_STAGES * WR_A_STAGE;          // [8 epilogue warps][32 rows x 128 B], SWIZZLE_128B (1024-byte aligned)
+  float* sBias = reinterpret_cast<float*>(sStg + WR_STG);   // [BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + 1024);
   uint64_t* w_full = bars;                  // 1
   uint64_t* a_full = bars + 1;              // [WR_STAGES]
@@ -714,7 +736,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constan
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmapW); tma_prefetch_desc(&tmapA); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmapW); tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapC); }
   for (int i = threadIdx.x; i < BN; i += WR_THREADS) sBias[i] = (g.bias && n0 + i < g.Npad) ? g.bias[n0 + i] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
@@ -763,9 +785,16 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constan
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global (one 32-column row segment per thread and trip) ====
+    // ===================== epilogue: TMEM -> registers -> swizzled staging tile -> TMA store ======================
+    // One thread = one output row.  Its 128-byte groups (64 fp16 or 32 fp32 columns) go through a per-warp 32 x 128 B
+    // staging tile and leave as ONE bulk tensor store: whole 128-byte lines reach L2, instead of 32 scattered 16-byte
+    // pieces per store instruction (session 12: the K = 256 projections ran at ~1.9 TB/s, bound by the L2 request rate of
+    // those partial-sector stores, not by HBM or the tensor pipe).  Rows beyond M are clipped by the tensor map.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    uint8_t* stg = sStg + (warp - 2) * 4096;
+    const uint32_t stg_row = smem_u32(stg) + (uint32_t)lane * 128;
+    const bool out16 = g.Chi != nullptr;                  // one fp16 plane (c_half), else fp32 (+ residual)
     int it = 0;
     for (int mt = mt0; mt < n_mtiles; mt += mt_step, ++it) {
       const int buf = it & 1;
@@ -780,9 +809,14 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constan
         if (n >= g.n_out) break;
         float rres[32];
         if (g.res && row_ok) {
-          const float4* rp = reinterpret_cast<const float4*>(g.res + (long)row * g.ldr + n);
+          const float* rp = g.res + (long)row * g.ldr + n;
+          if (g.epi_direct & 4) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 t = rp[j]; rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w; }
+            for (int j = 0; j < 32; j += 8) ldg256(rp + j, rres + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 t = reinterpret_cast<const float4*>(rp)[j]; rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w; }
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) rres[j] = 0.f;
@@ -797,19 +831,37 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
         }
-        if (row_ok) {
-          if (g.Chi) {           // one fp16 plane (c_half)
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(g.Chi) + (long)row * g.ldcb + n);
+        // staging: 16-byte unit u of the row lands at unit (u ^ (row & 7)) of its 128-byte line (SWIZZLE_128B)
+        const bool first = out16 ? ((cc & 32) == 0) : true;      // fp16: two 32-column chunks share one 128-byte group
+        if (first) {                                             // the previous store has finished reading the staging tile
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
+        if (out16) {
+          const int u0 = (cc & 32) ? 4 : 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
-                                  pack_h2(v[8 * j + 4], v[8 * j + 5]), pack_h2(v[8 * j + 6], v[8 * j + 7]));
-          } else {
-            float4* dst = reinterpret_cast<float4*>(g.C + (long)row * g.ldc + n);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t a = stg_row + ((uint32_t)((u0 + j) ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_h2(v[8 * j], v[8 * j + 1])), "r"(pack_h2(v[8 * j + 2], v[8 * j + 3])),
+                         "r"(pack_h2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_h2(v[8 * j + 6], v[8 * j + 7])) : "memory");
+          }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j] = make_float4((v[4 * j] + rres[4 * j]) * g.out_scale, (v[4 * j + 1] + rres[4 * j + 1]) * g.out_scale,
-                                   (v[4 * j + 2] + rres[4 * j + 2]) * g.out_scale, (v[4 * j + 3] + rres[4 * j + 3]) * g.out_scale);
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = stg_row + ((uint32_t)(j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"((v[4 * j] + rres[4 * j]) * g.out_scale), "f"((v[4 * j + 1] + rres[4 * j + 1]) * g.out_scale),
+                         "f"((v[4 * j + 2] + rres[4 * j + 2]) * g.out_scale), "f"((v[4 * j + 3] + rres[4 * j + 3]) * g.out_scale) : "memory");
+          }
+        }
+        const bool last = out16 ? ((cc & 32) != 0) : true;
+        if (last) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int c0 = out16 ? (n - 32) : n;                 // first column of the 128-byte group
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&tmapC), "r"(smem_u32(stg)), "r"(c0), "r"(mt * TC_BM + q * 32) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
       }
@@ -817,6 +869,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the stores have left shared memory and completed
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -871,8 +924,10 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                                 // (decode step) the producer of A / m_live has completed
   pdl_launch_dependents();
+  // Only the TMA producer waits for the preceding kernel (griddepcontrol.wait, below): everything the other warps touch is
+  // downstream of its A loads.  m_live is read before that wait on purpose -- it is written by the step's first kernel
+  // (t3_compact) and every projection sits at least two launches later, so the writer completed before our predecessor started.
   // work list: live row tiles x column tiles x K splits, row tile fastest
   const int m_rows = g.m_live ? min(*g.m_live, g.M) : g.M;
   const int n_mt = (m_rows + TC_BM - 1) / TC_BM;
@@ -893,17 +948,36 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_const
     // ===================== TMA producer =================================================================
     if (lane == 0) {
       uint32_t gi = 0;
+      // The weights do not depend on the previous kernel: the W tiles of the first item's first stages are already in flight
+      // (HBM latency, ~1.5 us) while that kernel drains; the A tiles of the same stages follow the wait.
+      int pre = 0;
+      if ((int)blockIdx.x < n_items) {
+        int m0, n0, kb0, KB, ks;
+        item(blockIdx.x, m0, n0, kb0, KB, ks);
+        pre = KB < STAGES ? KB : STAGES;
+        for (int kb = 0; kb < pre; ++kb) {
+          mbar_arrive_expect_tx(&full[kb], Cfg::STAGE_BYTES);
+          tma_load_2d(smem + kb * Cfg::STAGE_BYTES + 16384, &tmapW, &full[kb], (kb0 + kb) * TC_BK, n0);
+        }
+      }
+      pdl_wait();                               // the producer of A has completed
+      bool first = true;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         int m0, n0, kb0, KB, ks;
         item(it, m0, n0, kb0, KB, ks);
         for (int kb = 0; kb < KB; ++kb, ++gi) {
           const int s = gi % STAGES;
-          mbar_wait(&empty[s], ((gi / STAGES) & 1) ^ 1);
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          if (first && kb < pre) {               // W already requested, barrier already armed
+            tma_load_2d(st, &tmapA, &full[s], (kb0 + kb) * TC_BK, m0);
+            continue;
+          }
+          mbar_wait(&empty[s], ((gi / STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
           tma_load_2d(st, &tmapA, &full[s], (kb0 + kb) * TC_BK, m0);
           tma_load_2d(st + 16384, &tmapW, &full[s], (kb0 + kb) * TC_BK, n0);
         }
+        first = false;
       }
     }
   } else if (warp == 1) {
@@ -1347,8 +1421,8 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
   }
   set_epi_direct(g);
   dim3 grid((g.Npad + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM, g.splitk);
-  if (ctx.timer && ctx.timer->cls == K_GEMM_TC) {
-    ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
+  if (ctx.timer && ctx.timer->on(K_GEMM_TC)) {
+    const double flops = 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
     // algorithmic HBM bytes: weights once (bf16), the activation matrix once (fp32 or hi+lo planes = 4 B per element),
     // every output element once per destination, the residual once
     const double a_rows = (g.a_mode == A_TAPS && g.ntaps > 1) ? (double)g.M_in : (double)g.M * g.stride;
@@ -1359,11 +1433,24 @@ template <int BN, int DUAL> static void launch_tc(Ctx& ctx, GemmDev g, const Wei
     if (g.C2) b += out_elems * 4.0;
     if (g.res) b += out_elems * 4.0;
     if (g.accumulate) b += out_elems * 4.0;
-    ctx.timer->bytes += b;
+    ctx.timer->add(K_GEMM_TC, flops, b);
+  }
+  // fp32 result of a full-K launch: TMA-store epilogue (32-row x 128-byte boxes)
+  CUtensorMap tmC = tmA;
+  static const bool tma_store_on = !(getenv("CBX_TMA_STORE") && atoi(getenv("CBX_TMA_STORE")) == 0);
+  if (tma_store_on && (g.epi_direct & 1) && g.C && !g.Chi && !g.swiglu && g.splitk == 1 && (g.ldc % 4) == 0 && g.M >= 4 * TC_BM) {
+    PFN_encodeTiled enc = get_encode_fn();
+    cuuint64_t dims[2] = {(cuuint64_t)g.n_out, (cuuint64_t)g.M};
+    cuuint64_t strides[1] = {(cuuint64_t)g.ldc * 4};
+    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)g.C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) g.epi_direct |= 8;
   }
   if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
   launch_kernel(ctx, gemm_tc_kernel<BN, DUAL>, grid, dim3(TC_THREADS), (size_t)TcCfg<BN, DUAL>::SMEM,
-                g.A16 ? W.tmap16[tmap_idx] : W.tmap[tmap_idx], tmA, tmA2, g);
+                g.A16 ? W.tmap16[tmap_idx] : W.tmap[tmap_idx], tmA, tmA2, tmC, g);
   if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
 }
 
@@ -1378,15 +1465,29 @@ template <int BN> static void launch_wres(Ctx& ctx, GemmDev g, const Weight& W) 
   int groups = n_sm / n_panels;                         // row-tile groups: every CTA of a group owns one weight panel
   if (groups > n_mtiles) groups = n_mtiles;
   if (groups < 1) groups = 1;
-  if (ctx.timer && ctx.timer->cls == K_GEMM_TC) {
-    ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
+  if (ctx.timer && ctx.timer->on(K_WRES)) {
     double b = (double)g.Npad * g.Kpad * 2.0 + (double)g.M * g.k_total * 2.0 + (double)g.M * g.n_out * (g.Chi ? 2.0 : 4.0);
     if (g.res) b += (double)g.M * g.n_out * 4.0;
-    ctx.timer->bytes += b;
+    ctx.timer->add(K_WRES, 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total, b);
   }
-  if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
-  gemm_wres_kernel<BN><<<groups * n_panels, WR_THREADS, WR_SMEM, ctx.stream>>>(W.tmap16[BN == 256 ? 2 : 1], tmA, g, n_mtiles, n_panels);
-  if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
+  // output map of the TMA-store epilogue: 32-row x 128-byte boxes (64 fp16 or 32 fp32 columns), SWIZZLE_128B
+  CUtensorMap tmC;
+  {
+    PFN_encodeTiled enc = get_encode_fn();
+    const bool h16 = g.Chi != nullptr;
+    cuuint64_t dims[2] = {(cuuint64_t)g.n_out, (cuuint64_t)g.M};
+    cuuint64_t strides[1] = {h16 ? (cuuint64_t)g.ldcb * 2 : (cuuint64_t)g.ldc * 4};
+    cuuint32_t box[2] = {h16 ? 64u : 32u, 32u};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmC, h16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h16 ? (void*)g.Chi : (void*)g.C, dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cbx: cuTensorMapEncodeTiled (C store) failed");
+  }
+  set_epi_direct(g);       // (only the residual-load width bit is used by this kernel)
+  if (ctx.timer) ctx.timer->begin(K_WRES, ctx.stream);
+  gemm_wres_kernel<BN><<<groups * n_panels, WR_THREADS, WR_SMEM, ctx.stream>>>(W.tmap16[BN == 256 ? 2 : 1], tmA, tmC, g, n_mtiles, n_panels);
+  if (ctx.timer) ctx.timer->end(K_WRES, ctx.stream);
 }
 
 // persistent streaming kernel for the decode-step projections: eligible launches (see gemm())
@@ -1398,19 +1499,18 @@ template <int BN> static void launch_stream(Ctx& ctx, GemmDev g, const Weight& W
   if (g.splitk < 1) g.splitk = 1;
   const int n_ntiles = (g.Npad + BN - 1) / BN;
   const int n_items = ((g.M + TC_BM - 1) / TC_BM) * n_ntiles * g.splitk;
-  if (ctx.timer && ctx.timer->cls == K_GEMM_TC) {
-    ctx.timer->work += 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total;
+  if (ctx.timer && ctx.timer->on(K_STREAM)) {
     const double out_elems = (double)g.M * (double)(g.swiglu ? g.n_out / 2 : g.n_out);
     double b = (double)g.Npad * g.Kpad * 2.0 + (double)g.M * g.k_total * 2.0;
     if (g.C) b += out_elems * 4.0 * g.splitk;
     if (g.Chi) b += out_elems * (g.c_half ? 2.0 : 4.0);
     if (g.res) b += out_elems * 4.0;
-    ctx.timer->bytes += b;
+    ctx.timer->add(K_STREAM, 2.0 * (double)g.M * (double)g.n_out * (double)g.k_total, b);
   }
-  if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
+  if (ctx.timer) ctx.timer->begin(K_STREAM, ctx.stream);
   launch_kernel(ctx, gemm_stream_kernel<BN>, dim3(n_items < n_sm ? n_items : n_sm), dim3(WR_THREADS), (size_t)StreamCfg<BN>::SMEM,
                 W.tmap16[BN == 64 ? 0 : (BN == 128 ? 1 : 2)], tmA, g, n_ntiles);
-  if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
+  if (ctx.timer) ctx.timer->end(K_STREAM, ctx.stream);
 }
 
 template <int R> static void launch_gemv(Ctx& ctx, const GemmDev& g) {
@@ -1442,7 +1542,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
     const bool wres_epi = !g.swiglu && !g.C2 && !g.accumulate && (g.act == ACT_NONE || g.act == ACT_GELU) && !g.act_vec &&
                           ((g.Chi && g.c_half && !g.C && !g.res) || (g.C && !g.Chi)) &&
                           (!g.C || ((g.ldc % 4) == 0 && (g.n_out % 32) == 0 && (!g.res || (g.ldr % 4) == 0))) &&
-                          (!g.Chi || ((g.ldcb % 8) == 0 && (g.n_out % 32) == 0));
+                          (!g.Chi || ((g.ldcb % 8) == 0 && (g.n_out % 64) == 0));      // TMA-store groups: 64 fp16 / 32 fp32 columns
     if (wres_on && g.A16 && W.w16 && !g.has_seq && g.ntaps == 1 && g.splitk <= 1 && wres_epi && g.M >= 4 * TC_BM) {
       if (g.Kpad == 256 && g.Npad % 256 == 0) { launch_wres<256>(ctx, g, W); CBX_CHECK(cudaGetLastError()); return; }
       if (g.Kpad == 512 && g.Npad % 128 == 0) { launch_wres<128>(ctx, g, W); CBX_CHECK(cudaGetLastError()); return; }

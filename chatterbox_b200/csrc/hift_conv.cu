@@ -293,15 +293,13 @@ void hift_conv(Ctx& ctx, const Weight& W, int C, int k, int dil, const cbx_layou
   make_plane_tmap(&tmLo, in_lo, L.rows, C, p.rin, C);
   const int grid = p.n_tiles < n_sm ? p.n_tiles : n_sm;
   ctx.launches++;
-  if (ctx.timer && ctx.timer->cls == K_GEMM_TC) {
-    ctx.timer->work += 2.0 * (double)L.rows * C * (double)(k * C);
-    ctx.timer->bytes += (double)L.rows * C * 4.0 + (double)k * C * C * 2.0 + (double)L.rows * C * 4.0 * ((out ? 1 : 0) + (out_hi ? 1 : 0) + (res ? 1 : 0));
-  }
-  if (ctx.timer) ctx.timer->begin(K_GEMM_TC, ctx.stream);
+  if (ctx.timer) ctx.timer->add(K_HIFT_CONV, 2.0 * (double)L.rows * C * (double)(k * C),
+                                (double)L.rows * C * 4.0 + (double)k * C * C * 2.0 + (double)L.rows * C * 4.0 * ((out ? 1 : 0) + (out_hi ? 1 : 0) + (res ? 1 : 0)));
+  if (ctx.timer) ctx.timer->begin(K_HIFT_CONV, ctx.stream);
   if (C == 64) hift_conv_kernel<64><<<grid, HC_THREADS, HC_SMEM, ctx.stream>>>(tmHi, tmLo, W.tmap[0], p);
   else if (C == 128) hift_conv_kernel<128><<<grid, HC_THREADS, HC_SMEM, ctx.stream>>>(tmHi, tmLo, W.tmap[1], p);
   else hift_conv_kernel<256><<<grid, HC_THREADS, HC_SMEM, ctx.stream>>>(tmHi, tmLo, W.tmap[2], p);
-  if (ctx.timer) ctx.timer->end(K_GEMM_TC, ctx.stream);
+  if (ctx.timer) ctx.timer->end(K_HIFT_CONV, ctx.stream);
   CBX_CHECK(cudaGetLastError());
 }
 

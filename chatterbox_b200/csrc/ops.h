@@ -81,7 +81,7 @@ struct GemmDev {
   // GEMV path only (<= 8 rows, B=1 latency): A is the RAW residual stream and the kernel applies the row norm itself
   // (RMSNorm: norm_w * (x * rsqrt(mean x^2 + eps)); LayerNorm when norm_ln) -- one launch less per projection
   const float* norm_w; const float* norm_b; int norm_ln; float norm_eps;
-  int epi_direct;           // set by the launcher: bit 0 = register-direct epilogue, bit 1 = 32-byte C stores, bit 2 = 32-byte residual loads
+  int epi_direct;           // set by the launcher: bit 0 = register-direct epilogue, bit 1 = 32-byte C stores, bit 2 = 32-byte residual loads, bit 3 = TMA-store of fp32 rows
 };
 
 struct Arena {  // bump allocator over caller-owned workspace; dry=true only counts
@@ -102,31 +102,43 @@ struct Arena {  // bump allocator over caller-owned workspace; dry=true only cou
 };
 
 // Optional CUDA-event timer around one class of kernel launches (bench.py roofline: events on the launching stream).
-enum KClass : int { K_NONE = 0, K_GEMM_TC = 1, K_GEMV = 2, K_FLASH = 3, K_PAGED = 4 };
+enum KClass : int { K_NONE = 0, K_GEMM_TC = 1, K_GEMV = 2, K_FLASH = 3, K_PAGED = 4, K_WRES = 5, K_STREAM = 6, K_ATTN_TC = 7,
+                    K_HIFT_CONV = 8, K_NCLASS = 9, K_ALL = 99 };
+// One class (cbx_set_option "time_kernel" = its name) or every class at once ("all"): each timed launch is bracketed by a
+// pair of events tagged with its class; drain() adds the elapsed times up per class.
 struct KTimer {
   int cls = K_NONE;
   std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+  std::vector<int> tag;          // class of each pair
   size_t used = 0;
-  double ms = 0.0; long long n = 0;
-  double work = 0.0;             // algorithmic work of the timed launches (flops for GEMMs), added by the launcher
-  double bytes = 0.0;            // algorithmic HBM bytes of the timed launches (operands once in, results once out)
+  double ms_c[K_NCLASS] = {}; long long n_c[K_NCLASS] = {};
+  double work_c[K_NCLASS] = {};  // algorithmic work of the timed launches (flops), added by the launcher
+  double bytes_c[K_NCLASS] = {}; // algorithmic HBM bytes of the timed launches (operands once in, results once out)
+  bool on(int c) const { return cls == c || cls == K_ALL; }
+  void add(int c, double work, double bytes) { if (on(c)) { work_c[c] += work; bytes_c[c] += bytes; } }
   void begin(int c, cudaStream_t st) {
-    if (c != cls) return;
+    if (!on(c)) return;
     if (used + 2 > ev.size()) {
       if (ev.size() >= 32768) { drain(); }
-      else { size_t old = ev.size(); ev.resize(old + 2048); for (size_t i = old; i < ev.size(); ++i) cudaEventCreate(&ev[i]); }
+      else { size_t old = ev.size(); ev.resize(old + 2048); tag.resize(ev.size() / 2 + 1); for (size_t i = old; i < ev.size(); ++i) cudaEventCreate(&ev[i]); }
     }
+    tag[used / 2] = c;
     cudaEventRecord(ev[used], st);
   }
-  void end(int c, cudaStream_t st) { if (c != cls) return; cudaEventRecord(ev[used + 1], st); used += 2; }
+  void end(int c, cudaStream_t st) { if (!on(c)) return; cudaEventRecord(ev[used + 1], st); used += 2; }
   void drain() {
     for (size_t i = 0; i + 1 < used; i += 2) {
       cudaEventSynchronize(ev[i + 1]);
       float t = 0.f; cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
-      ms += t; n += 1;
+      ms_c[tag[i / 2]] += t; n_c[tag[i / 2]] += 1;
     }
     used = 0;
   }
+  void reset() { drain(); for (int c = 0; c < K_NCLASS; ++c) { ms_c[c] = 0; n_c[c] = 0; work_c[c] = 0; bytes_c[c] = 0; } }
+  double ms() const { double t = 0; for (int c = 0; c < K_NCLASS; ++c) t += ms_c[c]; return t; }
+  long long n() const { long long t = 0; for (int c = 0; c < K_NCLASS; ++c) t += n_c[c]; return t; }
+  double work() const { double t = 0; for (int c = 0; c < K_NCLASS; ++c) t += work_c[c]; return t; }
+  double bytes() const { double t = 0; for (int c = 0; c < K_NCLASS; ++c) t += bytes_c[c]; return t; }
 };
 
 struct Ctx {

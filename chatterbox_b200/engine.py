@@ -353,16 +353,20 @@ class Engine:
         return out
 
     def _decode_loop(self, st, st_t, B, rp, max_new, ws):
-        """Host side of the decode loop: no blocking device->host read.  The device retires finished utterances every
-        step (t3_compact_kernel); the host only picks the launch capacity from what it knows for sure -- the budgets --
-        and from asynchronous snapshots of the device's live count (pinned memory + event, polled without waiting)."""
+        """Host side of the decode loop: no device->host read on the critical path.  The device retires finished utterances
+        every step (t3_compact_kernel); the host only picks the launch capacity from what it knows for sure -- the budgets --
+        and from asynchronous snapshots of the device's live count (pinned memory + event) taken two calls earlier."""
         budget = np.asarray(max_new, dtype=np.int64)
         total = int(budget.max())
         steps_done, live_seen = 0, B
         pending = []
+        lag = 2        # snapshots are consumed with a FIXED lag of `lag` calls (their copies finished long ago: no stall), never
+                       # by polling: the capacity sequence -- and with it tile / split choices and the rounding of every logit --
+                       # is then a function of the device state alone, not of host timing (run-to-run reproducible ids)
         while steps_done < total:
-            while pending and pending[0][0].query():
+            while len(pending) > lag:
                 ev, buf = pending.pop(0)
+                ev.synchronize()
                 live_seen = min(live_seen, int(buf[0]))
                 self._pinned.append((ev, buf))
             live = min(live_seen, int((budget > steps_done).sum()))

@@ -70,6 +70,9 @@ long long cbx_launch_count(cbx_handle* h);
 int cbx_timer_read(cbx_handle* h, double* ms, long long* launches, double* work);
 /* algorithmic HBM bytes of the same launches (GEMM family: weights, activations and results once each) */
 int cbx_timer_read_bytes(cbx_handle* h, double* bytes);
+/* per-class readout after cbx_set_option(h, "time_kernel", "all" | <class>): classes gemm_tc | wres | stream | gemv | attn_tc |
+ * flash | paged | hift_conv (one CUDA-event pair per launch on the launching stream) */
+int cbx_timer_read_class(cbx_handle* h, const char* cls, double* ms, long long* launches, double* work, double* bytes);
 /* host fp32 tensor with the reference's state-dict name ("t3." / "flow." / "hift." prefix added by the caller) */
 int cbx_load_tensor(cbx_handle* h, const char* name, const float* host_data, int ndim, const int64_t* shape);
 /* pack loaded tensors of one model ("t3" | "flow" | "hift"): bf16 K-major weights + TMA maps, QKV concat,
