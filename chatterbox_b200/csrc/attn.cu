@@ -504,11 +504,16 @@ constexpr int PB_TOK = 32;                    // tokens per page (required by th
 constexpr int PB_THREADS = 160;               // 4 consumer warps + 1 producer warp
 constexpr int PB_OCC = 3;                     // persistent CTAs per SM
 
-template <typename T> constexpr int pb_smem_bytes() { return BulkCfg<T>::NST * 2 * PB_TOK * 64 * (int)sizeof(T) + 256 + 4 * 4 * 18 * 4; }
+// shared memory: [NST stages of (K slab | V slab)] [512 B barriers] [merge buffer 1152 B] [2 x (q | k_new | v_new) 768 B]
+template <typename T> constexpr int pb_smem_bytes() { return BulkCfg<T>::NST * 2 * PB_TOK * 64 * (int)sizeof(T) + 512 + 4 * 4 * 18 * 4 + 2 * 192 * 4; }
 
 // Persistent: gridDim.x CTAs walk the (slot, head, split) work items with a fixed stride.  The producer warp runs ahead
 // of the consumers ACROSS items (the stage ring and its mbarrier phases never reset), so while the consumers merge one
-// row's partial results and set up the next row's query, that row's first pages are already landing in shared memory.
+// row's partial results, the next row's first pages are already landing in shared memory -- and so is its QUERY: the
+// producer warp's 32 lanes fetch the next item's q / k / v (and the RoPE table row) while the current item's pages stream,
+// rotate them, append the new k / v to the cache and leave q (scaled), k_new, v_new in a double-buffered shared-memory
+// slot.  The consumers used to do this themselves at the top of every item behind three dependent global loads
+// (slot -> row -> position -> q, ~1.5 us) -- a fifth of an average item.
 template <typename T>
 __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const PagedDev p, const int n_items) {
   constexpr int NST = BulkCfg<T>::NST;
@@ -518,7 +523,10 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
   extern __shared__ __align__(128) uint8_t pb_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(pb_smem + NST * STAGE);
   uint64_t* empty = full + NST;
-  float* mrg = reinterpret_cast<float*>(pb_smem + NST * STAGE + 256);     // [4 warps][4 subs][18]: m, l, o[16]
+  uint64_t* q_full = empty + NST;                         // [2] query slot staged (1 arrival: the producer warp)
+  uint64_t* q_empty = q_full + 2;                         // [2] query slot consumed (4 arrivals: the consumer warps)
+  float* mrg = reinterpret_cast<float*>(pb_smem + NST * STAGE + 512);     // [4 warps][4 subs][18]: m, l, o[16]
+  float* qs = mrg + 4 * 4 * 18;                           // [2][q 64 | k_new 64 | v_new 64]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.n_heads;
   const int per_slot = H * p.nsplit;
@@ -530,30 +538,81 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
   const T* layer_base = reinterpret_cast<const T*>(p.pages) + (long)p.layer * p.n_pages * page_stride;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 4); }
     fence_mbar_init();
   }
   __syncthreads();
   if (warp == 4) {
-    // ===================== producer warp: bulk copies of every item's pages (split, split + nsplit, ...) =========
-    // All 32 lanes fetch metadata (the page ids of the next 32 pages in one coalesced load, the next item's row / position
-    // while the current item streams); lane 0 alone talks to the barriers and the copy engine, so no page-table load sits
-    // on its critical path between two bulk copies.
+    // ===================== producer warp ==========================================================================
+    // All 32 lanes fetch metadata (the page ids of the next 32 pages in one coalesced load, the next item's row / position /
+    // query while the current item streams); lane 0 alone talks to the copy engine.
+    struct QRaw { float qa, qb, ka, kb, va, vb, c, s; };   // dims lane and lane + 32 of q, k, v; cos / sin of dim lane
+    auto q_fetch = [&](int slot_, int head_, int pos_, QRaw& r) {
+      const float* qp = p.qkv + (long)slot_ * p.ldqkv + head_ * 64;
+      r.qa = qp[lane]; r.qb = qp[lane + 32];
+      r.ka = r.kb = r.va = r.vb = 0.f; r.c = 1.f; r.s = 0.f;
+      if (p.fuse_rope) {
+        const float* kq = qp + H * 64; const float* vq = qp + 2 * H * 64;
+        r.ka = kq[lane]; r.kb = kq[lane + 32]; r.va = vq[lane]; r.vb = vq[lane + 32];
+        r.c = p.cos_t[(long)pos_ * 32 + lane]; r.s = p.sin_t[(long)pos_ * 32 + lane];
+      }
+    };
+    auto q_stage = [&](int li, const QRaw& r, int row_, int head_, int split_, int pos_) {
+      // rotate_half convention (modeling_llama.py:138-167): out = x*cos + rotate_half(x)*sin, products rounded separately like
+      // the reference's elementwise ops (no fused multiply-add)
+      float q0 = r.qa, q1 = r.qb, k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+      if (p.fuse_rope) {
+        q0 = __fadd_rn(__fmul_rn(r.qa, r.c), __fmul_rn(-r.qb, r.s));
+        q1 = __fadd_rn(__fmul_rn(r.qb, r.c), __fmul_rn(r.qa, r.s));
+        k0 = kv_round<T>(__fadd_rn(__fmul_rn(r.ka, r.c), __fmul_rn(-r.kb, r.s)));
+        k1 = kv_round<T>(__fadd_rn(__fmul_rn(r.kb, r.c), __fmul_rn(r.ka, r.s)));
+        v0 = kv_round<T>(r.va); v1 = kv_round<T>(r.vb);
+      }
+      const int b = li & 1;
+      mbar_wait(&q_empty[b], ((li >> 1) & 1) ^ 1);        // the consumers are done with the item that used this slot
+      float* d = qs + b * 192;
+      d[lane] = q0 * p.scale; d[lane + 32] = q1 * p.scale;
+      d[64 + lane] = k0; d[96 + lane] = k1; d[128 + lane] = v0; d[160 + lane] = v1;
+      // the split that owns the new token's page appends it to the cache
+      const int new_pg = pos_ >> 5, new_t = pos_ & 31;
+      if (p.fuse_rope && (new_pg % p.nsplit) == split_) {
+        const int* pt_ = p.page_table + (long)row_ * p.max_pages;
+        T* kd = const_cast<T*>(layer_base) + (long)head_ * slab_e + (long)pt_[new_pg] * page_stride + (long)new_t * 64;
+        T* vd = kd + (long)H * slab_e;
+        kd[lane] = (T)k0; kd[lane + 32] = (T)k1; vd[lane] = (T)v0; vd[lane + 32] = (T)v1;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_full[b]);
+    };
     uint32_t gi = 0;
+    int li = 0;
     int it = blockIdx.x;
     int slot = it < n_items ? it / per_slot : n_live;
     int row = 0, pos = 0;
-    if (slot < n_live) { row = p.slot_row[slot]; pos = p.positions[row]; }
+    if (slot < n_live) {
+      row = p.slot_row[slot]; pos = p.positions[row];
+      const int rem0 = it - slot * per_slot;
+      QRaw r0;
+      q_fetch(slot, rem0 / p.nsplit, pos, r0);
+      q_stage(0, r0, row, rem0 / p.nsplit, rem0 % p.nsplit, pos);
+    }
     while (it < n_items && slot < n_live) {
       const int rem = it - slot * per_slot;
       const int head = rem / p.nsplit, split = rem - head * p.nsplit;
       const int npg = (pos + PB_TOK) / PB_TOK;
       const int* pt = p.page_table + (long)row * p.max_pages;
       const T* base = layer_base + (long)head * slab_e;
-      // next item's metadata: issued now, needed after this item's pages
+      // next item's metadata and query: issued now, needed after this item's pages
       const int it_n = it + gridDim.x;
       const int slot_n = it_n < n_items ? it_n / per_slot : n_live;
-      int row_n = 0, pos_n = 0;
-      if (slot_n < n_live) { row_n = p.slot_row[slot_n]; pos_n = p.positions[row_n]; }
+      int row_n = 0, pos_n = 0, head_n = 0, split_n = 0;
+      QRaw rn;
+      if (slot_n < n_live) {
+        row_n = p.slot_row[slot_n]; pos_n = p.positions[row_n];
+        const int rem_n = it_n - slot_n * per_slot;
+        head_n = rem_n / p.nsplit; split_n = rem_n - head_n * p.nsplit;
+        q_fetch(slot_n, head_n, pos_n, rn);
+      }
       int i = 0;
       for (int pj0 = split; pj0 < npg; pj0 += 32 * p.nsplit) {
         const int pj_l = pj0 + lane * p.nsplit;
@@ -572,6 +631,9 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
           }
         }
       }
+      __syncwarp();
+      ++li;
+      if (slot_n < n_live) q_stage(li, rn, row_n, head_n, split_n, pos_n);
       it = it_n; slot = slot_n; row = row_n; pos = pos_n;
     }
     return;
@@ -580,7 +642,8 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
   const int sub = lane & 3, grp = lane >> 2;              // 4 lanes per token, 8 tokens per warp and page
   const int d0 = sub * DPL;
   uint32_t gi = 0;
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+  int li = 0;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
     const int slot = it / per_slot;
     if (slot >= n_live) break;
     const int rem = it - slot * per_slot;
@@ -589,60 +652,13 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
     const int pos = p.positions[row];
     const int S = pos + 1;
     const int npg = (S + PB_TOK - 1) / PB_TOK;
-    const int* pt = p.page_table + (long)row * p.max_pages;
-    const T* base = layer_base + (long)head * slab_e;
-    float q[DPL], kn[DPL], vn[DPL];
-    {
-      const float* qp = p.qkv + (long)slot * p.ldqkv + head * 64;
-      float4 qa[4];
+    const float* qsl = qs + (li & 1) * 192;
+    mbar_wait(&q_full[li & 1], (li >> 1) & 1);            // q (rotated, scaled), k_new, v_new of this item are staged
+    float q[DPL];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qa[i] = *reinterpret_cast<const float4*>(qp + d0 + 4 * i);
-      if (p.fuse_rope) {
-        // rotate_half convention (modeling_llama.py:138-167): out = x*cos + rotate_half(x)*sin, products rounded
-        // separately like the reference's elementwise ops (no fused multiply-add)
-        const float* kq = qp + H * 64;
-        const float* vq = qp + 2 * H * 64;
-        const int pd0 = d0 < 32 ? d0 + 32 : d0 - 32;
-        const float sgn = d0 < 32 ? -1.f : 1.f;
-        const float* ct = p.cos_t + (long)pos * 32 + (d0 & 31);
-        const float* sn = p.sin_t + (long)pos * 32 + (d0 & 31);
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const float4 qb = *reinterpret_cast<const float4*>(qp + pd0 + 4 * i4);
-          const float4 ka = *reinterpret_cast<const float4*>(kq + d0 + 4 * i4);
-          const float4 kb = *reinterpret_cast<const float4*>(kq + pd0 + 4 * i4);
-          const float4 va = *reinterpret_cast<const float4*>(vq + d0 + 4 * i4);
-          const float4 c4 = *reinterpret_cast<const float4*>(ct + 4 * i4);
-          const float4 s4 = *reinterpret_cast<const float4*>(sn + 4 * i4);
-          const float xq[4] = {qa[i4].x, qa[i4].y, qa[i4].z, qa[i4].w}, yq[4] = {qb.x, qb.y, qb.z, qb.w};
-          const float xk[4] = {ka.x, ka.y, ka.z, ka.w}, yk[4] = {kb.x, kb.y, kb.z, kb.w};
-          const float xv[4] = {va.x, va.y, va.z, va.w};
-          const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = 4 * i4 + e;
-            q[i] = __fadd_rn(__fmul_rn(xq[e], cc[e]), __fmul_rn(sgn * yq[e], ss[e])) * p.scale;
-            float kr = __fadd_rn(__fmul_rn(xk[e], cc[e]), __fmul_rn(sgn * yk[e], ss[e]));
-            float vr = xv[e];
-            kn[i] = kv_round<T>(kr); vn[i] = kv_round<T>(vr);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          q[4 * i4] = qa[i4].x * p.scale; q[4 * i4 + 1] = qa[i4].y * p.scale; q[4 * i4 + 2] = qa[i4].z * p.scale; q[4 * i4 + 3] = qa[i4].w * p.scale;
-        }
-#pragma unroll
-        for (int i = 0; i < DPL; ++i) { kn[i] = 0.f; vn[i] = 0.f; }
-      }
-    }
-    // the item that owns the page of the new token appends it to the cache (the lanes that attend to it)
-    const int new_pg = pos >> 5, new_t = pos & 31;
-    if (p.fuse_rope && (new_pg % p.nsplit) == split && warp == (new_t >> 3) && grp == (new_t & 7)) {
-      T* kd = const_cast<T*>(base) + (long)pt[new_pg] * page_stride + (long)new_t * 64 + d0;
-      T* vd = kd + (long)H * slab_e;
-#pragma unroll
-      for (int i = 0; i < DPL; ++i) { kd[i] = (T)kn[i]; vd[i] = (T)vn[i]; }
+    for (int i4 = 0; i4 < 4; ++i4) {
+      const float4 t = *reinterpret_cast<const float4*>(qsl + d0 + 4 * i4);
+      q[4 * i4] = t.x; q[4 * i4 + 1] = t.y; q[4 * i4 + 2] = t.z; q[4 * i4 + 3] = t.w;
     }
     float m = -INFINITY, l = 0.f, o[DPL];
 #pragma unroll
@@ -659,21 +675,22 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
 #pragma unroll
       for (int j = 0; j < NPC; ++j) { kr[j] = kp[j]; vr[j] = vp[j]; }
       // Release the stage only once the shared-memory loads have RETURNED: the arrive takes a value derived from every
-      // load as an (unused) operand, so it cannot issue while one of them is still in flight -- otherwise the producer's
-      // next bulk copy may land in the stage under a pending LDS (seen with the fp32 cache: 8 conflicted LDS.128 per trip).
+      // load as an (unused) operand, so it cannot issue while one of them is still in flight; and order the generic-proxy
+      // reads against the async-proxy write of the producer's next bulk copy into the same bytes (A/B: CBX_PB_NOFENCE=1).
       uint32_t dep = 0;
 #pragma unroll
       for (int j = 0; j < NPC; ++j) dep ^= kr[j].x ^ vr[j].x;
+      if (!(p.dbg_early_release & 2)) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (p.dbg_early_release) mbar_arrive(&empty[s]);
+        if (p.dbg_early_release & 1) mbar_arrive(&empty[s]);
         else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])), "r"(dep) : "memory");
       }
 #pragma unroll
       for (int j = 0; j < NPC; ++j) { KvPiece<T>::decode(kr[j], kx + j * KvPiece<T>::N); KvPiece<T>::decode(vr[j], vx + j * KvPiece<T>::N); }
-      if (p.fuse_rope && tok == pos) {                    // taken from registers, its cache slot is being written now
+      if (p.fuse_rope && tok == pos) {                    // the step's own token: taken from the staged slot, its cache entry is being written now
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) { kx[j] = kn[j]; vx[j] = vn[j]; }
+        for (int j = 0; j < DPL; ++j) { kx[j] = qsl[64 + d0 + j]; vx[j] = qsl[128 + d0 + j]; }
       }
       float sc = 0.f;
       if (tok < S) {
@@ -693,6 +710,8 @@ __global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const Pa
         l = l * c + e; m = mn;
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&q_empty[li & 1]);         // this warp no longer reads the item's query slot
     // ---- merge the 32 token streams of this CTA: 8 lane groups per warp by shuffles, then the 4 warps through smem
 #pragma unroll
     for (int ofs = 4; ofs < 32; ofs <<= 1) {
@@ -791,7 +810,8 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
   p.n_live = opts ? opts->n_live : nullptr;
   p.out16 = opts ? opts->out16 : nullptr;
   static const bool early = getenv("CBX_PB_EARLY") != nullptr;
-  p.dbg_early_release = early ? 1 : 0;
+  static const bool nofence = getenv("CBX_PB_NOFENCE") != nullptr;
+  p.dbg_early_release = (early ? 1 : 0) | (nofence ? 2 : 0);
   CBX_REQUIRE(!p.out16 || (kv.page_tokens == PB_TOK && !(opts && opts->impl == 1)), "fp16 output needs the bulk-copy kernel");
   // default: the bulk-copy (TMA engine) kernel; CBX_PAGED=ldg keeps the round-1 __ldg kernel for A/B runs
   static const bool force_ldg = getenv("CBX_PAGED") && std::string(getenv("CBX_PAGED")) == "ldg";

@@ -704,8 +704,8 @@ attn_otm_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcDev p) {
   uint64_t* q_full = bars;                  // 1
   uint64_t* kv_full = bars + 1;             // [STAGES]
   uint64_t* kv_empty = kv_full + STAGES;    // [STAGES]
-  uint64_t* s_full = kv_empty + STAGES;     // [2]
-  uint64_t* p_full = s_full + 2;            // 1   (4 softmax warps: P_j written, O rescaled if it had to be)
+  uint64_t* s_full = kv_empty + STAGES;     // [3]
+  uint64_t* p_full = s_full + 3;            // 1   (4 softmax warps: P_j written, O rescaled if it had to be)
   uint64_t* pv_full = p_full + 1;           // 1   (PV_j accumulated)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 1);
 
@@ -713,7 +713,7 @@ attn_otm_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcDev p) {
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) mbar_init(&s_full[s], 1);
+    for (int s = 0; s < 3; ++s) mbar_init(&s_full[s], 1);
     mbar_init(p_full, 4); mbar_init(pv_full, 1);
     fence_mbar_init();
   }
@@ -723,7 +723,10 @@ attn_otm_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcDev p) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS0 = tmem_base, tS1 = tmem_base + 64, tO = tmem_base + 128;
+  // three S tiles: S_{j+2} is issued before the softmax of block j has finished (it used to be issued only then, and the
+  // softmax warps spent a fifth of their time waiting for the next tile: profiles/r2_ncu_attn_otm_prefetch.txt)
+  const uint32_t tO = tmem_base + 192;
+  auto tS = [&](int j) { return tmem_base + (uint32_t)((j % 3) * 64); };
 
   if (warp == 0) {
     // ===================== TMA producer ===============================================================
@@ -745,7 +748,7 @@ attn_otm_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcDev p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =================================================================
-    // Issue order S_0, S_1, PV_0, S_2, PV_1, ...: S_{j+2} overwrites the tile that held S_j / P_j, and it is issued after
+    // Issue order S_0, S_1, S_2, PV_0, S_3, PV_1, ...: S_{j+3} overwrites the tile that held S_j / P_j, and it is issued after
     // PV_j by this same thread (the tensor pipe executes in issue order), PV_j in turn after the softmax has read S_j.
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(AT_BM, AT_BN);                   // A, B K-major
@@ -757,20 +760,21 @@ attn_otm_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcDev p) {
         mbar_wait(&kv_full[s], (j / STAGES) & 1);
         tcgen05_fence_after();
         const uint32_t k_a = smem_u32(sKV + s * KV_STAGE);
-        const uint32_t d = (j & 1) ? tS1 : tS0;
+        const uint32_t d = tS(j);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
           umma_bf16(d, umma_desc_sw128(q_a + k4 * 32), umma_desc_sw128(k_a + k4 * 32), idesc_s, k4 != 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
+        umma_commit(&s_full[j % 3]);
       };
       issue_s(0);
+      if (nblk > 1) issue_s(1);
       for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) issue_s(j + 1);            // S of the next block overlaps the softmax of this one
+        if (j + 2 < nblk) issue_s(j + 2);            // two S tiles ahead of the softmax
         const int s = j % STAGES;
         mbar_wait(p_full, j & 1);                    // P_j is in TMEM, O carries the right scale
         tcgen05_fence_after();
         const uint32_t v_a = smem_u32(sKV + s * KV_STAGE + AT_TILE);
-        const uint32_t tP = (j & 1) ? tS1 : tS0;
+        const uint32_t tP = tS(j);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)               // 16 keys per step: 8 TMEM columns of P, 2048 B along V rows
           umma_f16_ts(tO, tP + k4 * 8, umma_desc_sw128_mn(v_a + k4 * 2048), idesc_pv, (j | k4) != 0 ? 1u : 0u);
@@ -787,10 +791,10 @@ attn_otm_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcDev p) {
     const uint64_t sc2 = pk2(p.scale_log2e, p.scale_log2e);
     const float thr = AT_RESCALE_LOG2 / p.scale_log2e;           // raw-score units
     for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[j % 3], (j / 3) & 1);
       tcgen05_fence_after();
       uint32_t r[64];
-      const uint32_t ts = ((j & 1) ? tS1 : tS0) + lane_off;
+      const uint32_t ts = tS(j) + lane_off;
       tmem_ld_32x32(ts, *reinterpret_cast<uint32_t(*)[32]>(r));
       tmem_ld_32x32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(r + 32));
       tmem_ld_wait();

@@ -1556,7 +1556,7 @@ void gemm(Ctx& ctx, GemmDev g, const Weight& W) {
       const bool split_ok = gs.splitk == 1 || (gs.C && !gs.bias && !gs.res && !gs.Chi && !gs.swiglu && gs.act == ACT_NONE && gs.alpha == 1.0f &&
                                                gs.out_scale == 1.0f && gs.splitk <= gs.Kpad / TC_BK);
       if (gs.epi_direct && split_ok) {
-        const int bn = (g.tile_bn == 64 || g.tile_bn == 256) && g.Npad % g.tile_bn == 0 ? g.tile_bn : (g.Npad % 128 == 0 ? 128 : 64);
+        const int bn = (g.tile_bn == 64 || g.tile_bn == 128 || g.tile_bn == 256) && g.Npad % g.tile_bn == 0 ? g.tile_bn : (g.Npad % 128 == 0 ? 128 : 64);
         if (bn == 64) launch_stream<64>(ctx, gs, W); else if (bn == 128) launch_stream<128>(ctx, gs, W); else launch_stream<256>(ctx, gs, W);
         CBX_CHECK(cudaGetLastError());
         return;

@@ -327,8 +327,8 @@ void t3_prefill(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int n_tok, cons
 // flags -- live in device memory), so a step is captured once into a CUDA graph per (state, capacity) and replayed.
 struct DecodeTiles { int qkv_bn, qkv_dual, o_bn, o_split, gu_bn, gu_dual, down_bn, down_split, head_bn; };
 
-static DecodeTiles decode_tiles(int S) {
-  // measured on the B200 with tools/gemm_decode_sweep.py (profiles/r2_gemm_decode_sweep.txt); env overrides for sweeps
+static DecodeTiles decode_tiles(int S, bool f16) {
+  // one-tile-per-CTA kernel (fp32-faithful planes): tuned by sweeps in round 2's first sessions; env overrides for sweeps
   DecodeTiles t;
   const int mt = (S + 127) / 128;
   t.qkv_bn = mt >= 3 ? 64 : 64;  t.qkv_dual = mt >= 4 ? 1 : 0;
@@ -336,6 +336,11 @@ static DecodeTiles decode_tiles(int S) {
   t.gu_bn = mt >= 2 ? 128 : 64;  t.gu_dual = mt >= 3 ? 1 : 0;
   t.down_bn = 64; t.down_split = mt >= 3 ? 4 : 8;
   t.head_bn = 0;
+  if (f16) {
+    // persistent streaming kernel (fp16 plane): tools/decode_gemm_bench.py at 512 rows (profiles/r2_decode_gemm_bench.txt):
+    // qkv 12.4 us at BN 128 (16.5 at 64), gate/up 18.5 at BN 256 (20.5 at 128), down 13.9 at BN 128 split 4 (17.7 at BN 64)
+    t.qkv_bn = 128; t.gu_bn = mt >= 2 ? 256 : 128; t.down_bn = 128; t.down_split = mt >= 2 ? 4 : 8; t.o_split = mt >= 3 ? 2 : 4;
+  }
   static const char* ov = getenv("CBX_DECODE_TILES");     // "qkv_bn,qkv_dual,o_bn,o_split,gu_bn,gu_dual,down_bn,down_split"
   if (ov) {
     int v[8];
@@ -351,7 +356,7 @@ static void decode_step(cbx_handle* h, Ctx& ctx, const cbx_t3_state& st, int cap
   const int rows_per = st.cfg ? 2 : 1;
   const int S = cap * rows_per;
   const size_t mark = ctx.ws.mark();
-  const DecodeTiles tl = decode_tiles(S);
+  const DecodeTiles tl = decode_tiles(S, S > 8 && ctx.gemm_impl == 0 && st.act_fp16 != 0);
   const bool pdl_saved = ctx.pdl;
   ctx.pdl = h->decode_pdl != 0;     // every kernel of the step waits (griddepcontrol.wait) before its first global access
   const int max_split = 8;

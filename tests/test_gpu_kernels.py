@@ -325,6 +325,9 @@ def test_gemm_splitk_partials_reduce_deterministically(M, K, N, splitk, bn):
     (20000, 256, 1536, 0, 1, 0),     # many row tiles per CTA (accumulator ring wraps several times)
     (640, 512, 256, 0, 0, 1),        # fewer row tiles than CTA groups
     (4096, 1024, 256, 0, 0, 1),      # ff2 (K = 1024): the one-tile-per-CTA kernel with the same operand format
+    (512, 1024, 3072, 0, 0, 0),      # decode qkv at 512 rows: persistent streaming kernel (M <= 1024, K >= 512)
+    (300, 4096, 1024, 0, 0, 1),      # decode down projection, ragged rows, residual
+    (64, 1024, 1024, 2, 1, 0),       # half a row tile, GELU, fp16 plane out (streaming kernel)
 ])
 def test_fp16_plane_gemm_weight_resident(M, K, N, act, out_half, use_res):
     """fp16-plane operand format of the CFM block projections (A fp16 x fp16 copy of W, fp32 accumulate) against fp64 on
@@ -350,4 +353,5 @@ def test_fp16_plane_gemm_weight_resident(M, K, N, act, out_half, use_res):
     if out_half:
         ref = ref.half().double()
     err = relerr(Cc, ref)
-    assert torch.isfinite(Cc).all() and err < (1e-3 if out_half else 2e-6), f"rel err {err}"
+    tol = 1e-3 if out_half else (2e-6 if K <= 1024 else 6e-6)      # fp32 accumulation error grows with the reduction length
+    assert torch.isfinite(Cc).all() and err < tol, f"rel err {err}"

@@ -22,4 +22,4 @@ for name, N, K, swiglu in shapes:
         eng.h.call("cbx_bench_gemm_f16", M, N, K, splitk, bn, dual, swiglu, nw, reps, C.byref(us), _ptr(ws), ws.numel(),
                    C.c_void_p(torch.cuda.current_stream().cuda_stream))
         print(f"{name:8s} M={M} N={N} K={K} splitk={splitk} bn={bn} dual={dual}: {us.value:7.2f} us  (floor {floor_us:.2f} us, "
-              f"{N*K*2/us.value/1e6:.0f} GB/s weights, {2.0*M*N*K/us.value/1e6:.0f} TFLOP/s)", flush=True)
+              f"{N*K*2/us.value/1e3:.0f} GB/s weights, {2.0*M*N*K/us.value/1e6:.0f} TFLOP/s)", flush=True)

@@ -17,5 +17,8 @@ for cls in os.environ.get("FCLS", "none").split(","):
     mels = eng.flow_mel(toks, cg, n_timesteps=int(os.environ.get("NT", 2)))
     torch.cuda.synchronize(); dt = time.time() - t0
     ms, n, work = eng.h.timer_read()
+    if cls == "all":
+        print("  per class: " + ", ".join(f"{c} {r['ms']:.1f} ms / {r['n']}" for c, r in ((c, eng.h.timer_read_class(c)) for c in
+              ("gemm_tc", "wres", "stream", "attn_tc", "flash")) if r["n"]), flush=True)
     print(f"class={cls} wall={dt*1e3:.1f}ms kernel_ms={ms:.1f} launches={n} tflops={work/1e9/max(ms,1e-9):.1f} "
           f"frames={sum(2 * (250 + t.numel()) for t in toks)} total_launches={eng.h.launch_count()}", flush=True)
