@@ -493,7 +493,7 @@ def run_engine(args, rank, world, local_rank):
               "K = 256: 95 FLOP/B, below the ridge (222 FLOP/B): HBM-bound by its activations")
         entry("stream", "gemm_stream_kernel", "persistent GEMM of the T3 decode-step projections (weights streamed once per step)", "hbm")
         entry("gemv", "gemv_kernel", "weight-streaming GEMV (<= 8 rows)", "hbm")
-        entry("attn_tc", "attn_otm2_kernel", "tcgen05 flash attention of the CFM estimator blocks (fp16 operands, P and O in TMEM)", "tensor",
+        entry("attn_tc", "attn_otm_kernel", "tcgen05 flash attention of the CFM estimator blocks (fp16 operands, P and O in TMEM)", "tensor",
               "algorithmic flops = 4*64*heads*sum(T^2); head dim 64: 8192 ex2 per 128x64 block = 512 MUFU clocks against 256 MMA clocks -> <= ~50 % of the tensor peak")
         entry("flash", "flash_attn_kernel", "mma.sync flash attention (conformer encoder with rel-pos bias, T3 prefill)", "tensor", "legacy path; time share only")
         entry("paged", "paged_bulk_kernel", "T3 decode attention over the paged KV cache (bulk-copy staged, fused RoPE + append)", "hbm",

@@ -496,16 +496,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                : "memory");
 }
 
-template <typename T> struct BulkCfg;
-template <> struct BulkCfg<__nv_bfloat16> { static constexpr int NST = 8; };
-template <> struct BulkCfg<float> { static constexpr int NST = 4; };
-template <> struct BulkCfg<__nv_fp8_e4m3> { static constexpr int NST = 16; };
+// stages per CTA: OCC = 3 -> 64 KB of K/V in flight per CTA (8 bf16 stages), OCC = 4 -> 48 KB (6 bf16 stages): the same ~200 KB per SM,
+// spread over 12 or 16 consumer warps
+template <typename T, int OCC> struct BulkCfg;
+template <int OCC> struct BulkCfg<__nv_bfloat16, OCC> { static constexpr int NST = OCC == 4 ? 6 : 8; };
+template <int OCC> struct BulkCfg<float, OCC> { static constexpr int NST = OCC == 4 ? 3 : 4; };
+template <int OCC> struct BulkCfg<__nv_fp8_e4m3, OCC> { static constexpr int NST = OCC == 4 ? 12 : 16; };
 constexpr int PB_TOK = 32;                    // tokens per page (required by this kernel)
 constexpr int PB_THREADS = 160;               // 4 consumer warps + 1 producer warp
-constexpr int PB_OCC = 3;                     // persistent CTAs per SM
+constexpr int PB_OCC = 3;                     // persistent CTAs per SM (default; CBX_PB_OCC=4 selects the 4-CTA instantiation)
 
 // shared memory: [NST stages of (K slab | V slab)] [512 B barriers] [merge buffer 1152 B] [2 x (q | k_new | v_new) 768 B]
-template <typename T> constexpr int pb_smem_bytes() { return BulkCfg<T>::NST * 2 * PB_TOK * 64 * (int)sizeof(T) + 512 + 4 * 4 * 18 * 4 + 2 * 192 * 4; }
+template <typename T, int OCC = PB_OCC> constexpr int pb_smem_bytes() { return BulkCfg<T, OCC>::NST * 2 * PB_TOK * 64 * (int)sizeof(T) + 512 + 4 * 4 * 18 * 4 + 2 * 192 * 4; }
 
 // Persistent: gridDim.x CTAs walk the (slot, head, split) work items with a fixed stride.  The producer warp runs ahead
 // of the consumers ACROSS items (the stage ring and its mbarrier phases never reset), so while the consumers merge one
@@ -514,9 +516,9 @@ template <typename T> constexpr int pb_smem_bytes() { return BulkCfg<T>::NST * 2
 // rotate them, append the new k / v to the cache and leave q (scaled), k_new, v_new in a double-buffered shared-memory
 // slot.  The consumers used to do this themselves at the top of every item behind three dependent global loads
 // (slot -> row -> position -> q, ~1.5 us) -- a fifth of an average item.
-template <typename T>
-__global__ void __launch_bounds__(PB_THREADS, PB_OCC) paged_bulk_kernel(const PagedDev p, const int n_items) {
-  constexpr int NST = BulkCfg<T>::NST;
+template <typename T, int OCC = PB_OCC>
+__global__ void __launch_bounds__(PB_THREADS, OCC) paged_bulk_kernel(const PagedDev p, const int n_items) {
+  constexpr int NST = BulkCfg<T, OCC>::NST;
   constexpr int SLAB = PB_TOK * 64 * (int)sizeof(T);      // one (page, head) slab of K or of V
   constexpr int STAGE = 2 * SLAB;
   constexpr int DPL = 16, NPC = DPL / KvPiece<T>::N;      // dims per lane, 16-byte pieces per lane
@@ -791,6 +793,7 @@ void paged_attention_init() {     // per device, before any stream capture
   CBX_CHECK(cudaFuncSetAttribute(paged_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes<__nv_bfloat16>()));
   CBX_CHECK(cudaFuncSetAttribute(paged_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes<float>()));
   CBX_CHECK(cudaFuncSetAttribute(paged_bulk_kernel<__nv_fp8_e4m3>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes<__nv_fp8_e4m3>()));
+  CBX_CHECK(cudaFuncSetAttribute(paged_bulk_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem_bytes<__nv_bfloat16, 4>()));
 }
 
 void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV& kv, int layer, const int* slot_row,
@@ -825,8 +828,13 @@ void paged_decode_attention(Ctx& ctx, const float* qkv, int ldqkv, const PagedKV
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; CBX_CHECK(cudaGetDevice(&dev)); CBX_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
     const int n_items = n_slots * kv.n_heads * nsplit;
+    // bf16 cache: 4 CTAs per SM x 6 stages (4.77 TB/s against 4.49 with 3 x 8 at B = 256, 400 steps; session 20); CBX_PB_OCC=3 for A/B
+    static const int occ = getenv("CBX_PB_OCC") ? atoi(getenv("CBX_PB_OCC")) : 4;
     const int g = n_items < PB_OCC * n_sm ? n_items : PB_OCC * n_sm;
-    if (kv.kv_fp32 == 1) launch_kernel(ctx, paged_bulk_kernel<float>, dim3(g), dim3(PB_THREADS), (size_t)pb_smem_bytes<float>(), p, n_items);
+    if (kv.kv_fp32 == 0 && occ == 4) {
+      const int g4 = n_items < 4 * n_sm ? n_items : 4 * n_sm;
+      launch_kernel(ctx, paged_bulk_kernel<__nv_bfloat16, 4>, dim3(g4), dim3(PB_THREADS), (size_t)pb_smem_bytes<__nv_bfloat16, 4>(), p, n_items);
+    } else if (kv.kv_fp32 == 1) launch_kernel(ctx, paged_bulk_kernel<float>, dim3(g), dim3(PB_THREADS), (size_t)pb_smem_bytes<float>(), p, n_items);
     else if (kv.kv_fp32 == 2) launch_kernel(ctx, paged_bulk_kernel<__nv_fp8_e4m3>, dim3(g), dim3(PB_THREADS), (size_t)pb_smem_bytes<__nv_fp8_e4m3>(), p, n_items);
     else launch_kernel(ctx, paged_bulk_kernel<__nv_bfloat16>, dim3(g), dim3(PB_THREADS), (size_t)pb_smem_bytes<__nv_bfloat16>(), p, n_items);
   } else {

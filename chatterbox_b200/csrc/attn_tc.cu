@@ -1132,6 +1132,253 @@ attn_otm2_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcDev p) {
 }
 
 
+
+// ================================================================================================
+// attn_pp_kernel: TWO query tiles per CTA with their softmax warp groups in enforced anti-phase ("ping-pong", the structure
+// FlashAttention-4 uses).  Why: with one tile per CTA and two CTAs per SM (attn_otm_kernel) the two CTAs run in phase -- both
+// read their S tile through the 64 B/clk tcgen05.ld port, then both queue on the MUFU pipe -- and a key block costs the SUM
+// of the two floors (measured 1040 clocks) instead of their maximum (512).  Here one CTA owns 256 query rows of a (sequence,
+// head): tile A and tile B share every K/V stage (half the TMA traffic), each has its own S ring and O accumulator in TMEM
+// (2 x (128 + 64) = 384 columns), and a pair of mbarriers hands the TMEM read port back and forth: group B may load S_B(j) only
+// after group A has S_A(j) in registers, group A may load S_A(j+1) only after group B has S_B(j) -- so one group's
+// exponentials always run under the other group's tcgen05.ld.
+//   warp 0: TMA producer   warp 1: MMA issuer (+ TMEM owner)   warps 2-5: softmax of tile A   warps 6-9: softmax of tile B
+// ================================================================================================
+constexpr int APP_STAGES = 8;
+constexpr int APP_SMEM = 2 * (2 * AT_TILE) + APP_STAGES * (2 * AT_TILE) + 512 + 1024;
+
+template <int HANDOFF>
+__global__ void __launch_bounds__(320, 1)
+attn_pp_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcDev p) {
+  constexpr int STAGES = APP_STAGES;
+  constexpr int Q_TILE = 2 * AT_TILE, KV_STAGE = 2 * AT_TILE;
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int qlen = p.q_len[seq], kvlen = p.kv_len[seq];
+  const int q0 = blockIdx.x * (2 * AT_BM);
+  if (q0 >= qlen) return;
+  const bool b_on = q0 + AT_BM < qlen;                  // the second tile holds real rows
+  const int qrow0 = p.q_start[seq] + q0, krow0 = p.kv_start[seq];
+  const int nblk = (kvlen + AT_BN - 1) / AT_BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                                   // [tile][128 rows x 128 B]
+  uint8_t* sKV = sQ + 2 * Q_TILE;                       // stages of [K 64 rows][V 64 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + STAGES * KV_STAGE);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* kv_full = bars + 1;             // [STAGES]
+  uint64_t* kv_empty = kv_full + STAGES;    // [STAGES]
+  uint64_t* s_full = kv_empty + STAGES;     // [tile][2]
+  uint64_t* p_full = s_full + 4;            // [tile]
+  uint64_t* pv_full = p_full + 2;           // [tile]
+  uint64_t* ld_done = pv_full + 2;          // [tile]  the group has its S tile of the current block in registers (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 4; ++s) mbar_init(&s_full[s], 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 4); mbar_init(&pv_full[t], 1); mbar_init(&ld_done[t], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tm);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  auto tS = [&](int t, int j) { return tmem_base + (uint32_t)(t * 192 + (j & 1) * 64); };
+  auto tO = [&](int t) { return tmem_base + (uint32_t)(t * 192 + 128); };
+
+  if (warp == 0) {
+    // ===================== TMA producer ===============================================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * Q_TILE);
+      const int qc = p.q_col + head * 64;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tma_load_2d(sQ + i * AT_TILE, &tm, q_full, qc, qrow0 + 64 * i);      // rows past the buffer read as zeros
+      const int kc = p.k_col + head * 64, vc = p.v_col + head * 64;
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % STAGES;
+        mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
+        uint8_t* st = sKV + s * KV_STAGE;
+        mbar_arrive_expect_tx(&kv_full[s], KV_STAGE);
+        const int r = krow0 + j * AT_BN;
+        tma_load_2d(st, &tm, &kv_full[s], kc, r);
+        tma_load_2d(st + AT_TILE, &tm, &kv_full[s], vc, r);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =================================================================
+    // Issue order per key block: S_A(j+1), S_B(j+1), PV_A(j), PV_B(j).  S_t(j+1) overwrites the tile that held S_t(j-1) / P_t(j-1),
+    // after PV_t(j-1) in issue order (the tensor pipe executes in issue order).
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(AT_BM, AT_BN);                   // A, B K-major
+      constexpr uint32_t idesc_pv = umma_idesc_f16(AT_BM, 64) | (1u << 16);        // B (= V) MN-major
+      const int nt = b_on ? 2 : 1;
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int j) {
+        const int s = j % STAGES;
+        mbar_wait(&kv_full[s], (j / STAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t k_a = smem_u32(sKV + s * KV_STAGE);
+        for (int t = 0; t < nt; ++t) {
+          const uint32_t q_a = smem_u32(sQ + t * Q_TILE);
+          const uint32_t d = tS(t, j);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_bf16(d, umma_desc_sw128(q_a + k4 * 32), umma_desc_sw128(k_a + k4 * 32), idesc_s, k4 != 0 ? 1u : 0u);
+          umma_commit(&s_full[t * 2 + (j & 1)]);
+        }
+      };
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) issue_s(j + 1);
+        const int s = j % STAGES;
+        const uint32_t v_a = smem_u32(sKV + s * KV_STAGE + AT_TILE);
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(&p_full[t], j & 1);              // P_t(j) is in TMEM, O_t carries the right scale
+          tcgen05_fence_after();
+          const uint32_t tP = tS(t, j);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_f16_ts(tO(t), tP + k4 * 8, umma_desc_sw128_mn(v_a + k4 * 2048), idesc_pv, (j | k4) != 0 ? 1u : 0u);
+          umma_commit(&pv_full[t]);
+        }
+        umma_commit(&kv_empty[s]);                   // K/V stage free (both tiles' S and PV products of block j have read it)
+      }
+    }
+  } else {
+    // ===================== softmax: group A (warps 2-5) / group B (warps 6-9), one query row per thread =================
+    const int t = (warp - 2) >> 2;                    // tile of this group
+    if (t == 1 && !b_on) { /* nothing to do: fall through to the teardown */ }
+    else {
+      const int quarter = warp & 3;                   // TMEM lane quarter of this warp (hardware: warp id % 4)
+      const int row = quarter * 32 + lane;
+      const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+      const bool handoff = HANDOFF && b_on;
+      float m_ref = -INFINITY, l = 0.f;
+      const uint64_t sc2 = pk2(p.scale_log2e, p.scale_log2e);
+      const float thr = AT_RESCALE_LOG2 / p.scale_log2e;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&s_full[t * 2 + (j & 1)], (j >> 1) & 1);
+        // the TMEM read port goes A(0) B(0) A(1) B(1) ...: wait for the other group's load of the previous slot in that order
+        if (handoff) {
+          if (t == 0) { if (j > 0) mbar_wait(&ld_done[1], (j - 1) & 1); }
+          else mbar_wait(&ld_done[0], j & 1);
+        }
+        tcgen05_fence_after();
+        uint32_t r[64];
+        const uint32_t ts = tS(t, j) + lane_off;
+        tmem_ld_32x32(ts, *reinterpret_cast<uint32_t(*)[32]>(r));
+        tmem_ld_32x32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(r + 32));
+        tmem_ld_wait();
+        if (handoff) { __syncwarp(); if (lane == 0) mbar_arrive(&ld_done[t]); }
+        if (j * AT_BN + AT_BN > kvlen) {              // only the last key block needs the length mask
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (j * AT_BN + i >= kvlen) r[i] = 0xff800000u;
+        }
+        float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          mxa = max3(mxa, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          mxb = max3(mxb, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        }
+        const float mx = fmaxf(mxa, mxb);
+        const bool move = mx > m_ref + thr;           // lazy rescale (see attn_otm_kernel)
+        float c = 1.f;
+        if (move) {
+          c = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - mx) * p.scale_log2e);
+          m_ref = mx;
+          l *= c;
+        }
+        bool synced = false;
+        if (j > 0 && __any_sync(0xffffffffu, move)) {
+          mbar_wait(&pv_full[t], (j - 1) & 1);
+          synced = true;
+          tcgen05_fence_after();
+#pragma unroll
+          for (int cc = 0; cc < 64; cc += 32) {
+            uint32_t ov[32];
+            tmem_ld_32x32(tO(t) + lane_off + cc, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * c);
+            tmem_st_32x32_x32(tO(t) + lane_off + cc, ov);
+          }
+        }
+        const float mrs = m_ref * p.scale_log2e;
+        const uint64_t nm2 = pk2(-mrs, -mrs);
+        uint64_t sa = 0ull, sb = 0ull;
+        uint32_t ph[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          float x0, x1, x2, x3;
+          upk2(fma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, nm2), x0, x1);
+          upk2(fma2(pk2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), sc2, nm2), x2, x3);
+          x0 = fast_exp2(x0); x1 = fast_exp2(x1); x2 = fast_exp2(x2); x3 = fast_exp2(x3);
+          add2_acc(sa, pk2(x0, x1));
+          add2_acc(sb, pk2(x2, x3));
+          ph[i / 2] = pack_half2(x0, x1);
+          ph[i / 2 + 1] = pack_half2(x2, x3);
+        }
+        {
+          float s0, s1, s2, s3;
+          upk2(sa, s0, s1); upk2(sb, s2, s3);
+          l += (s0 + s1) + (s2 + s3);
+        }
+        tmem_st_32x32_x32(ts, ph);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        if (j > 0 && !synced) mbar_wait(&pv_full[t], (j - 1) & 1);     // every warp observes every phase of pv_full
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      // epilogue: the accumulated O, normalised
+      mbar_wait(&pv_full[t], (nblk - 1) & 1);
+      tcgen05_fence_after();
+      const int qr = q0 + t * AT_BM + row;
+      const long off = (long)(qrow0 + t * AT_BM + row) * p.ldo + head * 64;
+      const bool live = qr < qlen;
+      const float inv = (live && l > 0.f) ? 1.f / l : 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 32) {
+        uint32_t ov[32];
+        tmem_ld_32x32(tO(t) + lane_off + cc, ov);
+        tmem_ld_wait();
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = live ? __uint_as_float(ov[i]) * inv : 0.f;
+        if (p.O16) {
+          uint4* d16 = reinterpret_cast<uint4*>(p.O16 + off + cc);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8)
+            d16[i / 8] = make_uint4(pack_half2(o[i], o[i + 1]), pack_half2(o[i + 2], o[i + 3]), pack_half2(o[i + 4], o[i + 5]), pack_half2(o[i + 6], o[i + 7]));
+        } else if (p.Ohi) {
+          uint4* dh = reinterpret_cast<uint4*>(p.Ohi + off + cc);
+          uint4* dl = reinterpret_cast<uint4*>(p.Olo + off + cc);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 h, lw;
+            split_pair_at(o[i], o[i + 1], h.x, lw.x); split_pair_at(o[i + 2], o[i + 3], h.y, lw.y);
+            split_pair_at(o[i + 4], o[i + 5], h.z, lw.z); split_pair_at(o[i + 6], o[i + 7], h.w, lw.w);
+            dh[i / 8] = h; dl[i / 8] = lw;
+          }
+        } else if (live) {
+          float* dst = p.O + off + cc;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // ---- host --------------------------------------------------------------------------------------------
 
 template <int SPLIT, int F16, int OCC> static void at_attr() {
@@ -1139,6 +1386,8 @@ template <int SPLIT, int F16, int OCC> static void at_attr() {
 }
 void attention_tc_init() {      // per device
   at_attr<1, 0, 1>(); at_attr<2, 0, 1>(); at_attr<1, 1, 1>(); at_attr<2, 1, 1>(); at_attr<1, 1, 2>(); at_attr<2, 1, 2>();
+  CBX_CHECK(cudaFuncSetAttribute(attn_pp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, APP_SMEM));
+  CBX_CHECK(cudaFuncSetAttribute(attn_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, APP_SMEM));
   CBX_CHECK(cudaFuncSetAttribute(attn_otm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, af_smem(1, 1)));
   CBX_CHECK(cudaFuncSetAttribute(attn_otm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, af_smem(2, 1)));
   CBX_CHECK(cudaFuncSetAttribute(attn_otm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, af_smem(1, 1)));
@@ -1170,7 +1419,11 @@ void attention_tc(Ctx& ctx, const AttnTcArgs& a) {
   // 3 (default): attn_otm_kernel -- P and O both stay in TMEM (lazy rescale)
   // 4: attn_otm2_kernel -- the same with two softmax threads per query row (measured 5 % slower than 3, session 15)
   static const int f16_kernel = getenv("CBX_ATTN_F16") ? atoi(getenv("CBX_ATTN_F16")) : 3;
-  if (a.f16 && f16_kernel >= 4 && variant == 1) {
+  if (a.f16 && f16_kernel >= 5 && variant == 1) {        // 5: attn_pp_kernel (two query tiles per CTA, anti-phase hand-off); 6: without the hand-off
+    dim3 grid2((a.max_q_len + 2 * AT_BM - 1) / (2 * AT_BM), a.n_heads, a.n_seq);
+    if (f16_kernel == 5) attn_pp_kernel<1><<<grid2, 320, APP_SMEM, ctx.stream>>>(*a.tm_hi, p);
+    else attn_pp_kernel<0><<<grid2, 320, APP_SMEM, ctx.stream>>>(*a.tm_hi, p);
+  } else if (a.f16 && f16_kernel >= 4 && variant == 1) {
     if (occ == 2) attn_otm2_kernel<2><<<grid, 320, af_smem(2, 1), ctx.stream>>>(*a.tm_hi, p);
     else attn_otm2_kernel<1><<<grid, 320, af_smem(1, 1), ctx.stream>>>(*a.tm_hi, p);
   } else if (a.f16 && f16_kernel >= 3 && variant == 1) {

@@ -339,7 +339,8 @@ static DecodeTiles decode_tiles(int S, bool f16) {
   if (f16) {
     // persistent streaming kernel (fp16 plane): tools/decode_gemm_bench.py at 512 rows (profiles/r2_decode_gemm_bench.txt):
     // qkv 12.4 us at BN 128 (16.5 at 64), gate/up 18.5 at BN 256 (20.5 at 128), down 13.9 at BN 128 split 4 (17.7 at BN 64)
-    t.qkv_bn = 128; t.gu_bn = mt >= 2 ? 256 : 128; t.down_bn = 128; t.down_split = mt >= 2 ? 4 : 8; t.o_split = mt >= 3 ? 2 : 4;
+    // and at 128 / 256 / 384 rows (session 22): gate/up 14.4 us at BN 128 up to 256 rows (18.5 at 256), down 10.6 us with split 8 (12.5 with 4)
+    t.qkv_bn = 128; t.gu_bn = mt >= 3 ? 256 : 128; t.down_bn = 128; t.down_split = mt >= 3 ? 4 : 8; t.o_split = mt >= 3 ? 2 : 4;
   }
   static const char* ov = getenv("CBX_DECODE_TILES");     // "qkv_bn,qkv_dual,o_bn,o_split,gu_bn,gu_dual,down_bn,down_split"
   if (ov) {

@@ -11,8 +11,8 @@ M = int(os.environ.get("DM", 512))
 reps = int(os.environ.get("DREPS", 4))
 ws = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 shapes = [("qkv", 3072, 1024, 0), ("o", 1024, 1024, 0), ("gate_up", 8192, 1024, 1), ("down", 1024, 4096, 0), ("head", 8256, 1024, 0)]
-variants = {"qkv": [(1, 64, 1), (1, 128, 1), (1, 128, 0), (1, 256, 0)], "o": [(2, 64, 0), (4, 64, 0), (1, 64, 0), (2, 128, 0)],
-            "gate_up": [(1, 128, 1), (1, 256, 0), (1, 64, 1)], "down": [(4, 64, 0), (8, 64, 0), (2, 64, 0), (4, 128, 0)],
+variants = {"qkv": [(1, 64, 1), (1, 128, 1), (1, 256, 0)], "o": [(2, 64, 0), (4, 64, 0), (8, 64, 0), (2, 128, 0), (4, 128, 0)],
+            "gate_up": [(1, 128, 1), (1, 256, 0), (1, 64, 1)], "down": [(4, 64, 0), (8, 64, 0), (2, 64, 0), (4, 128, 0), (8, 128, 0)],
             "head": [(1, 0, 0), (1, 64, 0)]}
 for name, N, K, swiglu in shapes:
     nw = max(2, min(48, int(300e6 / (N * K * 2))))
