@@ -520,7 +520,7 @@ def run_engine(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 weights/KV, fp32 residual stream + accumulate; T3/HiFT activations bf16 hi+lo planes, CFM block operands fp16",
+        "dtype": "bf16 weights/KV, fp32 residual stream + accumulate; T3 decode and CFM block operands one fp16 plane, CFM convs / encoder / HiFT operands bf16 hi+lo planes",
         "data": "synthetic",
         "rtf": (ms / 1000.0) / audio_total * world,
         "config": {"workload": WORKLOAD,
