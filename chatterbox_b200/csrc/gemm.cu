@@ -688,13 +688,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
 // Why: with K = 256 a 128 x 128 output tile moves 128 KB of operands through L2 -> shared memory for 1024 cycles of MMA;
 // at ~42 B/clk per SM of L2 read bandwidth that alone caps the one-tile-per-CTA kernel at a third of the tensor peak, and
 // the TMEM allocation, barrier set-up and epilogue of every tile sit on top.  Here a CTA loads its BN x K weight panel ONCE
-// (128 KB), then walks the row tiles: A streams through a 4-stage ring (16 KB per K block), the accumulator is double
+// (128 KB), then walks the row tiles: A streams through a 4-stage ring (16 KB per K block; 231.7 KB of shared memory in all), the accumulator is double
 // buffered in TMEM (2 x BN columns) so the epilogue of tile i runs under the MMAs of tile i+1, and the epilogue stores each
 // thread's 32-column row segment straight from registers (whole 32-byte sectors, no shared-memory transpose).
 //   warp 0: TMA producer   warp 1: MMA issuer (+ TMEM owner)   warps 2-9: epilogue (lane quarter = warp % 4, column half = (warp-2)/4)
 // Algorithmic HBM bytes per launch: M*K*2 (A) + N*K*2 (W, once) + outputs (+ residual).
 // ================================================================================================
-constexpr int WR_THREADS = 320, WR_STAGES = 3, WR_W_BYTES = 131072, WR_A_STAGE = 16384;
+constexpr int WR_THREADS = 320, WR_STAGES = 4, WR_W_BYTES = 131072, WR_A_STAGE = 16384;
 constexpr int WR_STG = 8 * 4096;        // per epilogue warp: one 32-row x 128-byte staging tile of the TMA-store epilogue
 constexpr int WR_SMEM = WR_W_BYTES + WR_STAGES * WR_A_STAGE + WR_STG + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
 
